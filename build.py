@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""Build libhpt_b200.so (CUDA kernels + C ABI) and the oracle/baseline helpers, in-tree.
+
+    python build.py            # incremental (ninja)
+    python build.py --clean
+
+Every .cu is compiled for sm_100a only (`-gencode arch=compute_100a,code=sm_100a -lineinfo`).
+The elementwise kernels are instantiated per (op, lhs dtype) translation unit from three template
+sources with -D flags, so the ~100 units compile in parallel.  Outputs:
+    hpt_b200/lib/libhpt_b200.so     the product
+    oracle/_build/liboracle_cpu.so  C++/OpenMP restatement of Hpt's CPU path (test oracle + CPU baseline)
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(ROOT, "hpt_b200", "csrc")
+BUILD = os.path.join(ROOT, "build")
+LIBDIR = os.path.join(ROOT, "hpt_b200", "lib")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+DTYPES = [("b8", "bool"), ("int8_t", "i8"), ("int16_t", "i16"), ("int32_t", "i32"), ("int64_t", "i64"),
+          ("uint8_t", "u8"), ("uint16_t", "u16"), ("uint32_t", "u32"), ("uint64_t", "u64"),
+          ("f16", "f16"), ("bf16", "bf16"), ("float", "f32"), ("double", "f64")]
+BINARY_OPS = [("OpAdd", "add", 0, 1), ("OpSub", "sub", 0, 0), ("OpMul", "mul", 0, 1), ("OpRem", "rem", 0, 0),
+              ("OpDiv", "div", 1, 0), ("OpMax", "maximum", 0, 1), ("OpMin", "minimum", 0, 1)]
+UNARY_OPS = ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh",
+             "exp", "exp2", "exp10", "ln", "log2", "log10", "sqrt", "cbrt", "recip", "erf", "sigmoid", "gelu",
+             "selu", "elu", "celu", "mish", "softplus", "softsign", "hard_sigmoid", "hard_swish"]
+REDUCE_OPS = ["sum", "mean", "max", "min", "argmax", "argmin", "logsumexp", "sum_square", "prod"]
+
+NVCC_FLAGS = ("-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr "
+              "-Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xcudafe --diag_suppress=177 "
+              "-Xcudafe --diag_suppress=550 -I%s" % os.path.join(ROOT, "include"))
+CXX_FLAGS = "-O2 -std=c++17 -fPIC -fvisibility=hidden -I/usr/local/cuda/include -I%s" % os.path.join(ROOT, "include")
+
+
+def units():
+    """(object name, source, extra defines)"""
+    u = []
+    for fn, name, kind, bool_ok in BINARY_OPS:
+        for cty, short in DTYPES:
+            u.append((f"binary_{name}_{short}", "binary_inst.cu",
+                      f"-DHPTB_OP={fn} -DHPTB_OPNAME={name} -DHPTB_KIND={kind} -DHPTB_BOOL_OK={bool_ok} "
+                      f"-DHPTB_LHS={cty} -DHPTB_LHSNAME={short}"))
+    for name in UNARY_OPS:
+        u.append((f"unary_{name}", "unary_inst.cu", f"-DHPTB_OPENUM=HPTB_{name.upper()} -DHPTB_OPNAME={name}"))
+    for cty, short in DTYPES:
+        u.append((f"cast_{short}", "cast_inst.cu", f"-DHPTB_LHS={cty} -DHPTB_LHSNAME={short}"))
+    for name in REDUCE_OPS:
+        if os.path.exists(os.path.join(CSRC, "reduce_inst.cu")):
+            u.append((f"reduce_{name}", "reduce_inst.cu", f"-DHPTB_OPENUM=HPTB_{name.upper()} -DHPTB_OPNAME={name}"))
+    for src in ("softmax.cu", "misc.cu", "meanvar.cu"):
+        if os.path.exists(os.path.join(CSRC, src)):
+            u.append((src[:-3], src, ""))
+    return u
+
+
+def write_ninja():
+    os.makedirs(BUILD, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    lines = [
+        "ninja_required_version = 1.3",
+        f"nvcc = {NVCC}",
+        f"nvflags = {NVCC_FLAGS}",
+        f"cxxflags = {CXX_FLAGS}",
+        "rule nvcc",
+        "  command = $nvcc $nvflags $defs -MD -MF $out.d -c $in -o $out",
+        "  depfile = $out.d",
+        "  deps = gcc",
+        "  description = NVCC $out",
+        "rule cxx",
+        "  command = g++ $cxxflags -MD -MF $out.d -c $in -o $out",
+        "  depfile = $out.d",
+        "  deps = gcc",
+        "  description = CXX $out",
+        "rule link",
+        "  command = g++ -shared -o $out @$out.rsp -L/usr/local/cuda/lib64 -lcudart_static -Wl,--exclude-libs,ALL -ldl -lrt -lpthread",
+        "  rspfile = $out.rsp",
+        "  rspfile_content = $in",
+        "  description = LINK $out",
+        "",
+    ]
+    objs = []
+    for name, src, defs in units():
+        obj = os.path.join(BUILD, "obj", name + ".o")
+        lines += [f"build {obj}: nvcc {os.path.join(CSRC, src)}", f"  defs = {defs}"]
+        objs.append(obj)
+    for src in sorted(os.listdir(CSRC)):
+        if src.endswith(".cpp"):
+            obj = os.path.join(BUILD, "obj", src[:-4] + ".o")
+            lines += [f"build {obj}: cxx {os.path.join(CSRC, src)}"]
+            objs.append(obj)
+    lib = os.path.join(LIBDIR, "libhpt_b200.so")
+    lines += [f"build {lib}: link {' '.join(objs)}", f"default {lib}", ""]
+    with open(os.path.join(BUILD, "build.ninja"), "w") as f:
+        f.write("\n".join(lines))
+    return lib
+
+
+def build_oracle():
+    """C++/OpenMP restatement of Hpt's CPU path: the parity oracle and the timed CPU baseline."""
+    src = os.path.join(ROOT, "oracle", "oracle_cpu.cpp")
+    if not os.path.exists(src):
+        return None
+    outdir = os.path.join(ROOT, "oracle", "_build")
+    os.makedirs(outdir, exist_ok=True)
+    out = os.path.join(outdir, "liboracle_cpu.so")
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    # x86-64-v3 (AVX2+FMA) rather than -march=native: the .so travels to the GPU box, whose host
+    # CPU may differ from the build container's.
+    cmd = ["g++", "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-march=x86-64-v3", "-ffp-contract=off",
+           "-o", out, src]
+    subprocess.check_call(cmd)
+    return out
+
+
+def main():
+    if "--clean" in sys.argv:
+        shutil.rmtree(BUILD, ignore_errors=True)
+        shutil.rmtree(LIBDIR, ignore_errors=True)
+        shutil.rmtree(os.path.join(ROOT, "oracle", "_build"), ignore_errors=True)
+    lib = write_ninja()
+    jobs = os.environ.get("HPTB_BUILD_JOBS", str(os.cpu_count() or 4))
+    subprocess.check_call(["ninja", "-C", BUILD, "-j", jobs] + (["-v"] if "-v" in sys.argv else []))
+    build_oracle()
+    print("built", lib)
+
+
+if __name__ == "__main__":
+    main()

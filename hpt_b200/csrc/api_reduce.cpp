@@ -1,0 +1,188 @@
+// api_reduce.cpp — C-ABI entry point for axis reductions and the host planner in front of reduce.cuh.
+//
+// Host flow mirrors reduce / reduce2 / reduce3 → contiguous_reduce / uncontiguous_reduce
+// (hpt/src/backends/cuda/utils/reduce/reduce.rs:62-838) and reduce_prepare (reduce_utils.rs:18-74):
+// validate axes, form the (out, in) stride pair with stride 0 on reduced dims, collapse, launch.
+// No per-call cuMemAlloc (reduce.rs:272-273, :446-451): scratch and tickets come from the context.
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "dtypes_x.h"
+#include "promote.h"
+#include "reduce_plan.h"
+
+#define HPTB_WEAK __attribute__((weak))
+extern "C" {
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_sum(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_mean(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_max(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_min(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_argmax(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_argmin(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_logsumexp(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_sum_square(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_prod(int);
+}
+
+namespace hptb {
+
+namespace {
+struct TicketBuf {
+  uint32_t* ptr = nullptr;
+  size_t n = 0;
+};
+struct TicketState {
+  std::mutex mu;
+  std::unordered_map<void*, TicketBuf> by_stream;
+  std::vector<void*> retired;
+};
+std::mutex g_mu;
+std::unordered_map<hptb_ctx*, TicketState*> g_states;
+
+TicketState* state_of(hptb_ctx* ctx) {
+  std::lock_guard<std::mutex> g(g_mu);
+  auto it = g_states.find(ctx);
+  if (it != g_states.end()) return it->second;
+  TicketState* s = new TicketState();
+  g_states[ctx] = s;
+  return s;
+}
+}  // namespace
+
+uint32_t* ctx_tickets(hptb_ctx* ctx, cudaStream_t stream, size_t n) {
+  TicketState* st = state_of(ctx);
+  std::lock_guard<std::mutex> g(st->mu);
+  TicketBuf& b = st->by_stream[(void*)stream];
+  if (b.n >= n) return b.ptr;
+  size_t cap = 1 << 16;
+  while (cap < n) cap <<= 1;
+  void* p = nullptr;
+  if (cudaMalloc(&p, cap * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaMemsetAsync(p, 0, cap * sizeof(uint32_t), stream) != cudaSuccess) { cudaFree(p); return nullptr; }
+  if (b.ptr) st->retired.push_back(b.ptr);  // earlier launches on the stream may still use it
+  b.ptr = (uint32_t*)p;
+  b.n = cap;
+  return b.ptr;
+}
+
+void ctx_tickets_destroy(hptb_ctx* ctx) {
+  TicketState* st = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_mu);
+    auto it = g_states.find(ctx);
+    if (it == g_states.end()) return;
+    st = it->second;
+    g_states.erase(it);
+  }
+  cudaDeviceSynchronize();
+  for (auto& kv : st->by_stream) cudaFree(kv.second.ptr);
+  for (void* p : st->retired) cudaFree(p);
+  delete st;
+}
+
+static ReduceLauncher reduce_launcher(int op, int dt) {
+  typedef ReduceLauncher (*G)(int);
+  G g = nullptr;
+  switch (op) {
+    case HPTB_SUM: g = hptb_reduce_sum; break;
+    case HPTB_MEAN: g = hptb_reduce_mean; break;
+    case HPTB_MAX: g = hptb_reduce_max; break;
+    case HPTB_MIN: g = hptb_reduce_min; break;
+    case HPTB_ARGMAX: g = hptb_reduce_argmax; break;
+    case HPTB_ARGMIN: g = hptb_reduce_argmin; break;
+    case HPTB_LOGSUMEXP: g = hptb_reduce_logsumexp; break;
+    case HPTB_SUM_SQUARE: g = hptb_reduce_sum_square; break;
+    case HPTB_PROD: g = hptb_reduce_prod; break;
+    default: break;
+  }
+  return g ? g(dt) : nullptr;
+}
+
+hptb_status build_reduce_plan(hptb_ctx* ctx, const hptb_tensor* in, const int32_t* axes, int naxes,
+                              const hptb_tensor* out, ReducePlan* plan) {
+  uint8_t mask[HPTB_MAX_DIMS] = {0};
+  for (int i = 0; i < naxes; ++i) {
+    int a = axes[i];
+    if (in->ndim > 0 && (a < 0 || a >= in->ndim)) return fail(HPTB_ERR_AXIS, "reduce: axis %d out of range for ndim %d", a, in->ndim);
+    if (in->ndim == 0) continue;
+    if (mask[a]) return fail(HPTB_ERR_AXIS, "reduce: axis %d is duplicated", a);
+    mask[a] = 1;
+  }
+  // expected output shape (keep_dims = false; all reduced → [1])
+  int64_t oshape[HPTB_MAX_DIMS];
+  int on = 0;
+  double count = 1.0;
+  for (int i = 0; i < in->ndim; ++i) {
+    if (mask[i]) count *= (double)in->shape[i];
+    else oshape[on++] = in->shape[i];
+  }
+  bool scalar_out = on == 0;
+  if (scalar_out) { oshape[0] = 1; on = 1; }
+  bool same = out->ndim == on;
+  for (int i = 0; same && i < on; ++i) same = out->shape[i] == oshape[i];
+  if (!same) return fail(HPTB_ERR_SHAPE, "reduce: out shape does not match the reduced shape of the input");
+  int64_t strides[kMaxOperands][HPTB_MAX_DIMS] = {{0}};
+  int k = 0;
+  for (int i = 0; i < in->ndim; ++i) {
+    strides[1][i] = in->strides[i];
+    strides[0][i] = mask[i] ? 0 : out->strides[k++];
+  }
+  collapse(in->ndim, in->shape, 2, strides, mask, &plan->c);
+  plan->in = in->data;
+  plan->out = out->data;
+  plan->count = count;
+  plan->ctx = ctx;
+  return HPTB_OK;
+}
+
+}  // namespace hptb
+
+namespace hptb {
+hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, hptb_tensor* out,
+                        int init_out, double count_override, void* stream);
+}
+using namespace hptb;
+
+extern "C" {
+
+int hptb_reduce_out_dtype(int op, int in) {
+  if (!dtype_valid(in)) return -1;
+  switch (op) {
+    case HPTB_SUM: case HPTB_MAX: case HPTB_MIN: case HPTB_SUM_SQUARE: case HPTB_PROD: return in;
+    case HPTB_MEAN: case HPTB_LOGSUMEXP: return kFloatOutBinary[in][in];
+    case HPTB_ARGMAX: case HPTB_ARGMIN: return HPTB_I64;
+    default: return -1;
+  }
+}
+
+hptb_status hptb_reduce(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, hptb_tensor* out,
+                        int init_out, void* stream) {
+  return reduce_impl(ctx, op, in, axes, naxes, out, init_out, -1.0, stream);
+}
+
+}  // extern "C"
+
+namespace hptb {
+hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, hptb_tensor* out,
+                        int init_out, double count_override, void* stream) {
+  if (!ctx) return fail(HPTB_ERR_INVALID, "reduce: null ctx");
+  if (op < 0 || op >= HPTB_REDUCE_COUNT) return fail(HPTB_ERR_INVALID, "reduce: bad op %d", op);
+  if (!axes && naxes) return fail(HPTB_ERR_INVALID, "reduce: null axes");
+  HPTB_TRY(validate_tensor(in, "reduce in"));
+  HPTB_TRY(validate_tensor(out, "reduce out"));
+  if ((op == HPTB_ARGMAX || op == HPTB_ARGMIN) && naxes != 1)
+    return fail(HPTB_ERR_AXIS, "argmax/argmin take exactly one axis (got %d)", naxes);
+  int odt = hptb_reduce_out_dtype(op, in->dtype);
+  if (out->dtype != odt)
+    return fail(HPTB_ERR_DTYPE, "reduce: out dtype is %s, expected %s", dtype_name(out->dtype), dtype_name(odt));
+  ReduceLauncher fn = reduce_launcher(op, in->dtype);
+  if (!fn) return fail(HPTB_ERR_DTYPE, "reduce: no kernel for op %d on %s", op, dtype_name(in->dtype));
+  ReducePlan plan;
+  HPTB_TRY(build_reduce_plan(ctx, in, axes, naxes, out, &plan));
+  plan.fold_out = init_out ? 0 : 1;
+  if (count_override > 0) plan.count = count_override;  // sharded mean: divide the local Σ by the GLOBAL count
+  DeviceGuard g(ctx->device);
+  return fn(plan, (cudaStream_t)stream);
+}
+}  // namespace hptb

@@ -1,0 +1,760 @@
+// reduce.cuh — axis reductions: op traits, the two kernel skeletons and their launcher.
+//
+// Replaces the eight-kernels-per-op families of hpt-cudakernels/src/reduce/reduce_template.cuh and
+// arg_template.cuh (`contiguous_<op>`, `<op>_fast_dim_include`, `{contiguous,uncontiguous}_<op>_fast_dim_only`,
+// `*_small_fast_dim_only`, `<op>_fast_dim_no_include`) and the host planner that picks among them
+// (hpt/src/backends/cuda/utils/reduce/reduce.rs:231-838).  After the collapse pass (layout.cpp) a
+// reduction is a list of kept dims and reduced dims; two skeletons cover every case:
+//
+//   reduce_rows_kernel  the innermost reduced dim is walked by adjacent lanes (unit stride when the
+//                       reduced axis is the contiguous one: full reduce, last-axis reduce, NCHW→C
+//                       statistics, and the transposed-view axis-0 reduce of config 2).  128-bit loads,
+//                       per-thread vector accumulators, warp shuffle + shared-memory tree.  A group
+//                       of G = 1..32 lanes (small rows) or a whole CTA (long rows) owns one output;
+//                       when there are too few outputs to fill the GPU each output is split over S
+//                       CTAs whose partials are combined by the last CTA to arrive (fixed order →
+//                       run-to-run deterministic, no float atomics) in the same launch.
+//   reduce_cols_kernel  the contiguous dim is kept: lanes run along it with 128-bit loads and each
+//                       thread strides over the reduced space; shared-memory tree over the CTA's
+//                       rows, the same single-launch split/combine over CTAs.
+//
+// Accumulation: f32 for f16/bf16/f32 (the reference sums halves in half precision,
+// reduce_classes.cuh:58-61), f64 for f64, wrapping integer arithmetic in T for ints, OR/AND for bool.
+#pragma once
+#include "common.h"
+#include "context.h"
+#include "layout.h"
+#include "promote.h"
+#include "reduce_plan.h"
+#include "scalar.cuh"
+
+namespace hptb {
+
+constexpr int kRedThreads = 256;
+constexpr int kRedMaxDims = HPTB_MAX_DIMS;
+
+// ---- op traits ---------------------------------------------------------------------------------------
+template <typename V>
+struct ArgPair {
+  V val;
+  int64_t idx;
+};
+
+template <typename T> struct is_argpair : std::false_type {};
+template <typename V> struct is_argpair<ArgPair<V>> : std::true_type {};
+
+template <int OP, typename T, typename Enable = void> struct ReduceOp;
+
+// helpers in the compute type
+template <typename C> __device__ __forceinline__ C red_add(C a, C b) {
+  if constexpr (is_bool_t<C>::value) return b8{(uint8_t)(a.v | b.v)};
+  else if constexpr (std::is_integral<C>::value) {
+    typedef typename std::make_unsigned<C>::type U;
+    return (C)(U)((U)a + (U)b);
+  } else return a + b;
+}
+template <typename C> __device__ __forceinline__ C red_mul(C a, C b) {
+  if constexpr (is_bool_t<C>::value) return b8{(uint8_t)(a.v & b.v)};
+  else if constexpr (std::is_integral<C>::value) {
+    typedef typename std::make_unsigned<C>::type U;
+    if constexpr (sizeof(C) < 4) return (C)(U)((uint32_t)(U)a * (uint32_t)(U)b);
+    else return (C)((U)a * (U)b);
+  } else return a * b;
+}
+template <typename C> __device__ __forceinline__ C red_max(C a, C b) {
+  if constexpr (is_bool_t<C>::value) return b8{(uint8_t)(a.v | b.v)};
+  else if constexpr (std::is_same<C, float>::value) return fmaxf(a, b);
+  else if constexpr (std::is_same<C, double>::value) return fmax(a, b);
+  else return a > b ? a : b;
+}
+template <typename C> __device__ __forceinline__ C red_min(C a, C b) {
+  if constexpr (is_bool_t<C>::value) return b8{(uint8_t)(a.v & b.v)};
+  else if constexpr (std::is_same<C, float>::value) return fminf(a, b);
+  else if constexpr (std::is_same<C, double>::value) return fmin(a, b);
+  else return a < b ? a : b;
+}
+template <typename C> __device__ __forceinline__ C red_zero() {
+  if constexpr (is_bool_t<C>::value) return b8{0};
+  else return (C)0;
+}
+template <typename C> __device__ __forceinline__ C red_one() {
+  if constexpr (is_bool_t<C>::value) return b8{1};
+  else return (C)1;
+}
+
+// SUM: common_reduce.rs:32-52 (identity ZERO, combine _add), output dtype T
+template <typename T> struct ReduceOp<HPTB_SUM, T> {
+  typedef T Out;
+  typedef compute_t<T> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return red_zero<Acc>(); }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { return to_compute<T>(x); }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return red_add<Acc>(a, b); }
+  static __device__ __forceinline__ Out post(Acc a, double) { return from_compute<T>(a); }
+  static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
+};
+// PROD: common_reduce.rs:80-99
+template <typename T> struct ReduceOp<HPTB_PROD, T> {
+  typedef T Out;
+  typedef compute_t<T> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return red_one<Acc>(); }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { return to_compute<T>(x); }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return red_mul<Acc>(a, b); }
+  static __device__ __forceinline__ Out post(Acc a, double) { return from_compute<T>(a); }
+  static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
+};
+// SUM_SQUARE: hpt-traits/src/ops/reduce.rs:171-175 (Σ x², in T)
+template <typename T> struct ReduceOp<HPTB_SUM_SQUARE, T> {
+  typedef T Out;
+  typedef compute_t<T> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return red_zero<Acc>(); }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { Acc c = to_compute<T>(x); return red_mul<Acc>(c, c); }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return red_add<Acc>(a, b); }
+  static __device__ __forceinline__ Out post(Acc a, double) { return from_compute<T>(a); }
+  static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
+};
+// MAX / MIN: common_reduce.rs:101-168 (identity NEG_INF / INF; f32::max/min ignore NaN)
+template <typename T> struct ReduceOp<HPTB_MAX, T> {
+  typedef T Out;
+  typedef compute_t<T> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return Limits<Acc>::lowest(); }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { return to_compute<T>(x); }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return red_max<Acc>(a, b); }
+  static __device__ __forceinline__ Out post(Acc a, double) { return from_compute<T>(a); }
+  static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
+};
+template <typename T> struct ReduceOp<HPTB_MIN, T> {
+  typedef T Out;
+  typedef compute_t<T> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return Limits<Acc>::highest(); }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { return to_compute<T>(x); }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return red_min<Acc>(a, b); }
+  static __device__ __forceinline__ Out post(Acc a, double) { return from_compute<T>(a); }
+  static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
+};
+// MEAN: common_reduce.rs:352-380 — cast to FloatOutBinaryPromote<T,T>, Σ, ÷ n.  (The reference rounds n to
+// the output dtype before dividing; here the division uses the exact count in the compute type.)
+template <typename T> struct ReduceOp<HPTB_MEAN, T> {
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type Out;
+  typedef compute_t<Out> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return (Acc)0; }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { return to_compute<Out>(cast<Out>(x)); }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return a + b; }
+  static __device__ __forceinline__ Out post(Acc a, double n) { return from_compute<Out>(a / (Acc)n); }
+  static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<Out>(o); }
+};
+// LOGSUMEXP: common_reduce.rs:451-480 — ln Σ exp(x), no max shift (as the reference; overflows to +inf alike)
+template <typename T> struct ReduceOp<HPTB_LOGSUMEXP, T> {
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type Out;
+  typedef compute_t<Out> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return (Acc)0; }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) {
+    Acc c = to_compute<Out>(cast<Out>(x));
+    if constexpr (std::is_same<Acc, float>::value) return expf(c);
+    else return exp(c);
+  }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return a + b; }
+  static __device__ __forceinline__ Out post(Acc a, double) {
+    if constexpr (std::is_same<Acc, float>::value) return from_compute<Out>(logf(a));
+    else return from_compute<Out>(log(a));
+  }
+  static __device__ __forceinline__ Acc from_out(Out o) {  // fold a previous logsumexp value: exp it back
+    Acc c = to_compute<Out>(o);
+    if constexpr (std::is_same<Acc, float>::value) return expf(c);
+    else return exp(c);
+  }
+};
+// ARGMAX / ARGMIN: cpu/kernels/argreduce_kernels.rs:13-21,49-57 — strict compare from NEG_INF / INF with
+// index 0 as the start, so ties resolve to the lowest index, NaN never wins and an all-NaN (or all-identity)
+// row yields 0.  A (value, index) pair with "better value, else lower index" is the associative form.
+template <typename T, bool IS_MAX> struct ArgOp {
+  typedef int64_t Out;
+  typedef ArgPair<compute_t<T>> Acc;
+  typedef compute_t<T> V;
+  static constexpr bool kIndexed = true;
+  static __device__ __forceinline__ Acc identity() {
+    return Acc{IS_MAX ? Limits<V>::lowest() : Limits<V>::highest(), 0};
+  }
+  static __device__ __forceinline__ Acc pre(T x, int64_t i) { return Acc{to_compute<T>(x), i}; }
+  static __device__ __forceinline__ bool better(V a, V b) {  // a strictly better than b
+    if constexpr (is_bool_t<V>::value) return IS_MAX ? (a.v > b.v) : (a.v < b.v);
+    else return IS_MAX ? (a > b) : (a < b);
+  }
+  static __device__ __forceinline__ bool equal(V a, V b) {
+    if constexpr (is_bool_t<V>::value) return a.v == b.v;
+    else return a == b;
+  }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) {
+    if (better(b.val, a.val) || (equal(b.val, a.val) && b.idx < a.idx)) return b;
+    return a;
+  }
+  static __device__ __forceinline__ Out post(Acc a, double) { return a.idx; }
+  static __device__ __forceinline__ Acc from_out(Out) { return identity(); }
+};
+template <typename T> struct ReduceOp<HPTB_ARGMAX, T> : ArgOp<T, true> {};
+template <typename T> struct ReduceOp<HPTB_ARGMIN, T> : ArgOp<T, false> {};
+
+// ---- launch parameters ---------------------------------------------------------------------------------
+struct DimWalk {
+  int32_t n;
+  uint32_t shape[kRedMaxDims];  // innermost first
+  FastDiv div[kRedMaxDims];
+  int64_t stride_a[kRedMaxDims];
+  int64_t stride_b[kRedMaxDims];
+};
+
+struct RowsRedParams {
+  DimWalk kept;        // outputs: stride_a = input strides, stride_b = output strides
+  DimWalk outer;       // reduced dims other than the innermost one: stride_a = input strides
+  int64_t M;           // outputs
+  int64_t L;           // innermost reduced extent
+  int64_t inner_stride;
+  int64_t cpr;         // chunks per inner run
+  int64_t chunks;      // chunks per output = (prod outer) * cpr
+  int64_t S;           // CTAs per output (block variant)
+  int64_t chunks_per_split;
+  double count;        // elements reduced per output
+  int32_t G;           // lanes per output (warp variant)
+  int32_t use64;
+  int32_t fold_out;    // combine with the previous contents of out
+};
+
+struct ColsRedParams {
+  DimWalk kept;        // kept dims other than the contiguous one: stride_a input, stride_b output
+  DimWalk red;         // reduced dims: stride_a input
+  int64_t C;           // extent of the contiguous kept dim (unit stride in input and output)
+  int64_t R;           // reduced elements per output
+  int64_t K;           // prod(kept.shape)
+  int64_t col_tiles;
+  int64_t S, rows_per_split;
+  double count;
+  int32_t TX;          // lanes along C (power of two ≤ 32)
+  int32_t use64;
+  int32_t fold_out;
+  int32_t index_dim;   // (arg reduce) unused: the single reduced dim is red.shape[0]
+};
+
+__device__ __forceinline__ void walk2(int64_t idx, const DimWalk& w, int use64, int64_t& oa, int64_t& ob) {
+  if (!use64) {
+    uint32_t r = (uint32_t)idx;
+#pragma unroll 1
+    for (int i = 0; i < w.n; ++i) {
+      uint32_t q = w.div[i].div(r);
+      uint32_t rem = r - q * w.shape[i];
+      oa += (int64_t)rem * w.stride_a[i];
+      ob += (int64_t)rem * w.stride_b[i];
+      r = q;
+    }
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < w.n; ++i) {
+      int64_t q = idx / (int64_t)w.shape[i];
+      int64_t rem = idx - q * (int64_t)w.shape[i];
+      oa += rem * w.stride_a[i];
+      ob += rem * w.stride_b[i];
+      idx = q;
+    }
+  }
+}
+
+template <typename V>
+__device__ __forceinline__ V shfl_xor(V v, int off) {
+  if constexpr (is_bool_t<V>::value) {
+    return b8{(uint8_t)__shfl_xor_sync(0xffffffffu, (int)v.v, off)};
+  } else if constexpr (std::is_arithmetic<V>::value && sizeof(V) < 4) {
+    return (V)__shfl_xor_sync(0xffffffffu, (int)v, off);
+  } else if constexpr (std::is_arithmetic<V>::value && sizeof(V) == 4) {
+    return __shfl_xor_sync(0xffffffffu, v, off);
+  } else {
+    // 8-byte scalars and accumulator structs (ArgPair, mean/var pair): word-wise
+    static_assert(sizeof(V) % 4 == 0, "accumulator size must be a multiple of 4 bytes");
+    V o;
+    uint32_t w[sizeof(V) / 4];
+    memcpy(w, &v, sizeof(V));
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(V) / 4); ++i) w[i] = __shfl_xor_sync(0xffffffffu, w[i], off);
+    memcpy(&o, w, sizeof(V));
+    return o;
+  }
+}
+
+// partials written by other CTAs are read through L2 (ld.global.cg): L1 is not coherent across SMs
+template <typename A>
+__device__ __forceinline__ A load_cg(const A* p) {
+  typedef typename VecBytes<sizeof(A)>::type V;
+  V raw = __ldcg(reinterpret_cast<const V*>(p));
+  A r;
+  memcpy(&r, &raw, sizeof(A));
+  return r;
+}
+
+template <typename Op, typename Acc>
+__device__ __forceinline__ Acc warp_reduce(Acc v, int width) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    if (off < width) {
+      Acc o = shfl_xor<Acc>(v, off);
+      // keep operand order independent of the lane so the result is identical on both sides
+      const bool lower = (threadIdx.x & off) == 0;
+      v = lower ? Op::combine(v, o) : Op::combine(o, v);
+    }
+  }
+  return v;
+}
+
+// combine S partials for `n` adjacent outputs; the last CTA to take a ticket does the work.
+// returns true in the CTA that must finish.  `scratch` holds [tile][S][n] accumulators.
+__device__ __forceinline__ bool take_ticket(uint32_t* ticket, uint32_t S) {
+  __shared__ uint32_t s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t old = atomicAdd(ticket, 1u);
+    s_last = (old == S - 1);
+    if (old == S - 1) *ticket = 0;  // self-reset: the buffer is reusable by the next launch on this stream
+  }
+  __syncthreads();
+  bool last = s_last != 0;
+  if (last) __threadfence();
+  return last;
+}
+
+// ---- rows kernel ---------------------------------------------------------------------------------------
+// BLOCK=false: a group of G lanes owns one output (M large, short rows); BLOCK=true: CTA (m, s) reduces split
+// s of output m.  VEC elements per load when the inner run is unit-stride and aligned, else VEC = 1.
+template <typename Op, typename T, int VEC, bool BLOCK>
+__global__ void __launch_bounds__(kRedThreads)
+reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out, typename Op::Acc* __restrict__ scratch,
+                   uint32_t* __restrict__ tickets, RowsRedParams p) {
+  typedef typename Op::Acc Acc;
+  constexpr int UNROLL = 4;
+  const int tid = threadIdx.x;
+  int64_t m, c_begin, c_end, c_step, split = 0;
+  int c_lane;
+  if constexpr (BLOCK) {
+    m = blockIdx.x / p.S;  // S is small; 64-bit division once per CTA
+    split = blockIdx.x - m * p.S;
+    c_begin = split * p.chunks_per_split;
+    c_end = c_begin + p.chunks_per_split;
+    if (c_end > p.chunks) c_end = p.chunks;
+    c_lane = tid;
+    c_step = kRedThreads;
+  } else {
+    const int per_cta = kRedThreads / p.G;
+    m = (int64_t)blockIdx.x * per_cta + tid / p.G;
+    c_begin = 0;
+    c_end = p.chunks;
+    c_lane = tid & (p.G - 1);
+    c_step = p.G;
+  }
+  const bool active = m < p.M;
+  int64_t in_off = 0, out_off = 0;
+  if (active) walk2(m, p.kept, p.use64, in_off, out_off);
+
+  Acc acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = Op::identity();
+
+  if (active) {
+    const T* base = in + in_off;
+    for (int64_t c = c_begin + c_lane; c < c_end; c += c_step * UNROLL) {
+      Pack<T, VEC> v[UNROLL];
+      int64_t e0[UNROLL];
+      int32_t cnt[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t cu = c + (int64_t)u * c_step;
+        cnt[u] = 0;
+        if (cu < c_end) {
+          int64_t col = cu, roff = 0, dummy = 0;
+          if (p.outer.n > 0) {
+            int64_t r;
+            if (!p.use64) { r = p.outer.div[kRedMaxDims - 1].div((uint32_t)cu); }
+            else { r = cu / p.cpr; }
+            col = cu - r * p.cpr;
+            walk2(r, p.outer, p.use64, roff, dummy);
+          }
+          const int64_t e = col * VEC;
+          const int64_t left = p.L - e;
+          cnt[u] = left >= VEC ? VEC : (int32_t)left;
+          e0[u] = e;
+          const T* src = base + roff + e * p.inner_stride;
+          if (VEC > 1 && cnt[u] == VEC) load_pack<T, VEC>(v[u], src);
+          else
+            for (int k = 0; k < cnt[u]; ++k) v[u].v[k] = load_one(src + k * p.inner_stride);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          if (k < cnt[u]) acc[k] = Op::combine(acc[k], Op::pre(v[u].v[k], e0[u] + k));
+      }
+    }
+  }
+  Acc a = acc[0];
+#pragma unroll
+  for (int k = 1; k < VEC; ++k) a = Op::combine(a, acc[k]);
+
+  if constexpr (!BLOCK) {
+    a = warp_reduce<Op, Acc>(a, p.G);
+    if (active && c_lane == 0) {
+      if (p.fold_out) a = Op::combine(Op::from_out(out[out_off]), a);
+      out[out_off] = Op::post(a, p.count);
+    }
+  } else {
+    __shared__ Acc s_part[kRedThreads / 32];
+    a = warp_reduce<Op, Acc>(a, 32);
+    if ((tid & 31) == 0) s_part[tid >> 5] = a;
+    __syncthreads();
+    if (tid < 32) {
+      a = tid < kRedThreads / 32 ? s_part[tid] : Op::identity();
+      a = warp_reduce<Op, Acc>(a, kRedThreads / 32);
+    }
+    if (p.S == 1) {
+      if (tid == 0) {
+        if (p.fold_out) a = Op::combine(Op::from_out(out[out_off]), a);
+        out[out_off] = Op::post(a, p.count);
+      }
+      return;
+    }
+    if (tid == 0) scratch[m * p.S + split] = a;
+    if (take_ticket(tickets + m, (uint32_t)p.S)) {
+      // fixed-order combine of the S partials by the finishing CTA
+      Acc r = Op::identity();
+      for (int64_t s = tid; s < p.S; s += kRedThreads) r = Op::combine(r, load_cg(scratch + m * p.S + s));
+      // lanes hold interleaved subsets; order within the tree is fixed by lane id → deterministic
+      r = warp_reduce<Op, Acc>(r, 32);
+      __syncthreads();
+      if ((tid & 31) == 0) s_part[tid >> 5] = r;
+      __syncthreads();
+      if (tid < 32) {
+        r = tid < kRedThreads / 32 ? s_part[tid] : Op::identity();
+        r = warp_reduce<Op, Acc>(r, kRedThreads / 32);
+        if (tid == 0) {
+          if (p.fold_out) r = Op::combine(Op::from_out(out[out_off]), r);
+          out[out_off] = Op::post(r, p.count);
+        }
+      }
+    }
+  }
+}
+
+// ---- cols kernel ---------------------------------------------------------------------------------------
+template <typename Op, typename T, int VEC>
+__global__ void __launch_bounds__(kRedThreads)
+reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out, typename Op::Acc* __restrict__ scratch,
+                   uint32_t* __restrict__ tickets, ColsRedParams p) {
+  typedef typename Op::Acc Acc;
+  typedef typename Op::Out Out;
+  constexpr int UNROLL = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Acc* sm = reinterpret_cast<Acc*>(smem_raw);  // [TY][TX*VEC]
+  const int tid = threadIdx.x;
+  const int TX = p.TX, TY = kRedThreads / TX;
+  const int tx = tid & (TX - 1), ty = tid / TX;
+  // blockIdx.x = ((k * col_tiles) + tile) * S + split
+  int64_t b = blockIdx.x;
+  const int64_t split = b % p.S;
+  b /= p.S;
+  const int64_t tile = b % p.col_tiles;
+  const int64_t k = b / p.col_tiles;
+  const int64_t col = (tile * TX + tx) * VEC;
+  const bool col_ok = col < p.C;
+  int32_t ncol = 0;
+  if (col_ok) ncol = (p.C - col) >= VEC ? VEC : (int32_t)(p.C - col);
+  int64_t in_off = 0, out_off = 0;
+  walk2(k, p.kept, p.use64, in_off, out_off);
+  const int64_t r_begin = split * p.rows_per_split;
+  int64_t r_end = r_begin + p.rows_per_split;
+  if (r_end > p.R) r_end = p.R;
+
+  Acc acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = Op::identity();
+  if (col_ok) {
+    const T* base = in + in_off + col;
+    for (int64_t r = r_begin + ty; r < r_end; r += (int64_t)TY * UNROLL) {
+      Pack<T, VEC> v[UNROLL];
+      bool ok[UNROLL];
+      int64_t ri[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t ru = r + (int64_t)u * TY;
+        ok[u] = ru < r_end;
+        ri[u] = ru;
+        if (ok[u]) {
+          int64_t roff = 0, dummy = 0;
+          if (p.red.n == 1) roff = ru * p.red.stride_a[0];
+          else walk2(ru, p.red, p.use64, roff, dummy);
+          if (VEC > 1 && ncol == VEC) load_pack<T, VEC>(v[u], base + roff);
+          else
+            for (int j = 0; j < ncol; ++j) v[u].v[j] = load_one(base + roff + j);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (!ok[u]) continue;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (j < ncol) acc[j] = Op::combine(acc[j], Op::pre(v[u].v[j], ri[u]));
+      }
+    }
+  }
+  // tree over ty in shared memory
+  const int W = TX * VEC;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = acc[j];
+  __syncthreads();
+  for (int h = TY >> 1; h > 0; h >>= 1) {
+    if (ty < h) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        Acc x = sm[ty * W + tx * VEC + j], y = sm[(ty + h) * W + tx * VEC + j];
+        sm[ty * W + tx * VEC + j] = Op::combine(x, y);
+      }
+    }
+    __syncthreads();
+  }
+  Out* dst = out + out_off + col;
+  if (p.S == 1) {
+    if (ty == 0 && col_ok) {
+      for (int j = 0; j < ncol; ++j) {
+        Acc a = sm[tx * VEC + j];
+        if (p.fold_out) a = Op::combine(Op::from_out(dst[j]), a);
+        dst[j] = Op::post(a, p.count);
+      }
+    }
+    return;
+  }
+  const int64_t group = k * p.col_tiles + tile;  // outputs sharing one ticket
+  Acc* my = scratch + (group * p.S + split) * W;
+  if (ty == 0)
+    for (int j = 0; j < VEC; ++j) my[tx * VEC + j] = sm[tx * VEC + j];
+  if (take_ticket(tickets + group, (uint32_t)p.S)) {
+    // thread (tx, ty): partial s = ty, ty+TY, … of its columns, then the same shared-memory tree
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = Op::identity();
+    for (int64_t s = ty; s < p.S; s += TY) {
+      const Acc* src = scratch + (group * p.S + s) * W;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] = Op::combine(acc[j], load_cg(src + tx * VEC + j));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = acc[j];
+    __syncthreads();
+    for (int h = TY >> 1; h > 0; h >>= 1) {
+      if (ty < h) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          Acc x = sm[ty * W + tx * VEC + j], y = sm[(ty + h) * W + tx * VEC + j];
+          sm[ty * W + tx * VEC + j] = Op::combine(x, y);
+        }
+      }
+      __syncthreads();
+    }
+    if (ty == 0 && col_ok) {
+      for (int j = 0; j < ncol; ++j) {
+        Acc a = sm[tx * VEC + j];
+        if (p.fold_out) a = Op::combine(Op::from_out(dst[j]), a);
+        dst[j] = Op::post(a, p.count);
+      }
+    }
+  }
+}
+
+// ---- host launcher -------------------------------------------------------------------------------------------
+inline bool red_fits_u32(int64_t v) { return v >= 0 && v < (int64_t(1) << 31); }
+
+inline void fill_walk(DimWalk& w, const Collapsed& c, const int* dims, int n, bool with_out, bool& big) {
+  w.n = n;
+  for (int i = 0; i < n; ++i) {
+    int d = dims[i];
+    if (!red_fits_u32(c.shape[d])) big = true;
+    w.shape[i] = (uint32_t)c.shape[d];
+    w.div[i] = FastDiv((uint32_t)c.shape[d]);
+    w.stride_a[i] = c.strides[1][d];
+    w.stride_b[i] = with_out ? c.strides[0][d] : 0;
+  }
+}
+
+template <typename Op, typename T>
+hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
+  typedef typename Op::Acc Acc;
+  typedef typename Op::Out Out;
+  const Collapsed& c = plan.c;
+  const T* in = static_cast<const T*>(plan.in);
+  Out* out = static_cast<Out*>(plan.out);
+  constexpr int VECMAX = 16 / sizeof(T) > 8 ? 8 : 16 / sizeof(T);
+  const int sms = plan.ctx->sm_count;
+
+  // split dims (innermost first lists)
+  int kept[kRedMaxDims], red[kRedMaxDims], nk = 0, nr = 0;
+  for (int d = c.ndim - 1; d >= 0; --d) {
+    if (c.reduced[d]) red[nr++] = d; else kept[nk++] = d;
+  }
+  int64_t M = 1, R = 1;
+  for (int i = 0; i < nk; ++i) M *= c.shape[kept[i]];
+  for (int i = 0; i < nr; ++i) R *= c.shape[red[i]];
+  if (M == 0) return HPTB_OK;  // no outputs
+
+  // ---- cols: the unit-stride dim is kept (and is the output's unit-stride dim) ---------------------------
+  int cdim = -1;
+  for (int i = 0; i < nk; ++i)
+    if (c.strides[1][kept[i]] == 1 && c.strides[0][kept[i]] == 1) { cdim = kept[i]; break; }
+  bool inner_red_unit = nr > 0 && c.strides[1][red[0]] == 1;
+  if (cdim >= 0 && !inner_red_unit && nr > 0 && c.shape[cdim] >= 4) {
+    ColsRedParams p;
+    memset(&p, 0, sizeof(p));
+    bool big = false;
+    int kd[kRedMaxDims], nkd = 0;
+    for (int i = 0; i < nk; ++i) if (kept[i] != cdim) kd[nkd++] = kept[i];
+    fill_walk(p.kept, c, kd, nkd, true, big);
+    fill_walk(p.red, c, red, nr, false, big);
+    p.C = c.shape[cdim];
+    p.R = R;
+    p.K = M / p.C;
+    p.count = plan.count;
+    p.fold_out = plan.fold_out;
+    // vector width: alignment of base pointers and of every stride that moves the row start
+    int vec = VECMAX;
+    auto aligned = [&](int v) {
+      if (v == 1) return true;
+      size_t ain = sizeof(T) * v > 16 ? 16 : sizeof(T) * v;
+      if (reinterpret_cast<uintptr_t>(in) % ain) return false;
+      if (p.C % v) return false;
+      for (int d = 0; d < c.ndim; ++d) {
+        if (d == cdim) continue;
+        if ((uint64_t)(std::llabs(c.strides[1][d]) * (int64_t)sizeof(T)) % ain) return false;
+      }
+      return true;
+    };
+    if (!aligned(vec) || p.C < vec) vec = 1;
+    int TX = 32;
+    while (TX > 1 && (int64_t)(TX / 2) * vec >= p.C) TX >>= 1;
+    p.TX = TX;
+    const int TY = kRedThreads / TX;
+    p.col_tiles = (p.C + (int64_t)TX * vec - 1) / ((int64_t)TX * vec);
+    const int64_t groups = p.K * p.col_tiles;
+    // splits: fill ~4 CTAs per SM, but keep ≥ 4 rows per thread
+    int64_t target = (int64_t)sms * 4;
+    int64_t S = 1;
+    if (groups < target) {
+      S = (target + groups - 1) / groups;
+      int64_t maxS = (p.R + (int64_t)TY * 4 - 1) / ((int64_t)TY * 4);
+      if (S > maxS) S = maxS;
+      if (S < 1) S = 1;
+    }
+    p.rows_per_split = (p.R + S - 1) / S;
+    S = (p.R + p.rows_per_split - 1) / p.rows_per_split;
+    p.S = S;
+    if (groups * S > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "reduce: grid too large");
+    if (groups * S >= (int64_t(1) << 31) || !red_fits_u32(p.R)) big = true;
+    p.use64 = big ? 1 : 0;
+    Scratch scratch;
+    uint32_t* tickets = nullptr;
+    if (S > 1) {
+      HPTB_TRY(scratch.get(plan.ctx, (size_t)(groups * S * TX * vec) * sizeof(Acc), stream));
+      tickets = ctx_tickets(plan.ctx, stream, (size_t)groups);
+      if (!tickets) return fail(HPTB_ERR_OOM, "reduce: ticket buffer allocation failed");
+    }
+    size_t smem = (size_t)kRedThreads * vec * sizeof(Acc);
+    unsigned grid = (unsigned)(groups * S);
+#define HPTB_LAUNCH_COLS(V)                                                                                 \
+  reduce_cols_kernel<Op, T, V><<<grid, kRedThreads, smem, stream>>>(in, out, (Acc*)scratch.ptr, tickets, p)
+    if (vec == VECMAX && VECMAX > 1) HPTB_LAUNCH_COLS(VECMAX);
+    else HPTB_LAUNCH_COLS(1);
+#undef HPTB_LAUNCH_COLS
+    HPTB_CUDA_CHECK(cudaGetLastError());
+    return HPTB_OK;
+  }
+
+  // ---- rows ---------------------------------------------------------------------------------------------
+  RowsRedParams p;
+  memset(&p, 0, sizeof(p));
+  bool big = false;
+  fill_walk(p.kept, c, kept, nk, true, big);
+  p.M = M;
+  p.count = plan.count;
+  p.fold_out = plan.fold_out;
+  if (nr == 0) { p.L = 1; p.inner_stride = 1; }
+  else { p.L = c.shape[red[0]]; p.inner_stride = c.strides[1][red[0]]; }
+  if (nr > 1) fill_walk(p.outer, c, red + 1, nr - 1, false, big);
+  int vec = 1;
+  if (p.inner_stride == 1) {
+    vec = VECMAX;
+    auto aligned = [&](int v) {
+      if (v == 1) return true;
+      size_t ain = sizeof(T) * v > 16 ? 16 : sizeof(T) * v;
+      if (reinterpret_cast<uintptr_t>(in) % ain) return false;
+      if (nr > 1 && p.L % v) return false;
+      for (int d = 0; d < c.ndim; ++d) {
+        if (nr > 0 && d == red[0]) continue;
+        if ((uint64_t)(std::llabs(c.strides[1][d]) * (int64_t)sizeof(T)) % ain) return false;
+      }
+      return true;
+    };
+    if (!aligned(vec) || p.L < vec) vec = 1;
+  }
+  p.cpr = (p.L + vec - 1) / vec;
+  int64_t router = 1;
+  for (int i = 1; i < nr; ++i) router *= c.shape[red[i]];
+  p.chunks = router * p.cpr;
+  if (!red_fits_u32(p.cpr) || p.chunks >= (int64_t(1) << 32) || !red_fits_u32(M)) big = true;
+  p.use64 = big ? 1 : 0;
+  p.outer.div[kRedMaxDims - 1] = FastDiv(big ? 1u : (uint32_t)p.cpr);  // chunk → (outer index, col)
+
+  const bool small = p.chunks <= 32 * 4 && M >= (int64_t)sms * 8;
+  Scratch scratch;
+  uint32_t* tickets = nullptr;
+  unsigned grid;
+  if (small) {
+    int G = 1;
+    while (G < 32 && (int64_t)G * 4 < p.chunks) G <<= 1;
+    p.G = G;
+    p.S = 1;
+    int64_t blocks = (M + (kRedThreads / G) - 1) / (kRedThreads / G);
+    if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "reduce: grid too large");
+    grid = (unsigned)blocks;
+  } else {
+    int64_t target = (int64_t)sms * 8;
+    int64_t S = 1;
+    if (M < target) {
+      S = (target + M - 1) / M;
+      int64_t maxS = (p.chunks + kRedThreads * 4 - 1) / (kRedThreads * 4);  // ≥ 4 chunks per thread
+      if (S > maxS) S = maxS;
+      if (S < 1) S = 1;
+    }
+    p.chunks_per_split = (p.chunks + S - 1) / S;
+    S = (p.chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+    if (S < 1) S = 1;
+    p.S = S;
+    p.G = kRedThreads;
+    if (M * S > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "reduce: grid too large");
+    grid = (unsigned)(M * S);
+    if (S > 1) {
+      HPTB_TRY(scratch.get(plan.ctx, (size_t)(M * S) * sizeof(Acc), stream));
+      tickets = ctx_tickets(plan.ctx, stream, (size_t)M);
+      if (!tickets) return fail(HPTB_ERR_OOM, "reduce: ticket buffer allocation failed");
+    }
+  }
+#define HPTB_LAUNCH_ROWS(V)                                                                                    \
+  do {                                                                                                         \
+    if (small) reduce_rows_kernel<Op, T, V, false><<<grid, kRedThreads, 0, stream>>>(in, out, nullptr, nullptr, p); \
+    else reduce_rows_kernel<Op, T, V, true><<<grid, kRedThreads, 0, stream>>>(in, out, (Acc*)scratch.ptr, tickets, p); \
+  } while (0)
+  if (vec == VECMAX && VECMAX > 1) HPTB_LAUNCH_ROWS(VECMAX);
+  else HPTB_LAUNCH_ROWS(1);
+#undef HPTB_LAUNCH_ROWS
+  HPTB_CUDA_CHECK(cudaGetLastError());
+  return HPTB_OK;
+}
+
+}  // namespace hptb

@@ -1,0 +1,320 @@
+// softmax.cu — softmax / log_softmax along one axis (NormalizationOps::{softmax, log_softmax},
+// hpt-traits/src/ops/normalization.rs:51-64).
+//
+// Replaces `<T>_{softmax,logsoftmax}_{warp,block,block_large}[_uncontiguous]`
+// (hpt-cudakernels/src/normalization/softmax.cu:19-318, f16/f32/f64 only there) and the host code in
+// hpt/src/backends/cuda/tensor_internal/softmax.rs:85-….  Semantics follow the CPU kernel
+// (hpt/src/backends/cpu/kernels/softmax.rs:204-310): y = exp(x − max) / Σ exp(x − max), computed in the
+// Intermediate type of FloatOutUnaryPromote<T> (f32 for f16/bf16/ints ≤ 32 bit, f64 for 64-bit types).
+//
+// Three kernels, picked after the collapse pass:
+//   softmax_rows_reg     axis has unit stride and the row fits in registers (≤ 8 packs per thread):
+//                        one warp (short rows) or one 256-thread CTA per row; ONE read and ONE write
+//                        of the row with 128-bit accesses (the reference's block variant stages the row
+//                        in shared memory and makes three passes over it).
+//   softmax_rows_stream  any axis stride / any length: one CTA per row, online (max, Σ) pass then a
+//                        write pass (two reads, one write).
+//   softmax_cols         axis is strided and another dim is contiguous: one thread per output column,
+//                        lanes along the contiguous dim (coalesced), online pass + write pass.
+#include "context.h"
+#include "dtypes_x.h"
+#include "layout.h"
+#include "promote.h"
+#include "reduce.cuh"
+#include "scalar.cuh"
+
+namespace hptb {
+namespace {
+
+constexpr int kSmThreads = 256;
+constexpr int kSmChunks = 8;
+
+struct SoftmaxParams {
+  DimWalk kept;  // stride_a = input, stride_b = output
+  int64_t M;     // rows
+  int64_t L;     // axis length
+  int64_t sa_in, sa_out;
+  int32_t log;
+  int32_t use64;
+  int32_t nchunks;  // packs per thread (rows_reg)
+  int32_t G;        // threads per row (32 or 256)
+  // cols: the contiguous kept dim is kept.shape[0] with unit strides
+};
+
+template <typename C> __device__ __forceinline__ C sm_exp(C x) {
+  if constexpr (std::is_same<C, float>::value) return expf(x); else return exp(x);
+}
+template <typename C> __device__ __forceinline__ C sm_log(C x) {
+  if constexpr (std::is_same<C, float>::value) return logf(x); else return log(x);
+}
+template <typename C> __device__ __forceinline__ C sm_max(C a, C b) {
+  if constexpr (std::is_same<C, float>::value) return fmaxf(a, b); else return fmax(a, b);
+}
+
+struct MaxOp {
+  template <typename C> static __device__ __forceinline__ C combine(C a, C b) { return sm_max<C>(a, b); }
+};
+struct AddOp {
+  template <typename C> static __device__ __forceinline__ C combine(C a, C b) { return a + b; }
+};
+template <typename OpT, typename C>
+struct WrapOp {
+  static __device__ __forceinline__ C combine(C a, C b) { return OpT::template combine<C>(a, b); }
+};
+
+// reduce over the G threads that own a row (G = 32: warp shuffle; G = 256: + shared memory)
+template <typename OpT, typename C, int G>
+__device__ __forceinline__ C group_reduce(C v, C* s_buf, C ident) {
+  v = warp_reduce<WrapOp<OpT, C>, C>(v, 32);
+  if constexpr (G > 32) {
+    const int tid = threadIdx.x;
+    __syncthreads();  // s_buf reuse
+    if ((tid & 31) == 0) s_buf[tid >> 5] = v;
+    __syncthreads();
+    C r = (tid & 31) < G / 32 ? s_buf[tid & 31] : ident;
+    v = warp_reduce<WrapOp<OpT, C>, C>(r, G / 32);
+  }
+  return v;
+}
+
+template <typename T, int VEC, int G>
+__global__ void __launch_bounds__(kSmThreads)
+softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
+                 SoftmaxParams p) {
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type O;
+  typedef compute_t<O> C;
+  __shared__ C s_buf[kSmThreads / 32];
+  const int tid = threadIdx.x;
+  const int lane = tid & (G - 1);
+  const int64_t row = (int64_t)blockIdx.x * (kSmThreads / G) + tid / G;
+  const bool active = row < p.M;  // whole groups are active or not (G divides the CTA)
+  int64_t in_off = 0, out_off = 0;
+  if (active) walk2(row, p.kept, p.use64, in_off, out_off);
+  const C neg_inf = Limits<C>::lowest();
+  C x[kSmChunks][VEC];
+  C mx = neg_inf;
+#pragma unroll
+  for (int i = 0; i < kSmChunks; ++i) {
+    const int64_t e = ((int64_t)i * G + lane) * VEC;
+    if (i < p.nchunks && active && e < p.L) {
+      Pack<T, VEC> v;
+      load_pack<T, VEC>(v, in + in_off + e);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        x[i][k] = to_compute<O>(cast<O>(v.v[k]));
+        mx = sm_max<C>(mx, x[i][k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) x[i][k] = neg_inf;
+    }
+  }
+  mx = group_reduce<MaxOp, C, G>(mx, s_buf, neg_inf);
+  C sum = (C)0;
+#pragma unroll
+  for (int i = 0; i < kSmChunks; ++i) {
+    if (i < p.nchunks) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const C sh = x[i][k] - mx;
+        const C ex = sm_exp<C>(sh);
+        sum += ex;  // padding lanes: exp(-inf - mx) = 0 (or NaN only if mx itself is -inf/NaN, handled by row)
+        x[i][k] = p.log ? sh : ex;
+      }
+    }
+  }
+  sum = group_reduce<AddOp, C, G>(sum, s_buf, (C)0);
+  const C inv = (C)1 / sum;
+  const C lg = sm_log<C>(sum);
+#pragma unroll
+  for (int i = 0; i < kSmChunks; ++i) {
+    const int64_t e = ((int64_t)i * G + lane) * VEC;
+    if (i < p.nchunks && active && e < p.L) {
+      Pack<O, VEC> o;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(p.log ? x[i][k] - lg : x[i][k] * inv);
+      store_pack<O, VEC>(out + out_off + e, o);
+    }
+  }
+}
+
+// online (max, Σ exp(x − max)) pair
+template <typename C> struct MS {
+  C m, s;
+};
+template <typename C>
+__device__ __forceinline__ MS<C> ms_combine(MS<C> a, MS<C> b) {
+  if (a.s == (C)0) return b;  // identity (also avoids (-inf) - (-inf))
+  if (b.s == (C)0) return a;
+  const C m = sm_max<C>(a.m, b.m);
+  return MS<C>{m, a.s * sm_exp<C>(a.m - m) + b.s * sm_exp<C>(b.m - m)};
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSmThreads)
+softmax_rows_stream(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
+                    SoftmaxParams p) {
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type O;
+  typedef compute_t<O> C;
+  __shared__ C s_m[kSmThreads / 32], s_s[kSmThreads / 32];
+  const int tid = threadIdx.x;
+  for (int64_t row = blockIdx.x; row < p.M; row += gridDim.x) {
+    int64_t in_off = 0, out_off = 0;
+    walk2(row, p.kept, p.use64, in_off, out_off);
+    const T* src = in + in_off;
+    O* dst = out + out_off;
+    MS<C> a{Limits<C>::lowest(), (C)0};
+    for (int64_t e = tid; e < p.L; e += kSmThreads) {
+      const C x = to_compute<O>(cast<O>(load_one(src + e * p.sa_in)));
+      a = ms_combine<C>(a, MS<C>{x, (C)1});
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      MS<C> b{shfl_xor<C>(a.m, off), shfl_xor<C>(a.s, off)};
+      a = (tid & off) == 0 ? ms_combine<C>(a, b) : ms_combine<C>(b, a);
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { s_m[tid >> 5] = a.m; s_s[tid >> 5] = a.s; }
+    __syncthreads();
+    MS<C> r{Limits<C>::lowest(), (C)0};
+    for (int w = 0; w < kSmThreads / 32; ++w) r = ms_combine<C>(r, MS<C>{s_m[w], s_s[w]});
+    const C inv = (C)1 / r.s, lg = sm_log<C>(r.s);
+    for (int64_t e = tid; e < p.L; e += kSmThreads) {
+      const C x = to_compute<O>(cast<O>(src[e * p.sa_in]));
+      const C sh = x - r.m;
+      dst[e * p.sa_out] = from_compute<O>(p.log ? sh - lg : sm_exp<C>(sh) * inv);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSmThreads)
+softmax_cols(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
+             SoftmaxParams p) {
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type O;
+  typedef compute_t<O> C;
+  const int64_t col = (int64_t)blockIdx.x * kSmThreads + threadIdx.x;
+  if (col >= p.M) return;
+  int64_t in_off = 0, out_off = 0;
+  walk2(col, p.kept, p.use64, in_off, out_off);
+  const T* src = in + in_off;
+  O* dst = out + out_off;
+  MS<C> a{Limits<C>::lowest(), (C)0};
+  for (int64_t e = 0; e < p.L; ++e) {
+    const C x = to_compute<O>(cast<O>(load_one(src + e * p.sa_in)));
+    a = ms_combine<C>(a, MS<C>{x, (C)1});
+  }
+  const C inv = (C)1 / a.s, lg = sm_log<C>(a.s);
+  for (int64_t e = 0; e < p.L; ++e) {
+    const C x = to_compute<O>(cast<O>(src[e * p.sa_in]));
+    const C sh = x - a.m;
+    dst[e * p.sa_out] = from_compute<O>(p.log ? sh - lg : sm_exp<C>(sh) * inv);
+  }
+}
+
+template <typename T>
+hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, void* out_v, int log, cudaStream_t stream) {
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type O;
+  const T* in = static_cast<const T*>(in_v);
+  O* out = static_cast<O*>(out_v);
+  SoftmaxParams p;
+  memset(&p, 0, sizeof(p));
+  int ad = -1, kept[kRedMaxDims], nk = 0;
+  for (int d = c.ndim - 1; d >= 0; --d) {
+    if (c.reduced[d]) ad = d; else kept[nk++] = d;
+  }
+  bool big = false;
+  p.log = log;
+  if (ad < 0) { p.L = 1; p.sa_in = 1; p.sa_out = 1; }  // axis of extent 1: softmax = 1, log_softmax = 0
+  else { p.L = c.shape[ad]; p.sa_in = c.strides[1][ad]; p.sa_out = c.strides[0][ad]; }
+  // kept dims: innermost first = smallest |out stride| first (they come sorted by out stride desc)
+  fill_walk(p.kept, c, kept, nk, true, big);
+  int64_t M = 1;
+  for (int i = 0; i < nk; ++i) M *= c.shape[kept[i]];
+  p.M = M;
+  if (M == 0 || p.L == 0) return HPTB_OK;
+  if (!red_fits_u32(M)) big = true;
+  p.use64 = big ? 1 : 0;
+  constexpr int kMinSz = sizeof(T) < sizeof(O) ? sizeof(T) : sizeof(O);
+  constexpr int VECMAX = 16 / kMinSz > 8 ? 8 : 16 / kMinSz;
+  if (p.sa_in == 1 && p.sa_out == 1) {
+    // vector path needs every row start 16 B (pack) aligned in both tensors
+    int vec = VECMAX;
+    auto aligned = [&](int v) {
+      if (v == 1) return true;
+      size_t ai = sizeof(T) * v > 16 ? 16 : sizeof(T) * v, ao = sizeof(O) * v > 16 ? 16 : sizeof(O) * v;
+      if (reinterpret_cast<uintptr_t>(in) % ai || reinterpret_cast<uintptr_t>(out) % ao) return false;
+      if (p.L % v) return false;
+      for (int i = 0; i < nk; ++i) {
+        if ((uint64_t)(std::llabs(c.strides[1][kept[i]]) * (int64_t)sizeof(T)) % ai) return false;
+        if ((uint64_t)(std::llabs(c.strides[0][kept[i]]) * (int64_t)sizeof(O)) % ao) return false;
+      }
+      return true;
+    };
+    if (!aligned(vec)) vec = 1;
+    const int64_t packs = (p.L + vec - 1) / vec;
+    int G = 0;
+    if (packs <= 32 * 4) G = 32;                       // short rows: a warp each, ≤ 4 packs per lane
+    else if (packs <= (int64_t)kSmThreads * kSmChunks) G = kSmThreads;
+    if (G) {
+      p.G = G;
+      p.nchunks = (int)((packs + G - 1) / G);
+      int64_t blocks = (M + (kSmThreads / G) - 1) / (kSmThreads / G);
+      if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "softmax: grid too large");
+      if (vec > 1) {
+        if (G == 32) softmax_rows_reg<T, VECMAX, 32><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
+        else softmax_rows_reg<T, VECMAX, kSmThreads><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
+      } else {
+        if (G == 32) softmax_rows_reg<T, 1, 32><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
+        else softmax_rows_reg<T, 1, kSmThreads><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
+      }
+      HPTB_CUDA_CHECK(cudaGetLastError());
+      return HPTB_OK;
+    }
+  }
+  const bool cols_ok = nk > 0 && c.strides[1][kept[0]] == 1 && c.strides[0][kept[0]] == 1 && !(p.sa_in == 1 && p.sa_out == 1) &&
+                       M >= 32;
+  if (cols_ok) {
+    int64_t blocks = (M + kSmThreads - 1) / kSmThreads;
+    if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "softmax: grid too large");
+    softmax_cols<T><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
+  } else {
+    int64_t blocks = M < (int64_t)ctx->sm_count * 16 ? M : (int64_t)ctx->sm_count * 16;
+    softmax_rows_stream<T><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
+  }
+  HPTB_CUDA_CHECK(cudaGetLastError());
+  return HPTB_OK;
+}
+
+}  // namespace
+}  // namespace hptb
+
+using namespace hptb;
+
+extern "C" hptb_status hptb_softmax(hptb_ctx* ctx, const hptb_tensor* in, int axis, int log, hptb_tensor* out, void* stream) {
+  if (!ctx) return fail(HPTB_ERR_INVALID, "softmax: null ctx");
+  HPTB_TRY(validate_tensor(in, "softmax in"));
+  HPTB_TRY(validate_tensor(out, "softmax out"));
+  if (in->ndim == 0) return fail(HPTB_ERR_AXIS, "softmax: input has no dims");
+  if (axis < 0) axis += in->ndim;
+  if (axis < 0 || axis >= in->ndim) return fail(HPTB_ERR_AXIS, "softmax: axis %d out of range for ndim %d", axis, in->ndim);
+  int odt = kFloatOutUnary[in->dtype];
+  if (out->dtype != odt) return fail(HPTB_ERR_DTYPE, "softmax: out dtype is %s, expected %s", dtype_name(out->dtype), dtype_name(odt));
+  bool same = in->ndim == out->ndim;
+  for (int i = 0; same && i < in->ndim; ++i) same = in->shape[i] == out->shape[i];
+  if (!same) return fail(HPTB_ERR_SHAPE, "softmax: out shape differs from the input shape");
+  uint8_t mask[HPTB_MAX_DIMS] = {0};
+  mask[axis] = 1;
+  int64_t strides[kMaxOperands][HPTB_MAX_DIMS] = {{0}};
+  for (int i = 0; i < in->ndim; ++i) { strides[0][i] = out->strides[i]; strides[1][i] = in->strides[i]; }
+  Collapsed c;
+  collapse(in->ndim, in->shape, 2, strides, mask, &c);
+  DeviceGuard g(ctx->device);
+  switch (in->dtype) {
+#define X(T, N, E) \
+  case E: return launch_softmax<T>(ctx, c, in->data, out->data, log ? 1 : 0, (cudaStream_t)stream);
+    HPTB_FOR_DTYPES(X)
+#undef X
+    default: return fail(HPTB_ERR_DTYPE, "softmax: bad dtype");
+  }
+}

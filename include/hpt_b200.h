@@ -1,0 +1,228 @@
+/*
+ * hpt_b200.h — C ABI of libhpt_b200: a B200 (sm_100a) backend for Hpt's data-parallel hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one place where the
+ * reference's Rust host code looks up a PTX kernel by string name and launches it through cudarc
+ * (`load_ptx_and_get_data` + `CudaFunction::launch`, hpt/src/backends/cuda/cuda_utils.rs:71-129).
+ * The Rust shim (rust/hpt-b200-sys, delivered as source) binds these symbols 1:1; the Python
+ * host mirror (hpt_b200/) binds them through ctypes.  Reference file:line for each entry is
+ * given next to its declaration.  All paths below are relative to the Hpt repository root.
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, enums; no C++ types and no exceptions cross this boundary.
+ *  - every call returns hptb_status (0 = ok); the message for the last failure on the calling
+ *    thread is available from hptb_last_error().  Nothing aborts or panics.
+ *  - every compute call is asynchronous and ordered on `stream` (a cudaStream_t passed as
+ *    void*; NULL = the legacy default stream, which is what cudarc 0.13's CudaDevice uses).
+ *  - the caller owns every tensor buffer, including `out` (mirrors `extract_out`,
+ *    hpt/src/backends/cuda/utils/binary/binary_normal.rs:546-564); scratch is library-owned and
+ *    comes from the context's stream-ordered pool.
+ *  - strides are in ELEMENTS (as in hpt-common Layout), may be 0 (broadcast) or negative.
+ *  - sizes and indices are 64-bit throughout (the reference is i32-limited,
+ *    hpt/src/backends/cuda/tensor_internal/normal_creation.rs:41-43).
+ */
+#ifndef HPT_B200_H
+#define HPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define HPTB_MAX_DIMS 8
+#define HPTB_VERSION 100
+
+/* Status codes.  Map to hpt-common/src/error/{shape,param,kernel,device,memory}.rs on the Rust side. */
+typedef enum {
+  HPTB_OK = 0,
+  HPTB_ERR_SHAPE = 1,       /* ShapeError: broadcast mismatch, out layout invalid, size mismatch */
+  HPTB_ERR_DTYPE = 2,       /* unsupported dtype / op combination (reference: kernel lookup miss → KernelError) */
+  HPTB_ERR_AXIS = 3,        /* ParamError::AxisDuplicated / ShapeError::DimOutOfRange (axis.rs:38-72) */
+  HPTB_ERR_INVALID = 4,     /* null pointers, bad enum values, ndim > HPTB_MAX_DIMS */
+  HPTB_ERR_CUDA = 5,        /* DeviceError: a CUDA runtime call failed (message carries the code) */
+  HPTB_ERR_OOM = 6,         /* MemoryError: device allocation failed even after emptying the cache */
+  HPTB_ERR_NCCL = 7,        /* collective failed / NCCL unavailable */
+  HPTB_ERR_UNSUPPORTED = 8  /* valid request the library does not implement yet */
+} hptb_status;
+
+/* Dtype order follows hpt-types/src/dtype.rs (bool, i8..u64, f16, bf16, f32, f64). */
+typedef enum {
+  HPTB_BOOL = 0, HPTB_I8 = 1, HPTB_I16 = 2, HPTB_I32 = 3, HPTB_I64 = 4,
+  HPTB_U8 = 5, HPTB_U16 = 6, HPTB_U32 = 7, HPTB_U64 = 8,
+  HPTB_F16 = 9, HPTB_BF16 = 10, HPTB_F32 = 11, HPTB_F64 = 12,
+  HPTB_DTYPE_COUNT = 13
+} hptb_dtype;
+
+/* A strided view of device memory: the C image of `_Tensor{data, layout}` (hpt/src/tensor_base.rs:17-29).
+ * `data` already points at the first logical element (as Hpt's `Pointer<T>` does after slicing). */
+typedef struct {
+  void* data;
+  int32_t dtype;                  /* hptb_dtype */
+  int32_t ndim;                   /* 0..HPTB_MAX_DIMS; ndim 0 = one element */
+  int64_t shape[HPTB_MAX_DIMS];
+  int64_t strides[HPTB_MAX_DIMS]; /* elements */
+} hptb_tensor;
+
+/* Binary ops.  ADD..REM replace `{add,sub,mul,rem}_<L>_<R>_{contiguous,uncontiguous,*_scalar}`
+ * (hpt-cudakernels/src/binary/binary_template.cuh:107-138) called from binary_fn_precompiled
+ * (hpt/src/backends/cuda/utils/binary/binary_normal.rs:371-544).  Output dtype NormalOutPromote<L,R>.
+ * DIV is FloatBinOps::div_ (hpt-traits/src/ops/binary.rs:149), output FloatOutBinaryPromote<L,R>.
+ * MAX/MIN are NormalOut::_max/_min (hpt-macros/src/normal_out.rs:121-133). */
+typedef enum {
+  HPTB_ADD = 0, HPTB_SUB = 1, HPTB_MUL = 2, HPTB_REM = 3, HPTB_DIV = 4, HPTB_MAXIMUM = 5, HPTB_MINIMUM = 6,
+  HPTB_BINARY_COUNT = 7
+} hptb_binary_op;
+
+/* FloatUnaryOps (hpt-traits/src/ops/unary.rs:8-608); replaces `<op>_<T>_{contiguous,uncontiguous}`
+ * (hpt-cudakernels/src/unary/unary_template.cuh:65-75) called from uary_fn_precompiled
+ * (hpt/src/backends/cuda/utils/unary/unary.rs:122-196).  Output dtype FloatOutUnaryPromote<T>. */
+typedef enum {
+  HPTB_SIN = 0, HPTB_COS, HPTB_TAN, HPTB_ASIN, HPTB_ACOS, HPTB_ATAN,
+  HPTB_SINH, HPTB_COSH, HPTB_TANH, HPTB_ASINH, HPTB_ACOSH, HPTB_ATANH,
+  HPTB_EXP, HPTB_EXP2, HPTB_EXP10, HPTB_LN, HPTB_LOG2, HPTB_LOG10,
+  HPTB_SQRT, HPTB_CBRT, HPTB_RECIP, HPTB_ERF,
+  HPTB_SIGMOID, HPTB_GELU, HPTB_SELU /* alpha, beta=scale */, HPTB_ELU /* alpha */, HPTB_CELU /* alpha */,
+  HPTB_MISH, HPTB_SOFTPLUS, HPTB_SOFTSIGN, HPTB_HARD_SIGMOID, HPTB_HARD_SWISH,
+  HPTB_UNARY_COUNT
+} hptb_unary_op;
+
+/* Reductions: NormalReduce / FloatReduce / IndexReduce (hpt-traits/src/ops/reduce.rs:6-358); replaces
+ * the 8-kernel-per-op families of hpt-cudakernels/src/reduce/declare_macros.cuh:48-326 chosen by
+ * hpt/src/backends/cuda/utils/reduce/reduce.rs:62-838.
+ * Output dtypes: SUM/MAX/MIN/PROD/SUM_SQUARE = T; MEAN/LOGSUMEXP = FloatOutBinaryPromote<T,T>;
+ * ARGMAX/ARGMIN = i64 (exactly one axis). */
+typedef enum {
+  HPTB_SUM = 0, HPTB_MEAN = 1, HPTB_MAX = 2, HPTB_MIN = 3, HPTB_ARGMAX = 4, HPTB_ARGMIN = 5,
+  HPTB_LOGSUMEXP = 6, HPTB_SUM_SQUARE = 7, HPTB_PROD = 8,
+  HPTB_REDUCE_COUNT = 9
+} hptb_reduce_op;
+
+typedef enum {
+  HPTB_PROMOTE_NORMAL = 0,        /* NormalOutPromote<L,R>::Output        (hpt-types/src/promotion/normal_promote/_*.rs) */
+  HPTB_PROMOTE_FLOAT_BINARY = 1,  /* FloatOutBinaryPromote<L,R>::Output */
+  HPTB_PROMOTE_FLOAT_UNARY = 2    /* FloatOutUnaryPromote<L>::Output (rhs ignored) */
+} hptb_promote_kind;
+
+typedef struct hptb_ctx hptb_ctx;    /* one per (process, device): stream-ordered pool + scratch */
+typedef struct hptb_comm hptb_comm;  /* one NCCL rank */
+
+/* ---- library / context --------------------------------------------------------------------- */
+int hptb_version(void);
+const char* hptb_last_error(void);   /* thread-local, valid until the next failing call on this thread */
+size_t hptb_dtype_size(int dtype);
+const char* hptb_dtype_name(int dtype);
+
+/* Replaces `CudaDevice::new(id)` + per-device LRU creation (hpt-allocator/src/allocators/cuda.rs:50-69). */
+hptb_status hptb_ctx_create(int device, hptb_ctx** out);
+hptb_status hptb_ctx_destroy(hptb_ctx* ctx);
+hptb_status hptb_ctx_device(const hptb_ctx* ctx, int* device);
+hptb_status hptb_ctx_sm_count(const hptb_ctx* ctx, int* sms);
+hptb_status hptb_stream_sync(hptb_ctx* ctx, void* stream);
+
+/* ---- allocator: replaces HptAllocator<Cuda> (hpt-allocator/src/allocators/cuda.rs:41-199,
+ *      utils/allocate.rs:66-124, utils/deallocate.rs:11-32) with a stream-ordered caching pool ------- */
+hptb_status hptb_alloc(hptb_ctx* ctx, size_t bytes, void** ptr, void* stream);
+hptb_status hptb_free(hptb_ctx* ctx, void* ptr, void* stream);
+hptb_status hptb_empty_cache(hptb_ctx* ctx);              /* resize_cuda_lru_cache(0) analogue, hpt/src/lib.rs:441-511 */
+typedef struct {
+  uint64_t bytes_in_use, bytes_cached, bytes_reserved_peak;
+  uint64_t n_alloc, n_cache_hit, n_device_malloc, n_device_free;
+} hptb_alloc_stats;
+hptb_status hptb_alloc_get_stats(hptb_ctx* ctx, hptb_alloc_stats* out);
+/* host-only self test of the caching logic against a fake device (runs without a GPU). */
+hptb_status hptb_alloc_selftest(void);
+
+/* ---- transfers: to_cuda / to_cpu (hpt/src/backends/cpu/tensor_impls.rs:295-313,
+ *      hpt/src/backends/cuda/tensor_impls.rs:142-169) ------------------------------------------------ */
+hptb_status hptb_memcpy_h2d(hptb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, void* stream);
+hptb_status hptb_memcpy_d2h(hptb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes, void* stream);
+hptb_status hptb_memcpy_d2d(hptb_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+hptb_status hptb_host_alloc_pinned(size_t bytes, void** ptr);
+hptb_status hptb_host_free_pinned(void* ptr);
+
+/* ---- type promotion and layout helpers (pure host; usable without a GPU) ------------------------------ */
+/* Returns the promoted dtype or -1.  Tables restated from hpt-types/src/promotion/normal_promote/_*.rs. */
+int hptb_promote(int lhs, int rhs, int kind);
+int hptb_binary_out_dtype(int op, int lhs, int rhs);
+int hptb_unary_out_dtype(int op, int in);
+int hptb_reduce_out_dtype(int op, int in);
+/* numpy-style broadcast of two shapes (hpt-common/src/shape/shape_utils.rs:370-400). */
+hptb_status hptb_broadcast_shape(const int64_t* a, int na, const int64_t* b, int nb, int64_t* out, int* nout);
+/* process_axes (hpt-common/src/axis/axis.rs:38-72): normalises negatives, rejects duplicates / out of range. */
+hptb_status hptb_process_axes(const int64_t* axes, int naxes, int ndim, int32_t* out);
+/* Layout::reduce (hpt-common/src/layout/layout_utils.rs:310-349): output shape; all axes reduced → [1]. */
+hptb_status hptb_reduce_shape(const int64_t* shape, int ndim, const int32_t* axes, int naxes, int keep_dims,
+                              int64_t* out_shape, int* out_ndim);
+
+/* The shape/stride collapse + broadcast-folding pass, exposed for inspection and tests.
+ * operands[0] is the output.  `reduce_mask` (may be NULL) flags reduced dims.  On return `plan` holds
+ * the collapsed dims (outermost first) with per-operand strides and the launch class. */
+typedef enum { HPTB_CLASS_CONTIGUOUS = 0, HPTB_CLASS_INNER_CONTIGUOUS = 1, HPTB_CLASS_STRIDED = 2 } hptb_launch_class;
+typedef struct {
+  int32_t ndim;
+  int32_t launch_class;
+  int32_t n_operands;
+  int32_t reserved;
+  int64_t shape[HPTB_MAX_DIMS];
+  int64_t strides[4][HPTB_MAX_DIMS];
+  uint8_t reduced[HPTB_MAX_DIMS];
+} hptb_collapse_plan;
+hptb_status hptb_collapse(const hptb_tensor* const* operands, int n_operands, const uint8_t* reduce_mask,
+                          hptb_collapse_plan* plan);
+
+/* ---- compute entry points ------------------------------------------------------------------------------- */
+/* out = op(cast(lhs), cast(rhs)) with numpy broadcasting.  `out->dtype` must equal
+ * hptb_binary_out_dtype(op, lhs, rhs) and `out->shape` the broadcast shape; any strides. */
+hptb_status hptb_binary(hptb_ctx* ctx, int op, const hptb_tensor* lhs, const hptb_tensor* rhs,
+                        hptb_tensor* out, void* stream);
+/* out = op(cast(in)); alpha/beta only for ELU/CELU (alpha) and SELU (alpha, scale). */
+hptb_status hptb_unary(hptb_ctx* ctx, int op, const hptb_tensor* in, hptb_tensor* out,
+                       double alpha, double beta, void* stream);
+/* Reduce `in` over `axes` (already normalised, unique).  `out` has the keep_dims=false shape
+ * (or [1] when every axis is reduced) and may carry any strides.  init_out follows reduce_prepare
+ * (hpt/src/backends/cpu/utils/reduce/reduce_utils.rs:46-50): non-zero = `out` is initialised to the
+ * identity first, i.e. it receives the plain result; zero = the previous contents of `out` are folded
+ * into the result with the op's combine (sum_ accumulating into an existing buffer).  Pass 1 for a
+ * freshly allocated output. */
+hptb_status hptb_reduce(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes,
+                        hptb_tensor* out, int init_out, void* stream);
+/* Fused single-read mean + variance (population, ddof = 0) — an EXTENSION: Hpt has no `var`
+ * (SURVEY.md §8a row a7); both outputs have dtype FloatOutBinaryPromote<T,T>. */
+hptb_status hptb_mean_var(hptb_ctx* ctx, const hptb_tensor* in, const int32_t* axes, int naxes,
+                          hptb_tensor* mean_out, hptb_tensor* var_out, void* stream);
+/* softmax / log_softmax along one axis (NormalizationOps, hpt-traits/src/ops/normalization.rs:51-64);
+ * replaces `<T>_{softmax,logsoftmax}_{warp,block,block_large}` (hpt-cudakernels/src/normalization/softmax.cu). */
+hptb_status hptb_softmax(hptb_ctx* ctx, const hptb_tensor* in, int axis, int log, hptb_tensor* out, void* stream);
+/* Gather a view into another layout with optional dtype conversion (Rust `as` semantics):
+ * replaces strided_copy_<T> (hpt-cudakernels/src/strided_copy.cu) used by contiguous()/to_cpu. */
+hptb_status hptb_copy(hptb_ctx* ctx, const hptb_tensor* in, hptb_tensor* out, void* stream);
+/* out[...] = *scalar (scalar has out's dtype, host memory): replaces set_val_<T> / fill_<T>. */
+hptb_status hptb_fill(hptb_ctx* ctx, hptb_tensor* out, const void* scalar, void* stream);
+
+/* ---- multi-GPU (new: the reference has no collectives) ---------------------------------- */
+#define HPTB_NCCL_ID_BYTES 128
+hptb_status hptb_comm_unique_id(void* id128);                          /* rank 0, then broadcast out of band */
+hptb_status hptb_comm_init_rank(hptb_ctx* ctx, int nranks, int rank, const void* id128, hptb_comm** out);
+hptb_status hptb_comm_destroy(hptb_comm* comm);
+/* Combine per-rank partials in place.  op = HPTB_SUM / HPTB_MAX / HPTB_MIN / HPTB_PROD. */
+hptb_status hptb_allreduce(hptb_comm* comm, int op, hptb_tensor* inout, void* stream);
+/* Reduction of a tensor sharded along axis `shard_axis` (each rank passes its own shard).  Reduces
+ * locally, then — only if shard_axis is among `axes` — exchanges partials over NCCL and applies the
+ * post-op (÷ global count for MEAN, log for LOGSUMEXP, lowest global index for ARGMAX/ARGMIN).
+ * `global_axis_len` is the full length of the sharded axis, `shard_offset` this rank's start. */
+hptb_status hptb_reduce_sharded(hptb_comm* comm, int op, const hptb_tensor* shard, const int32_t* axes,
+                                int naxes, int shard_axis, int64_t shard_offset, int64_t global_axis_len,
+                                hptb_tensor* out, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPT_B200_H */

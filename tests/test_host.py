@@ -1,0 +1,188 @@
+"""CPU-only checks of the C ABI surface: the library loads, exports every symbol include/hpt_b200.h
+declares, and its pure-host helpers (promotion, broadcasting, axes, collapse, allocator logic) agree
+with the reference's golden data.  No compute calls: there is no GPU here."""
+import ctypes
+import json
+import os
+import re
+from ctypes import byref, c_int, c_int32, c_int64, c_uint8, POINTER
+
+import pytest
+
+from util import DTYPES, ENUM, ROOT
+
+from hpt_b200 import _ffi
+from hpt_b200._ffi import HptbCollapsePlan, HptbTensor, HptError, check, lib, make_tensor
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "hpt_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(hptb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"symbols declared in the header but not exported: {missing}"
+    # and the ctypes table covers exactly the header
+    assert set(_ffi.SIGNATURES) == declared, set(_ffi.SIGNATURES) ^ declared
+    assert not _ffi.MISSING
+
+
+def test_version_and_dtype_sizes():
+    assert lib.hptb_version() == 100
+    for i, n in enumerate(DTYPES):
+        assert lib.hptb_dtype_name(i).decode() == n
+        assert lib.hptb_dtype_size(i) == _ffi.DTYPE_SIZES[i]
+
+
+def test_promotion_tables_match_reference_golden():
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "promotion.json")))
+    for a in DTYPES:
+        assert DTYPES[lib.hptb_promote(ENUM[a], 0, 2)] == g["float_out_unary"][a]
+        for b in DTYPES:
+            assert DTYPES[lib.hptb_promote(ENUM[a], ENUM[b], 0)] == g["normal_out"][a][b], (a, b)
+            assert DTYPES[lib.hptb_promote(ENUM[a], ENUM[b], 1)] == g["float_out_binary"][a][b], (a, b)
+    # the asymmetry called out in SURVEY.md §8c
+    assert DTYPES[lib.hptb_promote(ENUM["i32"], ENUM["f16"], 0)] == "f16"
+    assert DTYPES[lib.hptb_promote(ENUM["f16"], ENUM["i32"], 0)] == "f32"
+    assert DTYPES[lib.hptb_promote(ENUM["f32"], ENUM["i64"], 0)] == "f64"  # config 4
+    assert lib.hptb_promote(13, 0, 0) == -1
+
+
+def test_out_dtype_helpers():
+    assert lib.hptb_binary_out_dtype(_ffi.BINARY_OPS["add"], ENUM["bool"], ENUM["bool"]) == ENUM["bool"]
+    assert lib.hptb_binary_out_dtype(_ffi.BINARY_OPS["sub"], ENUM["bool"], ENUM["bool"]) == -1  # _bool.rs:31 panics
+    assert lib.hptb_binary_out_dtype(_ffi.BINARY_OPS["div"], ENUM["i32"], ENUM["i32"]) == ENUM["f32"]
+    assert lib.hptb_unary_out_dtype(_ffi.UNARY_OPS["sin"], ENUM["i64"]) == ENUM["f64"]
+    assert lib.hptb_reduce_out_dtype(_ffi.REDUCE_OPS["mean"], ENUM["bf16"]) == ENUM["bf16"]
+    assert lib.hptb_reduce_out_dtype(_ffi.REDUCE_OPS["mean"], ENUM["i32"]) == ENUM["f32"]
+    assert lib.hptb_reduce_out_dtype(_ffi.REDUCE_OPS["argmax"], ENUM["f32"]) == ENUM["i64"]
+    assert lib.hptb_reduce_out_dtype(_ffi.REDUCE_OPS["sum"], ENUM["u8"]) == ENUM["u8"]
+
+
+def _bshape(a, b):
+    out = (c_int64 * 8)()
+    n = c_int()
+    check(lib.hptb_broadcast_shape((c_int64 * max(len(a), 1))(*a), len(a), (c_int64 * max(len(b), 1))(*b), len(b), out, byref(n)))
+    return [out[i] for i in range(n.value)]
+
+
+def test_broadcast_shape_reference_vectors():
+    # hpt-tests/src/hpt_common/layout.rs:23-40
+    assert _bshape([5, 2, 10], [5, 1, 10]) == [5, 2, 10]
+    with pytest.raises(HptError) as e:
+        _bshape([5, 2, 10], [5, 1, 11])
+    assert "Broadcasting error: broadcast failed at index 2, lhs shape: [5, 2, 10], rhs shape: [5, 1, 11]" in str(e.value)
+    assert e.value.status == 1
+    assert _bshape([4096, 4096], [1, 4096]) == [4096, 4096]
+    assert _bshape([32, 128, 4096], [4096]) == [32, 128, 4096]
+    assert _bshape([1, 100, 1, 100], [100, 1, 100, 1]) == [100, 100, 100, 100]  # docs/benchmarks/binary.md
+    assert _bshape([], [3]) == [3]
+
+
+def _axes(axes, ndim):
+    out = (c_int32 * max(len(axes), 1))()
+    check(lib.hptb_process_axes((c_int64 * max(len(axes), 1))(*axes), len(axes), ndim, out))
+    return [out[i] for i in range(len(axes))]
+
+
+def test_process_axes_reference_vectors():
+    # hpt-tests/src/hpt_common/axis.rs:6-50
+    assert _axes([-1], 2) == [1]
+    with pytest.raises(HptError) as e:
+        _axes([10], 2)
+    assert "Dimension out of range: expected in 0..2, got 10" in str(e.value)
+    with pytest.raises(HptError) as e:
+        _axes([-3], 2)
+    assert "Dimension out of range: expected in 0..2, got -1" in str(e.value)
+    with pytest.raises(HptError) as e:
+        _axes([1, 1], 3)
+    assert "Axis 1 is duplicated" in str(e.value) and e.value.status == 3
+    assert _axes([0, -1], 3) == [0, 2]
+
+
+def test_reduce_shape():
+    def rs(shape, axes, keep):
+        out = (c_int64 * 8)()
+        n = c_int()
+        check(lib.hptb_reduce_shape((c_int64 * len(shape))(*shape), len(shape), (c_int32 * max(len(axes), 1))(*axes), len(axes),
+                                    keep, out, byref(n)))
+        return [out[i] for i in range(n.value)]
+    assert rs([4, 5, 6], [1], 0) == [4, 6]
+    assert rs([4, 5, 6], [1], 1) == [4, 1, 6]
+    assert rs([4, 5, 6], [0, 1, 2], 0) == [1]  # layout_utils.rs:342-347: never rank 0
+    assert rs([4, 5, 6], [0, 1, 2], 1) == [1, 1, 1]
+
+
+def _collapse(ops, mask=None):
+    ts = [make_tensor(0x1000, ENUM["f32"], s, st) for s, st in ops]
+    arr = (POINTER(HptbTensor) * len(ts))(*[ctypes.pointer(t) for t in ts])
+    plan = HptbCollapsePlan()
+    m = (c_uint8 * 8)(*mask) if mask is not None else None
+    check(lib.hptb_collapse(arr, len(ts), m, byref(plan)))
+    nd = plan.ndim
+    return (plan.launch_class, [plan.shape[i] for i in range(nd)],
+            [[plan.strides[o][i] for i in range(nd)] for o in range(len(ts))], [plan.reduced[i] for i in range(nd)])
+
+
+def test_collapse_elementwise_classes():
+    C, I, S = 0, 1, 2
+    # same-shape contiguous: one dim
+    cls, shape, st, _ = _collapse([((4096, 4096), (4096, 1))] * 3)
+    assert (cls, shape, st) == (C, [4096 * 4096], [[1], [1], [1]])
+    # config 1: [4096,4096] + [1,4096] → inner-contiguous, rhs outer stride 0
+    cls, shape, st, _ = _collapse([((4096, 4096), (4096, 1)), ((4096, 4096), (4096, 1)), ((1, 4096), (4096, 1))])
+    assert (cls, shape, st) == (I, [4096, 4096], [[4096, 1], [4096, 1], [0, 1]])
+    # scalar operand: everything folds to one dim, stride 0
+    cls, shape, st, _ = _collapse([((8, 16), (16, 1)), ((8, 16), (16, 1)), ((1,), (1,))])
+    assert (cls, shape, st) == (C, [128], [[1], [1], [0]])
+    # config 4: [32,128,4096] + [4096] → outer dims merge
+    cls, shape, st, _ = _collapse([((32, 128, 4096), (524288, 4096, 1)), ((32, 128, 4096), (524288, 4096, 1)), ((4096,), (1,))])
+    assert (cls, shape, st) == (I, [4096, 4096], [[4096, 1], [4096, 1], [0, 1]])
+    # config 2: transposed input → strided
+    cls, shape, st, _ = _collapse([((8192, 8192), (8192, 1)), ((8192, 8192), (1, 8192))])
+    assert (cls, shape, st) == (S, [8192, 8192], [[8192, 1], [1, 8192]])
+    # the reference's broadcast benchmark [1,100,1,100] + [100,1,100,1]
+    cls, shape, st, _ = _collapse([((100, 100, 100, 100), (1000000, 10000, 100, 1)), ((1, 100, 1, 100), (10000, 100, 100, 1)),
+                                   ((100, 1, 100, 1), (100, 100, 1, 1))])
+    assert cls == I and shape == [100, 100, 100, 100]  # inner dim: lhs stride 1, rhs broadcast (stride 0)
+    assert st[1] == [0, 100, 0, 1] and st[2] == [100, 0, 1, 0]
+    # size-1 dims vanish, sliced-with-step inner dim is strided
+    cls, shape, st, _ = _collapse([((1, 6, 1, 5), (30, 5, 5, 1)), ((1, 6, 1, 5), (120, 20, 20, 2))])
+    assert (cls, shape, st) == (S, [6, 5], [[5, 1], [20, 2]])
+    # Layout::coalesce_dims example: fully contiguous 3-D → 1 dim
+    cls, shape, st, _ = _collapse([((2, 5, 10), (50, 10, 1)), ((2, 5, 10), (50, 10, 1))])
+    assert (cls, shape) == (C, [100])
+
+
+def test_collapse_reduce():
+    # config 3: NCHW viewed NHWC, reduce view axes (0,1,2) → kept C, reduced (N, HW merged)
+    _, shape, st, red = _collapse([((512,), (1,)), ((64, 56, 56, 512), (1605632, 56, 1, 3136))], mask=[1, 1, 1, 0])
+    assert shape == [512, 64, 3136] and red == [0, 1, 1]
+    assert st[1] == [3136, 1605632, 1] and st[0] == [1, 0, 0]
+    # config 2: transposed view, reduce view axis 0 (the unit-stride one)
+    _, shape, st, red = _collapse([((8192,), (1,)), ((8192, 8192), (1, 8192))], mask=[1, 0])
+    assert shape == [8192, 8192] and red == [0, 1] and st[1] == [8192, 1]
+    # full reduce of a contiguous tensor: one reduced dim
+    _, shape, st, red = _collapse([((1,), (1,)), ((262144, 16384), (16384, 1))], mask=[1, 1])
+    assert shape == [262144 * 16384] and red == [1]
+    # axis-0 reduce keeps the contiguous dim
+    _, shape, st, red = _collapse([((16384,), (1,)), ((262144, 16384), (16384, 1))], mask=[1, 0])
+    assert shape == [16384, 262144] and red == [0, 1] and st[1] == [1, 16384]
+    # two kept dims around a reduced one do not merge; 1024×1024×80 axis 1 (docs/benchmarks/reduce.md)
+    _, shape, st, red = _collapse([((1024, 80), (80, 1)), ((1024, 1024, 80), (81920, 80, 1))], mask=[0, 1, 0])
+    assert shape == [1024, 80, 1024] and red == [0, 0, 1]
+
+
+def test_alloc_selftest_fake_device():
+    check(lib.hptb_alloc_selftest())
+
+
+def test_errors_without_gpu():
+    h = ctypes.c_void_p()
+    st = lib.hptb_ctx_create(0, byref(h))
+    import torch
+    if not torch.cuda.is_available():
+        assert st == 5 and b"cuda" in lib.hptb_last_error().lower()  # DeviceError, not a crash
+    t = make_tensor(0, ENUM["f32"], (2, 2), (2, 1))
+    assert lib.hptb_binary(None, 0, byref(t), byref(t), byref(t), None) == 4
+    assert b"null ctx" in lib.hptb_last_error()
