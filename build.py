@@ -32,7 +32,7 @@ UNARY_OPS = ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh"
 REDUCE_OPS = ["sum", "mean", "max", "min", "argmax", "argmin", "logsumexp", "sum_square", "prod"]
 
 NVCC_FLAGS = ("-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr "
-              "-Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xcudafe --diag_suppress=177 "
+              "-Xfatbin -compress-all -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xcudafe --diag_suppress=177 "
               "-Xcudafe --diag_suppress=550 -I%s" % os.path.join(ROOT, "include"))
 CXX_FLAGS = "-O2 -std=c++17 -fPIC -fvisibility=hidden -I/usr/local/cuda/include -I%s" % os.path.join(ROOT, "include")
 
@@ -113,7 +113,7 @@ def build_oracle():
     # x86-64-v3 (AVX2+FMA) rather than -march=native: the .so travels to the GPU box, whose host
     # CPU may differ from the build container's.
     cmd = ["g++", "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-march=x86-64-v3", "-ffp-contract=off",
-           "-o", out, src]
+           "-fno-math-errno", "-o", out, src, "-lmvec", "-lm"]
     subprocess.check_call(cmd)
     return out
 

@@ -63,6 +63,7 @@ class HptError(RuntimeError):
 _T = POINTER(HptbTensor)
 SIGNATURES = {
     "hptb_version": (c_int, []),
+    "hptb_kernel_launches": (c_uint64, []),
     "hptb_last_error": (c_char_p, []),
     "hptb_dtype_size": (c_size_t, [c_int]),
     "hptb_dtype_name": (c_char_p, [c_int]),

@@ -107,7 +107,9 @@ static hptb_status run_map(hptb_ctx* ctx, MapLauncher fn, hptb_tensor* out, cons
   plan.beta = beta;
   plan.sm_count = ctx->sm_count;
   DeviceGuard g(ctx->device);
-  return fn(plan, (cudaStream_t)stream);
+  hptb_status st = fn(plan, (cudaStream_t)stream);
+  if (st == HPTB_OK && plan.c.numel > 0) count_launches(1);
+  return st;
 }
 
 }  // namespace hptb

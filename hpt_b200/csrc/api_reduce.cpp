@@ -183,6 +183,8 @@ hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int3
   plan.fold_out = init_out ? 0 : 1;
   if (count_override > 0) plan.count = count_override;  // sharded mean: divide the local Σ by the GLOBAL count
   DeviceGuard g(ctx->device);
-  return fn(plan, (cudaStream_t)stream);
+  hptb_status st = fn(plan, (cudaStream_t)stream);
+  if (st == HPTB_OK) count_launches(1);
+  return st;
 }
 }  // namespace hptb

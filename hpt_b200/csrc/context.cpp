@@ -1,11 +1,13 @@
 #include "context.h"
 #include "reduce_plan.h"
 
+#include <atomic>
 #include <cstdlib>
 #include <new>
 
 namespace hptb {
 
+uint64_t launches();
 static thread_local char g_err[1024] = "";
 
 void set_error(const char* fmt, ...) {
@@ -22,6 +24,10 @@ hptb_status fail(hptb_status st, const char* fmt, ...) {
   return st;
 }
 const char* last_error() { return g_err; }
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+uint64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 
 const char* dtype_name(int dt) {
   static const char* names[] = {"bool", "i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "f16", "bf16", "f32", "f64"};
@@ -125,6 +131,7 @@ using namespace hptb;
 extern "C" {
 
 int hptb_version(void) { return HPTB_VERSION; }
+uint64_t hptb_kernel_launches(void) { return launches(); }
 const char* hptb_last_error(void) { return last_error(); }
 size_t hptb_dtype_size(int dtype) { return dtype_size(dtype); }
 const char* hptb_dtype_name(int dtype) { return dtype_name(dtype); }

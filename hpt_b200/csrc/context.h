@@ -15,6 +15,8 @@ struct hptb_ctx {
 };
 
 namespace hptb {
+// number of device kernels launched by this library in this process (evidence for bench.py's gpu_launches)
+void count_launches(int n);
 // RAII device scratch from the context's pool, returned to the pool on the same stream.
 struct Scratch {
   hptb_ctx* ctx = nullptr;

@@ -114,7 +114,9 @@ map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restric
       } else if (cnt[u] == VEC) {
         load_pack<A, VEC>(pa[u], ap);
       } else {
-        for (int k = 0; k < cnt[u]; ++k) pa[u].v[k] = ap[k];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          if (k < cnt[u]) pa[u].v[k] = ap[k];
       }
       if constexpr (NIN == 2) {
         const B* bp = b + off[2] + e * p.inner_stride[2];
@@ -125,7 +127,9 @@ map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restric
         } else if (cnt[u] == VEC) {
           load_pack<B, VEC>(pb[u], bp);
         } else {
-          for (int k = 0; k < cnt[u]; ++k) pb[u].v[k] = bp[k];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k)
+            if (k < cnt[u]) pb[u].v[k] = bp[k];
         }
       }
     }
@@ -140,8 +144,11 @@ map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restric
       else po.v[k] = f(pa[u].v[k]);
     }
     if (cnt[u] == VEC) store_pack<O, VEC>(out + oo[u], po);
-    else
-      for (int k = 0; k < cnt[u]; ++k) out[oo[u] + k] = po.v[k];
+    else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        if (k < cnt[u]) out[oo[u] + k] = po.v[k];
+    }
   }
 }
 

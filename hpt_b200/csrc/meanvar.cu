@@ -94,6 +94,7 @@ extern "C" hptb_status hptb_mean_var(hptb_ctx* ctx, const hptb_tensor* in, const
     default: break;
   }
   HPTB_TRY(st);
+  count_launches(1);
   // de-interleave into the caller's tensors (any strides) with the strided copy kernels
   MapLauncher (*getter)(int) = odt == HPTB_F16 ? hptb_cast_f16 : odt == HPTB_BF16 ? hptb_cast_bf16 : odt == HPTB_F32 ? hptb_cast_f32 : hptb_cast_f64;
   MapLauncher copy = getter ? getter(odt) : nullptr;
@@ -108,6 +109,7 @@ extern "C" hptb_status hptb_mean_var(hptb_ctx* ctx, const hptb_tensor* in, const
     mp.ptr[1] = static_cast<char*>(pairs.ptr) + which * osz;
     mp.sm_count = ctx->sm_count;
     HPTB_TRY(copy(mp, s));
+    count_launches(1);
   }
   return HPTB_OK;
 }

@@ -59,6 +59,7 @@ hptb_status fill_impl(hptb_ctx* ctx, const Collapsed& c, void* out, const void* 
     fill_strided_kernel<U><<<(unsigned)blocks, 256, 0, stream>>>(static_cast<U*>(out), v, n, w, big ? 1 : 0);
   }
   HPTB_CUDA_CHECK(cudaGetLastError());
+  count_launches(1);
   return HPTB_OK;
 }
 

@@ -386,8 +386,11 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
           e0[u] = e;
           const T* src = base + roff + e * p.inner_stride;
           if (VEC > 1 && cnt[u] == VEC) load_pack<T, VEC>(v[u], src);
-          else
-            for (int k = 0; k < cnt[u]; ++k) v[u].v[k] = load_one(src + k * p.inner_stride);
+          else {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+              if (k < cnt[u]) v[u].v[k] = load_one(src + k * p.inner_stride);
+          }
         }
       }
 #pragma unroll
@@ -494,8 +497,11 @@ reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
           if (p.red.n == 1) roff = ru * p.red.stride_a[0];
           else walk2(ru, p.red, p.use64, roff, dummy);
           if (VEC > 1 && ncol == VEC) load_pack<T, VEC>(v[u], base + roff);
-          else
-            for (int j = 0; j < ncol; ++j) v[u].v[j] = load_one(base + roff + j);
+          else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+              if (j < ncol) v[u].v[j] = load_one(base + roff + j);
+          }
         }
       }
 #pragma unroll
@@ -535,8 +541,10 @@ reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
   }
   const int64_t group = k * p.col_tiles + tile;  // outputs sharing one ticket
   Acc* my = scratch + (group * p.S + split) * W;
-  if (ty == 0)
+  if (ty == 0) {
+#pragma unroll
     for (int j = 0; j < VEC; ++j) my[tx * VEC + j] = sm[tx * VEC + j];
+  }
   if (take_ticket(tickets + group, (uint32_t)p.S)) {
     // thread (tx, ty): partial s = ty, ty+TY, … of its columns, then the same shared-memory tree
 #pragma unroll

@@ -269,6 +269,7 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
         else softmax_rows_reg<T, 1, kSmThreads><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
       }
       HPTB_CUDA_CHECK(cudaGetLastError());
+      count_launches(1);
       return HPTB_OK;
     }
   }
@@ -283,6 +284,7 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
     softmax_rows_stream<T><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
   }
   HPTB_CUDA_CHECK(cudaGetLastError());
+  count_launches(1);
   return HPTB_OK;
 }
 

@@ -22,6 +22,21 @@ _TORCH_DTYPES = [torch.bool, torch.int8, torch.int16, torch.int32, torch.int64, 
 _TORCH_TO_ENUM = {d: i for i, d in enumerate(_TORCH_DTYPES)}
 
 _contexts = {}
+_default_stream = [None]
+
+
+def set_stream(stream):
+    """Set the cudaStream_t (int handle or None = legacy default stream) used when a call gets no explicit
+    `stream`.  The Rust shim passes its device's stream the same way (one stream per CudaDevice)."""
+    _default_stream[0] = stream
+
+
+def get_stream():
+    return _default_stream[0]
+
+
+def _s(stream):
+    return _default_stream[0] if stream is None else stream
 
 
 class Context:
@@ -40,7 +55,7 @@ class Context:
         return n.value
 
     def synchronize(self, stream=None):
-        check(lib.hptb_stream_sync(self.handle, stream))
+        check(lib.hptb_stream_sync(self.handle, _s(stream)))
 
     def empty_cache(self):
         check(lib.hptb_empty_cache(self.handle))
@@ -65,10 +80,10 @@ class _Storage:
     def __init__(self, ctx, nbytes, stream=None):
         self.ctx = ctx
         p = c_void_p()
-        check(lib.hptb_alloc(ctx.handle, max(int(nbytes), 1), byref(p), stream))
+        check(lib.hptb_alloc(ctx.handle, max(int(nbytes), 1), byref(p), _s(stream)))
         self.ptr = p.value
         self.nbytes = nbytes
-        self.stream = stream
+        self.stream = _s(stream)
 
     def __del__(self):
         try:
@@ -135,7 +150,7 @@ class Tensor:
         t = Tensor.empty(tuple(host.shape), _TORCH_TO_ENUM[host.dtype], device, stream)
         nbytes = host.numel() * host.element_size()
         if nbytes:
-            check(lib.hptb_memcpy_h2d(t.ctx.handle, c_void_p(t.ptr), c_void_p(host.data_ptr()), nbytes, stream))
+            check(lib.hptb_memcpy_h2d(t.ctx.handle, c_void_p(t.ptr), c_void_p(host.data_ptr()), nbytes, _s(stream)))
             # pageable source: make the staging complete before the host tensor can be mutated
             t.ctx.synchronize(stream)
         return t
@@ -146,13 +161,19 @@ class Tensor:
         return Tensor(_Borrowed(context(device), ptr, keepalive), ptr, dtype, shape,
                       strides if strides is not None else _contig_strides(shape))
 
-    def to_cpu(self, stream=None):
-        """`to_cpu::<0>()` (hpt/src/backends/cuda/tensor_impls.rs:142-169): views are gathered first."""
+    def to_cpu(self, stream=None, out=None):
+        """`to_cpu::<0>()` (hpt/src/backends/cuda/tensor_impls.rs:142-169): views are gathered first.
+        `out` may be a preallocated (e.g. pinned) contiguous host tensor of the right shape and dtype."""
         src = self if self.is_contiguous() else self.contiguous(stream)
-        host = torch.empty(self.shape, dtype=_TORCH_DTYPES[self.dtype])
+        if out is not None:
+            if tuple(out.shape) != self.shape or out.dtype != _TORCH_DTYPES[self.dtype] or not out.is_contiguous():
+                raise HptError(1, "to_cpu: out must be a contiguous host tensor of the same shape and dtype")
+            host = out
+        else:
+            host = torch.empty(self.shape, dtype=_TORCH_DTYPES[self.dtype])
         nbytes = host.numel() * host.element_size()
         if nbytes:
-            check(lib.hptb_memcpy_d2h(self.ctx.handle, c_void_p(host.data_ptr()), c_void_p(src.ptr), nbytes, stream))
+            check(lib.hptb_memcpy_d2h(self.ctx.handle, c_void_p(host.data_ptr()), c_void_p(src.ptr), nbytes, _s(stream)))
         return host
 
     # ---- metadata ---------------------------------------------------------------------------------
@@ -257,18 +278,18 @@ class Tensor:
     # ---- copy / cast ------------------------------------------------------------------------------
     def contiguous(self, stream=None):
         out = Tensor.empty(self.shape, self.dtype, self.ctx.device, stream)
-        check(lib.hptb_copy(self.ctx.handle, byref(self._c()), byref(out._c()), stream))
+        check(lib.hptb_copy(self.ctx.handle, byref(self._c()), byref(out._c()), _s(stream)))
         return out
 
     def astype(self, dtype, stream=None):
         out = Tensor.empty(self.shape, dtype, self.ctx.device, stream)
-        check(lib.hptb_copy(self.ctx.handle, byref(self._c()), byref(out._c()), stream))
+        check(lib.hptb_copy(self.ctx.handle, byref(self._c()), byref(out._c()), _s(stream)))
         return out
 
     def fill_(self, value, stream=None):
         host = torch.tensor([value]).to(_TORCH_DTYPES[self.dtype]) if self.dtype not in (_ffi.U16, _ffi.U32, _ffi.U64) \
             else torch.tensor([value], dtype=torch.int64).to(_TORCH_DTYPES[self.dtype])
-        check(lib.hptb_fill(self.ctx.handle, byref(self._c()), c_void_p(host.data_ptr()), stream))
+        check(lib.hptb_fill(self.ctx.handle, byref(self._c()), c_void_p(host.data_ptr()), _s(stream)))
         return self
 
     # ---- NormalBinOps / std::ops (hpt/src/backends/cuda/std_ops.rs, tensor_external/binary.rs) ----------
@@ -293,7 +314,7 @@ class Tensor:
         oshape = tuple(bshape[i] for i in range(bn.value))
         if out is None:
             out = Tensor.empty(oshape, odt, self.ctx.device, stream)
-        check(lib.hptb_binary(self.ctx.handle, op, byref(self._c()), byref(rhs._c()), byref(out._c()), stream))
+        check(lib.hptb_binary(self.ctx.handle, op, byref(self._c()), byref(rhs._c()), byref(out._c()), _s(stream)))
         return out
 
     def add_(self, rhs, out, stream=None): return self._binary("add", rhs, out, stream)
@@ -315,7 +336,7 @@ class Tensor:
         odt = lib.hptb_unary_out_dtype(op, self.dtype)
         if out is None:
             out = Tensor.empty(self.shape, odt, self.ctx.device, stream)
-        check(lib.hptb_unary(self.ctx.handle, op, byref(self._c()), byref(out._c()), float(alpha), float(beta), stream))
+        check(lib.hptb_unary(self.ctx.handle, op, byref(self._c()), byref(out._c()), float(alpha), float(beta), _s(stream)))
         return out
 
     def selu(self, out=None, stream=None):
@@ -348,7 +369,7 @@ class Tensor:
                 raise HptError(1, f"out has shape {out.shape}/{_ffi.DTYPE_NAMES[out.dtype]}, expected {red_shape}/{_ffi.DTYPE_NAMES[odt]}")
             res = out if out.shape == red_shape else Tensor(out.storage, out.ptr, out.dtype, red_shape, _contig_strides(red_shape))
         check(lib.hptb_reduce(self.ctx.handle, op, byref(self._c()), ax, len(ax_in), byref(res._c()),
-                              1 if init_out else 0, stream))
+                              1 if init_out else 0, _s(stream)))
         if keep_dims:
             check(lib.hptb_reduce_shape(shp, self.ndim, ax, len(ax_in), 1, oshape, byref(on)))
             ks = tuple(oshape[i] for i in range(on.value))
@@ -378,7 +399,7 @@ class Tensor:
         red_shape = tuple(oshape[i] for i in range(on.value))
         m = Tensor.empty(red_shape, odt, self.ctx.device, stream)
         v = Tensor.empty(red_shape, odt, self.ctx.device, stream)
-        check(lib.hptb_mean_var(self.ctx.handle, byref(self._c()), ax, len(ax_in), byref(m._c()), byref(v._c()), stream))
+        check(lib.hptb_mean_var(self.ctx.handle, byref(self._c()), ax, len(ax_in), byref(m._c()), byref(v._c()), _s(stream)))
         return m, v
 
     # ---- NormalizationOps (hpt/src/backends/cuda/tensor_internal/softmax.rs) ------------------------------
@@ -390,7 +411,7 @@ class Tensor:
             raise HptError(3, f"axis {axis} out of range for ndim {self.ndim}")
         odt = lib.hptb_unary_out_dtype(0, self.dtype)
         out = Tensor.empty(self.shape, odt, self.ctx.device, stream)
-        check(lib.hptb_softmax(self.ctx.handle, byref(self._c()), axis, log, byref(out._c()), stream))
+        check(lib.hptb_softmax(self.ctx.handle, byref(self._c()), axis, log, byref(out._c()), _s(stream)))
         return out
 
     def softmax(self, axis): return self._softmax(axis, 0)

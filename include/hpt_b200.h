@@ -113,6 +113,8 @@ typedef struct hptb_comm hptb_comm;  /* one NCCL rank */
 
 /* ---- library / context --------------------------------------------------------------------- */
 int hptb_version(void);
+/* kernels launched by this library in this process so far (bench evidence; monotonically increasing) */
+uint64_t hptb_kernel_launches(void);
 const char* hptb_last_error(void);   /* thread-local, valid until the next failing call on this thread */
 size_t hptb_dtype_size(int dtype);
 const char* hptb_dtype_name(int dtype);
