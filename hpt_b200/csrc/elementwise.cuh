@@ -7,11 +7,14 @@
 //     fast-divmods, broadcast operands have inner stride 0 (one scalar load per row chunk).
 //     This replaces `*_contiguous`, `*_contiguous_{lhs,rhs}_scalar` and the broadcast use of
 //     `*_uncontiguous` (hpt-cudakernels/src/binary/binary_template.cuh:5-105).
-//   * strided → map_tiled_kernel: 64×64 tiles over (a = the output's unit-stride dim,
-//     b = the dim in which a permuted input has unit stride); permuted inputs are read along b
-//     (coalesced) into padded shared memory and re-read along a, so both global sides stay
-//     coalesced.  Replaces `*_uncontiguous` (binary_template.cuh:48-61, unary_template.cuh:48-62)
-//     whose lane-adjacent reads of a transposed operand are a full stride apart.
+//   * strided → map_tiled_kernel: tiles over (a = the output's unit-stride dim, b = the dim in which
+//     a permuted input has unit stride).  Every thread owns an MA×MB register micro-tile: permuted
+//     inputs are read with 128-bit loads ALONG b (8 lanes = one 128 B line), transposed in registers
+//     (compile-time indexing, no shared memory, no barrier), and the result is written with 128-bit
+//     stores ALONG a — both global sides stay sector-efficient and each thread keeps MA 16-byte
+//     loads in flight.  Replaces `*_uncontiguous` (binary_template.cuh:48-61,
+//     unary_template.cuh:48-62) whose lane-adjacent reads of a transposed operand are a full
+//     stride apart.
 // All indices are 64-bit capable; a 32-bit fast-divmod path is taken when the counts fit.
 #pragma once
 #include "common.h"
@@ -23,8 +26,6 @@ namespace hptb {
 
 constexpr int kMapThreads = 256;
 constexpr int kMaxOuter = HPTB_MAX_DIMS - 1;
-constexpr int kTile = 64;
-constexpr int kTilePitch = kTile + 1;
 
 struct RowsParams {
   int64_t inner;         // elements in the inner dim
@@ -45,8 +46,7 @@ struct TileParams {
   int64_t tiles_a, tiles_b, ntiles;
   int32_t nbatch;
   int32_t use64;
-  int32_t transposed[3];   // operand is staged through shared memory
-  int32_t smem_off[3];     // byte offset of the operand's tile in dynamic shared memory
+  int32_t mode[3];         // 0 = scalar access, 1 = vector along b (permuted operand), 2 = vector along a
   uint32_t batch_shape[kMaxOuter];
   FastDiv batch_div[kMaxOuter];
   FastDiv tiles_a_div, tiles_b_div;
@@ -153,17 +153,59 @@ map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// tiled kernel: permuted / strided layouts
+// tiled kernel: permuted / strided layouts (register micro-tile transpose)
 // ------------------------------------------------------------------------------------------------
+constexpr int kTileAG = 4, kTileBG = 8;    // lanes of a warp: 4 micro-tiles along a × 8 along b
+constexpr int kTileWA = 4, kTileWB = 2;    // warps of a CTA: 4 along a × 2 along b
+
+template <typename O, typename A, typename B>
+struct TileGeom {
+  static constexpr int szmin_in = sizeof(A) < sizeof(B) ? sizeof(A) : sizeof(B);
+  static constexpr int ma0 = 16 / sizeof(O), mb0 = 16 / szmin_in;
+  static constexpr int MA = ma0 > 8 ? 8 : ma0;  // elements along a per thread (one 16 B store for ≥2-byte outputs)
+  static constexpr int MB = mb0 > 8 ? 8 : mb0;  // elements along b per thread (one 16 B load for ≥2-byte inputs)
+  static constexpr int TA = kTileWA * kTileAG * MA;
+  static constexpr int TB = kTileWB * kTileBG * MB;
+};
+
+// load an MA×MB micro-tile of operand X at (a0, b0) into v[ai][bj]
+template <typename X, int MA, int MB>
+__device__ __forceinline__ void load_micro(X (&v)[MA][MB], const X* __restrict__ base, int64_t sa, int64_t sb, int mode,
+                                           bool full, int na, int nb) {
+  if (mode == 1 && full) {  // rows along b
+#pragma unroll
+    for (int i = 0; i < MA; ++i) {
+      Pack<X, MB> pk;
+      load_pack<X, MB>(pk, base + (int64_t)i * sa);
+#pragma unroll
+      for (int j = 0; j < MB; ++j) v[i][j] = pk.v[j];
+    }
+  } else if (mode == 2 && full) {  // columns along a
+#pragma unroll
+    for (int j = 0; j < MB; ++j) {
+      Pack<X, MA> pk;
+      load_pack<X, MA>(pk, base + (int64_t)j * sb);
+#pragma unroll
+      for (int i = 0; i < MA; ++i) v[i][j] = pk.v[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < MA; ++i)
+#pragma unroll
+      for (int j = 0; j < MB; ++j)
+        if (i < na && j < nb) v[i][j] = load_one(base + (int64_t)i * sa + (int64_t)j * sb);
+  }
+}
+
 template <int NIN, typename F, typename O, typename A, typename B>
 __global__ void __launch_bounds__(kMapThreads)
 map_tiled_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, TileParams p, F f) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  A* sm_a = reinterpret_cast<A*>(smem_raw + p.smem_off[1]);
-  B* sm_b = reinterpret_cast<B*>(smem_raw + p.smem_off[2]);
-  const int tx = threadIdx.x & (kTile - 1);
-  const int ty = threadIdx.x >> 6;  // 0..3
-  constexpr int kPasses = kTile / (kMapThreads / kTile);  // 16
+  typedef TileGeom<O, A, B> G;
+  constexpr int MA = G::MA, MB = G::MB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // micro-tile coordinates inside the CTA tile
+  const int ua = ((warp % kTileWA) * kTileAG + (lane / kTileBG)) * MA;
+  const int ub = ((warp / kTileWA) * kTileBG + (lane % kTileBG)) * MB;
 
   for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     int64_t ta, tb, batch;
@@ -180,71 +222,44 @@ map_tiled_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restri
       tb = q - q2 * p.tiles_b;
       batch = q2;
     }
+    const int64_t a0 = ta * G::TA + ua, b0 = tb * G::TB + ub;
+    if (a0 >= p.A || b0 >= p.B) continue;
     int64_t off[3] = {0, 0, 0};
     walk_outer<3>(batch, p.nbatch, p.use64, p.batch_shape, p.batch_div, p.batch_stride, off);
-    const int64_t a0 = ta * kTile, b0 = tb * kTile;
-    const int na = (int)((p.A - a0) < kTile ? (p.A - a0) : kTile);
-    const int nb = (int)((p.B - b0) < kTile ? (p.B - b0) : kTile);
+    const int na = (int)((p.A - a0) < MA ? (p.A - a0) : MA);
+    const int nb = (int)((p.B - b0) < MB ? (p.B - b0) : MB);
+    const bool full = na == MA && nb == MB;
 
-    // phase 1: stage permuted inputs (read along b, coalesced)
-    if (p.transposed[1]) {
-      A r[kPasses];
-      const A* src = a + off[1] + a0 * p.sa[1] + (b0 + tx) * p.sb[1];
-#pragma unroll
-      for (int k = 0; k < kPasses; ++k) {
-        const int al = ty + 4 * k;
-        if (tx < nb && al < na) r[k] = load_one(src + (int64_t)al * p.sa[1]);
-      }
-#pragma unroll
-      for (int k = 0; k < kPasses; ++k) {
-        const int al = ty + 4 * k;
-        if (tx < nb && al < na) sm_a[al * kTilePitch + tx] = r[k];
-      }
-    }
-    if constexpr (NIN == 2) if (p.transposed[2]) {
-      B r[kPasses];
-      const B* src = b + off[2] + a0 * p.sa[2] + (b0 + tx) * p.sb[2];
-#pragma unroll
-      for (int k = 0; k < kPasses; ++k) {
-        const int al = ty + 4 * k;
-        if (tx < nb && al < na) r[k] = load_one(src + (int64_t)al * p.sa[2]);
-      }
-#pragma unroll
-      for (int k = 0; k < kPasses; ++k) {
-        const int al = ty + 4 * k;
-        if (tx < nb && al < na) sm_b[al * kTilePitch + tx] = r[k];
-      }
-    }
-    __syncthreads();
+    A va[MA][MB];
+    B vb[MA][MB];
+    load_micro<A, MA, MB>(va, a + off[1] + a0 * p.sa[1] + b0 * p.sb[1], p.sa[1], p.sb[1], p.mode[1], full, na, nb);
+    if constexpr (NIN == 2)
+      load_micro<B, MA, MB>(vb, b + off[2] + a0 * p.sa[2] + b0 * p.sb[2], p.sa[2], p.sb[2], p.mode[2], full, na, nb);
 
-    // phase 2: compute and write along a (coalesced)
-    {
-      A ra[kPasses];
-      B rb[kPasses];
-      const A* adir = a + off[1] + (a0 + tx) * p.sa[1] + b0 * p.sb[1];
-      const B* bdir = b + off[2] + (a0 + tx) * p.sa[2] + b0 * p.sb[2];
+    O* dst = out + off[0] + a0 * p.sa[0] + b0 * p.sb[0];
+    if (p.mode[0] == 2 && full) {
 #pragma unroll
-      for (int k = 0; k < kPasses; ++k) {
-        const int bl = ty + 4 * k;
-        if (tx < na && bl < nb) {
-          ra[k] = p.transposed[1] ? sm_a[tx * kTilePitch + bl] : load_one(adir + (int64_t)bl * p.sb[1]);
-          if constexpr (NIN == 2)
-            rb[k] = p.transposed[2] ? sm_b[tx * kTilePitch + bl] : load_one(bdir + (int64_t)bl * p.sb[2]);
-        }
-      }
-      O* dst = out + off[0] + (a0 + tx) * p.sa[0] + b0 * p.sb[0];
+      for (int j = 0; j < MB; ++j) {
+        Pack<O, MA> pk;
 #pragma unroll
-      for (int k = 0; k < kPasses; ++k) {
-        const int bl = ty + 4 * k;
-        if (tx < na && bl < nb) {
-          O v;
-          if constexpr (NIN == 2) v = f(ra[k], rb[k]);
-          else v = f(ra[k]);
-          dst[(int64_t)bl * p.sb[0]] = v;
+        for (int i = 0; i < MA; ++i) {
+          if constexpr (NIN == 2) pk.v[i] = f(va[i][j], vb[i][j]);
+          else pk.v[i] = f(va[i][j]);
         }
+        store_pack<O, MA>(dst + (int64_t)j * p.sb[0], pk);
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < MB; ++j)
+#pragma unroll
+        for (int i = 0; i < MA; ++i)
+          if (i < na && j < nb) {
+            O r;
+            if constexpr (NIN == 2) r = f(va[i][j], vb[i][j]);
+            else r = f(va[i][j]);
+            dst[(int64_t)i * p.sa[0] + (int64_t)j * p.sb[0]] = r;
+          }
     }
-    __syncthreads();
   }
 }
 
@@ -340,20 +355,29 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
     for (int d = nd - 1; d >= 0; --d)
       if (d != da) { db = d; break; }
   }
+  typedef TileGeom<O, A, B> G;
   TileParams p;
   memset(&p, 0, sizeof(p));
   p.A = c.shape[da];
   p.B = db >= 0 ? c.shape[db] : 1;
-  size_t smem = 0;
   for (int o = 0; o <= NIN; ++o) {
     p.sa[o] = c.strides[o][da];
     p.sb[o] = db >= 0 ? c.strides[o][db] : 0;
-    p.transposed[o] = (o > 0 && db >= 0 && p.sb[o] == 1 && p.sa[o] != 1 && p.sa[o] != 0) ? 1 : 0;
-    if (p.transposed[o]) {
-      smem = (smem + 15) / 16 * 16;
-      p.smem_off[o] = (int32_t)smem;
-      smem += (size_t)kTile * kTilePitch * esz[o];
-    }
+    // vector access needs a unit stride along the vector dim and 16 B (pack) alignment of every micro-tile row
+    const int along_b = G::MB, along_a = G::MA;
+    auto aligned = [&](int vec, int unit_dim) {
+      size_t al = esz[o] * vec > 16 ? 16 : esz[o] * vec;
+      if (al <= esz[o]) return true;
+      if (reinterpret_cast<uintptr_t>(plan.ptr[o]) % al) return false;
+      for (int d = 0; d < nd; ++d) {
+        if (d == unit_dim) continue;
+        if ((uint64_t)(std::llabs(c.strides[o][d]) * (int64_t)esz[o]) % al) return false;
+      }
+      return true;
+    };
+    p.mode[o] = 0;
+    if (o > 0 && db >= 0 && p.sb[o] == 1 && aligned(along_b, db)) p.mode[o] = 1;
+    else if (p.sa[o] == 1 && aligned(along_a, da)) p.mode[o] = 2;
   }
   bool big = false;
   int nb = 0;  // innermost batch dim first
@@ -366,8 +390,8 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
     ++nb;
   }
   p.nbatch = nb;
-  p.tiles_a = (p.A + kTile - 1) / kTile;
-  p.tiles_b = (p.B + kTile - 1) / kTile;
+  p.tiles_a = (p.A + G::TA - 1) / G::TA;
+  p.tiles_b = (p.B + G::TB - 1) / G::TB;
   int64_t batch = 1;
   for (int i = 0; i < nb; ++i) batch *= p.batch_shape[i];
   p.ntiles = p.tiles_a * p.tiles_b * batch;
@@ -376,15 +400,7 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
   p.tiles_a_div = FastDiv(big ? 1u : (uint32_t)p.tiles_a);
   p.tiles_b_div = FastDiv(big ? 1u : (uint32_t)p.tiles_b);
   int64_t blocks = p.ntiles < 0x7fffffffLL ? p.ntiles : 0x7fffffffLL;
-  auto kern = map_tiled_kernel<NIN, F, O, A, B>;
-  if (smem > 48 * 1024) {
-    static bool opted_in = false;  // per instantiation
-    if (!opted_in) {
-      HPTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTile * kTilePitch * 8));
-      opted_in = true;
-    }
-  }
-  kern<<<(unsigned)blocks, kMapThreads, smem, stream>>>(out, a, b, p, f);
+  map_tiled_kernel<NIN, F, O, A, B><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, f);
   HPTB_CUDA_CHECK(cudaGetLastError());
   return HPTB_OK;
 }

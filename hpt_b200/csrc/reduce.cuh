@@ -200,6 +200,19 @@ template <typename T, bool IS_MAX> struct ArgOp {
 template <typename T> struct ReduceOp<HPTB_ARGMAX, T> : ArgOp<T, true> {};
 template <typename T> struct ReduceOp<HPTB_ARGMIN, T> : ArgOp<T, false> {};
 
+// per-element accumulate.  Arg reductions: every accumulator sees strictly increasing indices, so a strict
+// "better" test keeps the first occurrence without comparing indices (the full tie rule is only needed when
+// accumulators are combined).
+template <typename Op, typename T>
+__device__ __forceinline__ void red_accumulate(typename Op::Acc& acc, T x, int64_t idx) {
+  if constexpr (Op::kIndexed) {
+    const auto v = to_compute<T>(x);
+    if (Op::better(v, acc.val)) { acc.val = v; acc.idx = idx; }
+  } else {
+    acc = Op::combine(acc, Op::pre(x, idx));
+  }
+}
+
 // ---- launch parameters ---------------------------------------------------------------------------------
 struct DimWalk {
   int32_t n;
@@ -397,7 +410,7 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
       for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k)
-          if (k < cnt[u]) acc[k] = Op::combine(acc[k], Op::pre(v[u].v[k], e0[u] + k));
+          if (k < cnt[u]) red_accumulate<Op, T>(acc[k], v[u].v[k], e0[u] + k);
       }
     }
   }
@@ -509,7 +522,7 @@ reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
         if (!ok[u]) continue;
 #pragma unroll
         for (int j = 0; j < VEC; ++j)
-          if (j < ncol) acc[j] = Op::combine(acc[j], Op::pre(v[u].v[j], ri[u]));
+          if (j < ncol) red_accumulate<Op, T>(acc[j], v[u].v[j], ri[u]);
       }
     }
   }

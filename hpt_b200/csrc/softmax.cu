@@ -72,7 +72,7 @@ __device__ __forceinline__ C group_reduce(C v, C* s_buf, C ident) {
     if ((tid & 31) == 0) s_buf[tid >> 5] = v;
     __syncthreads();
     C r = (tid & 31) < G / 32 ? s_buf[tid & 31] : ident;
-    v = warp_reduce<WrapOp<OpT, C>, C>(r, G / 32);
+    v = warp_reduce<WrapOp<OpT, C>, C>(r, 32);  // full butterfly: every lane ends with the row total
   }
   return v;
 }
@@ -124,7 +124,6 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
     }
   }
   sum = group_reduce<AddOp, C, G>(sum, s_buf, (C)0);
-  const C inv = (C)1 / sum;
   const C lg = sm_log<C>(sum);
 #pragma unroll
   for (int i = 0; i < kSmChunks; ++i) {
@@ -132,7 +131,7 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
     if (i < p.nchunks && active && e < p.L) {
       Pack<O, VEC> o;
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(p.log ? x[i][k] - lg : x[i][k] * inv);
+      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(p.log ? x[i][k] - lg : x[i][k] / sum);
       store_pack<O, VEC>(out + out_off + e, o);
     }
   }
@@ -178,11 +177,11 @@ softmax_rows_stream(const T* __restrict__ in, typename type_of_dtype<promote_ct(
     __syncthreads();
     MS<C> r{Limits<C>::lowest(), (C)0};
     for (int w = 0; w < kSmThreads / 32; ++w) r = ms_combine<C>(r, MS<C>{s_m[w], s_s[w]});
-    const C inv = (C)1 / r.s, lg = sm_log<C>(r.s);
+    const C ssum = r.s, lg = sm_log<C>(r.s);
     for (int64_t e = tid; e < p.L; e += kSmThreads) {
       const C x = to_compute<O>(cast<O>(src[e * p.sa_in]));
       const C sh = x - r.m;
-      dst[e * p.sa_out] = from_compute<O>(p.log ? sh - lg : sm_exp<C>(sh) * inv);
+      dst[e * p.sa_out] = from_compute<O>(p.log ? sh - lg : sm_exp<C>(sh) / ssum);
     }
   }
 }
@@ -204,11 +203,11 @@ softmax_cols(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_o
     const C x = to_compute<O>(cast<O>(load_one(src + e * p.sa_in)));
     a = ms_combine<C>(a, MS<C>{x, (C)1});
   }
-  const C inv = (C)1 / a.s, lg = sm_log<C>(a.s);
+  const C ssum = a.s, lg = sm_log<C>(a.s);
   for (int64_t e = 0; e < p.L; ++e) {
     const C x = to_compute<O>(cast<O>(src[e * p.sa_in]));
     const C sh = x - a.m;
-    dst[e * p.sa_out] = from_compute<O>(p.log ? sh - lg : sm_exp<C>(sh) * inv);
+    dst[e * p.sa_out] = from_compute<O>(p.log ? sh - lg : sm_exp<C>(sh) / ssum);
   }
 }
 

@@ -409,6 +409,8 @@ def reduce_f64(op, x, xd, axes):
             return v.sum(axis=axes) / n
         if op == "sum_square":
             return (v * v).sum(axis=axes)
+        if op == "prod":
+            return v.prod(axis=axes)
         if op == "logsumexp":
             return np.log(np.exp(v).sum(axis=axes))
     raise ValueError(op)

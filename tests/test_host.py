@@ -27,6 +27,13 @@ def test_header_symbols_exported():
     assert not _ffi.MISSING
 
 
+def test_rust_sys_crate_binds_exactly_the_header():
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "hpt_b200.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(hptb_[a-z0-9_]+)\s*\(", hdr))
+    rs = set(re.findall(r"pub fn (hptb_[a-z0-9_]+)", open(os.path.join(ROOT, "rust", "hpt-b200-sys", "src", "lib.rs")).read()))
+    assert declared == rs, declared ^ rs
+
+
 def test_version_and_dtype_sizes():
     assert lib.hptb_version() == 100
     for i, n in enumerate(DTYPES):

@@ -22,11 +22,13 @@ def _softmax_check(hb, x, d, axis, log, view=None):
     assert got_t.dtype == ENUM[od] and tuple(got_t.shape) == tuple(x.shape)
     got = to_numpy(got_t.to_cpu(), od)
     u = O.ulp_diff(got, want, od)
-    # 2 ulp for softmax; log_softmax subtracts two O(|x|) numbers: absolute bound 4·eps·max|x| as well
+    # softmax = exp (≤1 ulp) ÷ Σ (n roundings, tree-summed) — a composite, not an elementwise transcendental:
+    # bound 4 ulp (the reference's own tests use allclose 1e-3); log_softmax subtracts two O(|x|) numbers:
+    # absolute bound 4·eps·max|x| as well
     eps = {"f16": 2.0 ** -10, "bf16": 2.0 ** -7, "f32": 2.0 ** -23, "f64": 2.0 ** -52}[od]
     err = np.abs(np.asarray(got, np.float64) - np.asarray(want, np.float64))
     scale = np.max(np.abs(np.asarray(x, np.float64)), axis=axis, keepdims=True) + 1.0
-    ok = (u <= 2) | (err <= 4 * eps * scale if log else err <= 2 * eps * np.maximum(np.asarray(want, np.float64), 1e-30) + 1e-45)
+    ok = (u <= 4) | (err <= 4 * eps * scale if log else err <= 4 * eps * np.maximum(np.asarray(want, np.float64), 1e-30) + 1e-45)
     assert ok.all(), f"softmax log={log} {d} shape={x.shape} axis={axis}: max ulp {u.max()}"
 
 
@@ -132,7 +134,8 @@ def test_allocator_caches_and_transfers(hb):
     # steady-state op loop performs no device mallocs
     x = hb.Tensor.to_cuda(to_torch(np.ones((256, 256), np.float32), "f32"))
     y = x + x
-    del y
+    z = y.sum([1])
+    del y, z
     m0 = ctx.alloc_stats()["n_device_malloc"]
     for _ in range(20):
         y = x + x
