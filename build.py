@@ -5,8 +5,8 @@
     python build.py --clean
 
 Every .cu is compiled for sm_100a only (`-gencode arch=compute_100a,code=sm_100a -lineinfo`).
-The elementwise kernels are instantiated per (op, lhs dtype) translation unit from three template
-sources with -D flags, so the ~100 units compile in parallel.  Outputs:
+The elementwise kernels are instantiated per op (specialised same-dtype kernels) and per output dtype
+(runtime-typed kernels) from template sources with -D flags, so the ~70 units compile in parallel.  Outputs:
     hpt_b200/lib/libhpt_b200.so     the product
     oracle/_build/liboracle_cpu.so  C++/OpenMP restatement of Hpt's CPU path (test oracle + CPU baseline)
 """
@@ -40,18 +40,19 @@ CXX_FLAGS = "-O2 -std=c++17 -fPIC -fvisibility=hidden -I/usr/local/cuda/include 
 def units():
     """(object name, source, extra defines)"""
     u = []
+    # specialised vector-only kernels: same-dtype binary, float unary, same-dtype copy
     for fn, name, kind, bool_ok in BINARY_OPS:
-        for cty, short in DTYPES:
-            u.append((f"binary_{name}_{short}", "binary_inst.cu",
-                      f"-DHPTB_OP={fn} -DHPTB_OPNAME={name} -DHPTB_KIND={kind} -DHPTB_BOOL_OK={bool_ok} "
-                      f"-DHPTB_LHS={cty} -DHPTB_LHSNAME={short}"))
+        u.append((f"binary_{name}", "binary_inst.cu",
+                  f"-DHPTB_OP={fn} -DHPTB_OPNAME={name} -DHPTB_KIND={kind} -DHPTB_BOOL_OK={bool_ok}"))
     for name in UNARY_OPS:
         u.append((f"unary_{name}", "unary_inst.cu", f"-DHPTB_OPENUM=HPTB_{name.upper()} -DHPTB_OPNAME={name}"))
+    u.append(("copy_same", "cast_inst.cu", ""))
+    # runtime-typed kernels: one unit per OUTPUT dtype (mixed-dtype binary, integer-input unary, astype)
     for cty, short in DTYPES:
-        u.append((f"cast_{short}", "cast_inst.cu", f"-DHPTB_LHS={cty} -DHPTB_LHSNAME={short}"))
+        is_float = 1 if short in ("f16", "bf16", "f32", "f64") else 0
+        u.append((f"dyn_{short}", "dyn_inst.cu", f"-DHPTB_OUT={cty} -DHPTB_OUTNAME={short} -DHPTB_OUT_FLOAT={is_float}"))
     for name in REDUCE_OPS:
-        if os.path.exists(os.path.join(CSRC, "reduce_inst.cu")):
-            u.append((f"reduce_{name}", "reduce_inst.cu", f"-DHPTB_OPENUM=HPTB_{name.upper()} -DHPTB_OPNAME={name}"))
+        u.append((f"reduce_{name}", "reduce_inst.cu", f"-DHPTB_OPENUM=HPTB_{name.upper()} -DHPTB_OPNAME={name}"))
     for src in ("softmax.cu", "misc.cu", "meanvar.cu"):
         if os.path.exists(os.path.join(CSRC, src)):
             u.append((src[:-3], src, ""))

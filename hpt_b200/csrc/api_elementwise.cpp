@@ -15,26 +15,24 @@
 #include "map_plan.h"
 
 // launcher getters exported by the instantiation units
-
 // (weak: a development build may leave units out; a missing unit reports HPTB_ERR_DTYPE)
 #define HPTB_WEAK __attribute__((weak))
 extern "C" {
-#define XB(F, NAME, E, K, B) \
-  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_bool(int); HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_i8(int);   \
-  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_i16(int);  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_i32(int);  \
-  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_i64(int);  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_u8(int);   \
-  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_u16(int);  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_u32(int);  \
-  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_u64(int);  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_f16(int);  \
-  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_bf16(int); HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_f32(int);  \
-  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_f64(int);
+// specialised, vector-only kernels: same-dtype binary (T,T)→T, float unary T→T, same-dtype copy by element size
+#define XB(F, NAME, E, K, B) HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME(int);
 HPTB_FOR_BINARY_OPS(XB)
 #undef XB
 #define XU(NAME, E) HPTB_WEAK hptb::MapLauncher hptb_unary_##NAME(int);
 HPTB_FOR_UNARY_OPS(XU)
 #undef XU
-#define XC(T, N, E) HPTB_WEAK hptb::MapLauncher hptb_cast_##N(int);
-HPTB_FOR_DTYPES(XC)
-#undef XC
+HPTB_WEAK hptb::MapLauncher hptb_copy_same(int);
+// runtime-typed kernels, one set per OUTPUT dtype (mixed-dtype pairs, integer-input unary, astype, odd layouts)
+#define XD(T, N, E)                                      \
+  HPTB_WEAK hptb::MapLauncher hptb_dyn_binary_##N(void); \
+  HPTB_WEAK hptb::MapLauncher hptb_dyn_cast_##N(void);   \
+  HPTB_WEAK hptb::MapLauncher hptb_dyn_unary_##N(void);
+HPTB_FOR_DTYPES(XD)
+#undef XD
 }
 
 namespace hptb {
@@ -49,18 +47,12 @@ int promote(int lhs, int rhs, int kind) {
 }
 
 typedef MapLauncher (*Getter)(int);
+typedef MapLauncher (*DynGetter)(void);
 
-static Getter binary_getter(int op, int lhs) {
+static Getter binary_getter(int op) {
   switch (op) {
-#define XB(F, NAME, E, K, B)                                                                       \
-  case E: {                                                                                        \
-    static const Getter tab[13] = {hptb_binary_##NAME##_bool, hptb_binary_##NAME##_i8, hptb_binary_##NAME##_i16, \
-                                   hptb_binary_##NAME##_i32, hptb_binary_##NAME##_i64, hptb_binary_##NAME##_u8, \
-                                   hptb_binary_##NAME##_u16, hptb_binary_##NAME##_u32, hptb_binary_##NAME##_u64, \
-                                   hptb_binary_##NAME##_f16, hptb_binary_##NAME##_bf16, hptb_binary_##NAME##_f32, \
-                                   hptb_binary_##NAME##_f64};                                       \
-    return tab[lhs];                                                                               \
-  }
+#define XB(F, NAME, E, K, B) \
+  case E: return hptb_binary_##NAME;
     HPTB_FOR_BINARY_OPS(XB)
 #undef XB
     default: return nullptr;
@@ -77,20 +69,25 @@ static Getter unary_getter(int op) {
   }
 }
 
-static Getter cast_getter(int src) {
-  switch (src) {
-#define XC(T, N, E) \
-  case E: return hptb_cast_##N;
-    HPTB_FOR_DTYPES(XC)
-#undef XC
-    default: return nullptr;
+enum DynKind { kDynBinary, kDynCast, kDynUnary };
+static MapLauncher dyn_launcher(DynKind kind, int out_dtype) {
+  DynGetter g = nullptr;
+  switch (out_dtype) {
+#define XD(T, N, E) \
+  case E: g = kind == kDynBinary ? hptb_dyn_binary_##N : kind == kDynCast ? hptb_dyn_cast_##N : hptb_dyn_unary_##N; break;
+    HPTB_FOR_DTYPES(XD)
+#undef XD
+    default: break;
   }
+  return g ? g() : nullptr;
 }
 
 static int binary_kind(int op) { return op == HPTB_DIV ? HPTB_PROMOTE_FLOAT_BINARY : HPTB_PROMOTE_NORMAL; }
 
-// shared tail of every elementwise entry: broadcast inputs to out's shape, collapse, launch.
-static hptb_status run_map(hptb_ctx* ctx, MapLauncher fn, hptb_tensor* out, const hptb_tensor* in0,
+// shared tail of every elementwise entry: broadcast inputs to out's shape, collapse, launch.  `fast` (may be
+// null) is the specialised same-dtype launcher; it may decline a layout (HPTB_FALLBACK), and `dyn` — the
+// runtime-typed launcher for out's dtype — takes everything else.
+static hptb_status run_map(hptb_ctx* ctx, MapLauncher fast, MapLauncher dyn, int op, hptb_tensor* out, const hptb_tensor* in0,
                            const hptb_tensor* in1, double alpha, double beta, void* stream) {
   int64_t strides[kMaxOperands][HPTB_MAX_DIMS] = {{0}};
   const int nd = out->ndim;
@@ -106,8 +103,15 @@ static hptb_status run_map(hptb_ctx* ctx, MapLauncher fn, hptb_tensor* out, cons
   plan.alpha = alpha;
   plan.beta = beta;
   plan.sm_count = ctx->sm_count;
+  plan.in_dtype[0] = in0->dtype;
+  plan.in_dtype[1] = in1 ? in1->dtype : -1;
+  plan.op = op;
   DeviceGuard g(ctx->device);
-  hptb_status st = fn(plan, (cudaStream_t)stream);
+  hptb_status st = fast ? fast(plan, (cudaStream_t)stream) : HPTB_FALLBACK;
+  if (st == HPTB_FALLBACK) {
+    if (!dyn) return fail(HPTB_ERR_DTYPE, "elementwise: no kernel for output dtype %s", dtype_name(out->dtype));
+    st = dyn(plan, (cudaStream_t)stream);
+  }
   if (st == HPTB_OK && plan.c.numel > 0) count_launches(1);
   return st;
 }
@@ -230,10 +234,12 @@ hptb_status hptb_binary(hptb_ctx* ctx, int op, const hptb_tensor* lhs, const hpt
   bool same = bn == out->ndim;
   for (int i = 0; same && i < bn; ++i) same = bshape[i] == out->shape[i];
   if (!same) return fail(HPTB_ERR_SHAPE, "binary: out shape does not equal the broadcast shape of the operands");
-  Getter g = binary_getter(op, lhs->dtype);
-  MapLauncher fn = g ? g(rhs->dtype) : nullptr;
-  if (!fn) return fail(HPTB_ERR_DTYPE, "binary: no kernel for op %d (%s, %s)", op, dtype_name(lhs->dtype), dtype_name(rhs->dtype));
-  return run_map(ctx, fn, out, lhs, rhs, 0.0, 0.0, stream);
+  MapLauncher fast = nullptr;
+  if (lhs->dtype == rhs->dtype && lhs->dtype == odt) {
+    Getter g = binary_getter(op);
+    fast = g ? g(odt) : nullptr;
+  }
+  return run_map(ctx, fast, dyn_launcher(kDynBinary, odt), op, out, lhs, rhs, 0.0, 0.0, stream);
 }
 
 hptb_status hptb_unary(hptb_ctx* ctx, int op, const hptb_tensor* in, hptb_tensor* out, double alpha, double beta,
@@ -249,21 +255,23 @@ hptb_status hptb_unary(hptb_ctx* ctx, int op, const hptb_tensor* in, hptb_tensor
   bool same = in->ndim == out->ndim;
   for (int i = 0; same && i < in->ndim; ++i) same = in->shape[i] == out->shape[i];
   if (!same) return fail(HPTB_ERR_SHAPE, "unary: out shape differs from the input shape");
-  Getter ug = unary_getter(op);
-  MapLauncher fn = ug ? ug(in->dtype) : nullptr;
-  if (!fn) return fail(HPTB_ERR_DTYPE, "unary: no kernel for op %d on %s", op, dtype_name(in->dtype));
-  return run_map(ctx, fn, out, in, nullptr, alpha, beta, stream);
+  MapLauncher fast = nullptr;
+  if (in->dtype == odt) {
+    Getter ug = unary_getter(op);
+    fast = ug ? ug(odt) : nullptr;
+  }
+  return run_map(ctx, fast, dyn_launcher(kDynUnary, odt), op, out, in, nullptr, alpha, beta, stream);
 }
 
 hptb_status hptb_copy(hptb_ctx* ctx, const hptb_tensor* in, hptb_tensor* out, void* stream) {
   if (!ctx) return fail(HPTB_ERR_INVALID, "copy: null ctx");
   HPTB_TRY(validate_tensor(in, "copy in"));
   HPTB_TRY(validate_tensor(out, "copy out"));
-  Getter cg = cast_getter(in->dtype);
-  MapLauncher fn = cg ? cg(out->dtype) : nullptr;
-  if (!fn) return fail(HPTB_ERR_DTYPE, "copy: no kernel for %s -> %s", dtype_name(in->dtype), dtype_name(out->dtype));
+  if (!dtype_valid(in->dtype) || !dtype_valid(out->dtype)) return fail(HPTB_ERR_DTYPE, "copy: bad dtype");
+  MapLauncher fast = nullptr;
+  if (in->dtype == out->dtype && hptb_copy_same) fast = hptb_copy_same((int)dtype_size(in->dtype));
   // `in` may broadcast into `out` (used by fill-from-tensor and expand().contiguous())
-  return run_map(ctx, fn, out, in, nullptr, 0.0, 0.0, stream);
+  return run_map(ctx, fast, dyn_launcher(kDynCast, out->dtype), 0, out, in, nullptr, 0.0, 0.0, stream);
 }
 
 }  // extern "C"

@@ -1,7 +1,9 @@
-// binary_inst.cu — one translation unit per (binary op, lhs dtype); compiled with
+// binary_inst.cu — one translation unit per binary op; compiled with
 //   -DHPTB_OP=<functor> -DHPTB_OPNAME=<name> -DHPTB_KIND=<promote kind> -DHPTB_BOOL_OK=<0|1>
-//   -DHPTB_LHS=<c++ type> -DHPTB_LHSNAME=<short name>
-// and exports `hptb_binary_<op>_<lhs>(rhs dtype) -> launcher`.  13 rhs dtypes × 3 kernels each.
+// and exports `hptb_binary_<op>(dtype) -> launcher` for the SAME-dtype pairs (T, T) → T: the vector-only
+// specialised kernels (map_rows_kernel with 128-bit accesses, map_tiled_kernel for permuted operands).
+// Mixed-dtype pairs, pairs whose Output differs from T (int / int → float for div) and unaligned layouts are
+// served by the runtime-typed kernel (dyn_inst.cu).
 #include "dtypes_x.h"
 #include "elementwise.cuh"
 #include "ops.cuh"
@@ -9,26 +11,25 @@
 
 namespace hptb {
 namespace {
-template <typename R>
+template <typename T>
 struct Inst {
-  typedef HPTB_LHS L;
-  static constexpr int odt = promote_ct(dtype_of<L>::value, dtype_of<R>::value, HPTB_KIND);
-  typedef typename type_of_dtype<odt>::type O;
+  static constexpr int odt = promote_ct(dtype_of<T>::value, dtype_of<T>::value, HPTB_KIND);
   static hptb_status launch(const MapPlan& plan, cudaStream_t s) {
-    typedef BinaryFn<HPTB_OP, O, L, R> F;
-    return launch_map<2, F, O, L, R>(plan, F{}, s);
+    typedef BinaryFn<HPTB_OP, T, T, T> F;
+    return launch_map<2, F, T, T, T>(plan, F{}, s);
   }
   static MapLauncher get() {
-    if constexpr (odt == HPTB_BOOL && !HPTB_BOOL_OK) return nullptr;
+    if constexpr (odt != dtype_of<T>::value) return nullptr;
+    else if constexpr (odt == HPTB_BOOL && !HPTB_BOOL_OK) return nullptr;
     else return &launch;
   }
 };
 }  // namespace
 }  // namespace hptb
 
-extern "C" hptb::MapLauncher HPTB_CAT4(hptb_binary_, HPTB_OPNAME, _, HPTB_LHSNAME)(int rhs) {
+extern "C" hptb::MapLauncher HPTB_CAT(hptb_binary_, HPTB_OPNAME)(int dt) {
   using namespace hptb;
-  switch (rhs) {
+  switch (dt) {
 #define X(T, N, E) \
   case E: return Inst<T>::get();
     HPTB_FOR_DTYPES(X)

@@ -1,31 +1,30 @@
-// cast_inst.cu — strided gather / dtype conversion (`contiguous()`, `to_cpu` of views, `astype`);
-// one translation unit per source dtype (-DHPTB_LHS, -DHPTB_LHSNAME), exports
-// `hptb_cast_<src>(dst dtype) -> launcher`.  Replaces strided_copy_<T>
-// (hpt-cudakernels/src/strided_copy.cu); conversions follow hpt-macros/src/scalar_convert.rs.
+// cast_inst.cu — same-dtype strided gather (`contiguous()`, `to_cpu` of views): a bit move, so one set of
+// specialised kernels per ELEMENT SIZE.  Exports `hptb_copy_same(element size) -> launcher`.  Replaces
+// strided_copy_<T> (hpt-cudakernels/src/strided_copy.cu); dtype-converting copies (`astype`) take the
+// runtime-typed kernel (dyn_inst.cu), whose conversions follow hpt-macros/src/scalar_convert.rs.
 #include "dtypes_x.h"
 #include "elementwise.cuh"
 #include "ops.cuh"
 
 namespace hptb {
 namespace {
-template <typename O>
+template <typename T>
 struct Inst {
-  typedef HPTB_LHS A;
   static hptb_status launch(const MapPlan& plan, cudaStream_t s) {
-    typedef CastFn<O, A> F;
-    return launch_map<1, F, O, A, A>(plan, F{}, s);
+    typedef CastFn<T, T> F;
+    return launch_map<1, F, T, T, T>(plan, F{}, s);
   }
 };
 }  // namespace
 }  // namespace hptb
 
-extern "C" hptb::MapLauncher HPTB_CAT(hptb_cast_, HPTB_LHSNAME)(int dst) {
+extern "C" hptb::MapLauncher hptb_copy_same(int esz) {
   using namespace hptb;
-  switch (dst) {
-#define X(T, N, E) \
-  case E: return &Inst<T>::launch;
-    HPTB_FOR_DTYPES(X)
-#undef X
+  switch (esz) {
+    case 1: return &Inst<uint8_t>::launch;
+    case 2: return &Inst<uint16_t>::launch;
+    case 4: return &Inst<uint32_t>::launch;
+    case 8: return &Inst<uint64_t>::launch;
     default: return nullptr;
   }
 }

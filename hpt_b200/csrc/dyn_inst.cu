@@ -1,0 +1,26 @@
+// dyn_inst.cu — one translation unit per OUTPUT dtype (-DHPTB_OUT=<c++ type> -DHPTB_OUTNAME=<short name>
+// -DHPTB_OUT_FLOAT=<0|1>): the runtime-typed elementwise kernels (elementwise_dyn.cuh) for binary ops, dtype
+// conversion and — float outputs only — FloatUnaryOps.  Exports `hptb_dyn_{binary,cast,unary}_<out>()`.
+#include "dtypes_x.h"
+#include "elementwise_dyn.cuh"
+
+namespace hptb {
+namespace {
+typedef HPTB_OUT O;
+hptb_status launch_binary(const MapPlan& plan, cudaStream_t s) { return launch_map_dyn<2, DynBinaryFn<O>, O>(plan, s); }
+hptb_status launch_cast(const MapPlan& plan, cudaStream_t s) { return launch_map_dyn<1, DynCastFn<O>, O>(plan, s); }
+#if HPTB_OUT_FLOAT
+hptb_status launch_unary(const MapPlan& plan, cudaStream_t s) { return launch_map_dyn<1, DynUnaryFn<O>, O>(plan, s); }
+#endif
+}  // namespace
+}  // namespace hptb
+
+extern "C" hptb::MapLauncher HPTB_CAT(hptb_dyn_binary_, HPTB_OUTNAME)() { return &hptb::launch_binary; }
+extern "C" hptb::MapLauncher HPTB_CAT(hptb_dyn_cast_, HPTB_OUTNAME)() { return &hptb::launch_cast; }
+extern "C" hptb::MapLauncher HPTB_CAT(hptb_dyn_unary_, HPTB_OUTNAME)() {
+#if HPTB_OUT_FLOAT
+  return &hptb::launch_unary;
+#else
+  return nullptr;
+#endif
+}

@@ -34,6 +34,7 @@ struct RowsParams {
   int32_t nouter;
   int32_t use64;         // 1: counts exceed 32 bits, use 64-bit division
   int32_t inner_stride[3];
+  int32_t reuse[3];      // operand is re-read across rows (a broadcast outer dim): keep it in L1
   uint32_t outer_shape[kMaxOuter];  // innermost outer dim first
   FastDiv outer_div[kMaxOuter];
   FastDiv cpr_div;
@@ -85,6 +86,7 @@ __device__ __forceinline__ void walk_outer(int64_t row, int nouter, int use64, c
 template <int NIN, int VEC, int UNROLL, typename F, typename O, typename A, typename B>
 __global__ void __launch_bounds__(kMapThreads)
 map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, RowsParams p, F f) {
+  static_assert(VEC > 1, "the specialised rows kernel is vector-only; scalar layouts take the runtime-typed kernel");
   const int64_t c0 = (int64_t)blockIdx.x * (kMapThreads * UNROLL) + threadIdx.x;
   Pack<A, VEC> pa[UNROLL];
   Pack<B, VEC> pb[UNROLL];
@@ -112,7 +114,8 @@ map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restric
 #pragma unroll
         for (int k = 0; k < VEC; ++k) pa[u].v[k] = s;
       } else if (cnt[u] == VEC) {
-        load_pack<A, VEC>(pa[u], ap);
+        if (p.reuse[1]) load_pack_cached<A, VEC>(pa[u], ap);
+        else load_pack<A, VEC>(pa[u], ap);
       } else {
 #pragma unroll
         for (int k = 0; k < VEC; ++k)
@@ -125,7 +128,8 @@ map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restric
 #pragma unroll
           for (int k = 0; k < VEC; ++k) pb[u].v[k] = s;
         } else if (cnt[u] == VEC) {
-          load_pack<B, VEC>(pb[u], bp);
+          if (p.reuse[2]) load_pack_cached<B, VEC>(pb[u], bp);
+          else load_pack<B, VEC>(pb[u], bp);
         } else {
 #pragma unroll
           for (int k = 0; k < VEC; ++k)
@@ -311,13 +315,15 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
         if (p.inner_stride[o] == 0) continue;
         size_t align = esz[o] * VEC > 16 ? 16 : esz[o] * VEC;
         if (reinterpret_cast<uintptr_t>(plan.ptr[o]) % align) vec_ok = false;
-        for (int i = 0; i < p.nouter; ++i)
+        for (int i = 0; i < p.nouter; ++i) {
           if ((uint64_t)(std::llabs(p.outer_stride[o][i]) * (int64_t)esz[o]) % align) vec_ok = false;
+          if (o > 0 && p.outer_stride[o][i] == 0) p.reuse[o] = 1;
+        }
       }
       if (p.nouter > 0 && p.inner % VEC) vec_ok = false;
     }
-    const int vec = vec_ok ? VEC : 1;
-    p.cpr = (p.inner + vec - 1) / vec;
+    if (!vec_ok) return HPTB_FALLBACK;  // unaligned / odd rows: the runtime-typed kernel handles them
+    p.cpr = (p.inner + VEC - 1) / VEC;
     int64_t rows = 1;
     for (int i = 0; i < p.nouter; ++i) rows *= c.shape[nd - 2 - i];
     p.total_chunks = rows * p.cpr;
@@ -327,10 +333,7 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
     constexpr int UNROLL = VEC >= 16 ? 1 : VEC >= 8 ? 2 : 4;  // ~16 elements per thread
     int64_t blocks = (p.total_chunks + kMapThreads * UNROLL - 1) / (kMapThreads * UNROLL);
     if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "elementwise: tensor too large for one launch");
-    if (vec_ok)
-      map_rows_kernel<NIN, VEC, UNROLL, F, O, A, B><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, f);
-    else
-      map_rows_kernel<NIN, 1, UNROLL, F, O, A, B><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, f);
+    map_rows_kernel<NIN, VEC, UNROLL, F, O, A, B><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, f);
     HPTB_CUDA_CHECK(cudaGetLastError());
     return HPTB_OK;
   }

@@ -234,6 +234,18 @@ __device__ __forceinline__ void load_pack(Pack<T, N>& dst, const T* src) {
 #pragma unroll
   for (int i = 0; i < bytes / chunk; ++i) d[i] = ldg_stream(s + i);
 }
+// re-read operands (a row broadcast over the outer dims): plain read-only loads that DO allocate in L1, so the
+// repeats are served by the SM's own L1 instead of crossing to L2 every time
+template <typename T, int N>
+__device__ __forceinline__ void load_pack_cached(Pack<T, N>& dst, const T* src) {
+  constexpr int bytes = sizeof(T) * N;
+  constexpr int chunk = bytes > 16 ? 16 : bytes;
+  typedef typename VecBytes<chunk>::type V;
+  const V* s = reinterpret_cast<const V*>(src);
+  V* d = reinterpret_cast<V*>(&dst);
+#pragma unroll
+  for (int i = 0; i < bytes / chunk; ++i) d[i] = __ldg(s + i);
+}
 template <typename T, int N>
 __device__ __forceinline__ void store_pack(T* dst, const Pack<T, N>& src) {
   constexpr int bytes = sizeof(T) * N;

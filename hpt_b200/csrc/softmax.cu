@@ -44,6 +44,20 @@ struct SoftmaxParams {
 template <typename C> __device__ __forceinline__ C sm_exp(C x) {
   if constexpr (std::is_same<C, float>::value) return expf(x); else return exp(x);
 }
+// exp(x − m) with the rounding error of the subtraction folded back in.  x − m rounds to sh with an absolute
+// error of up to ulp(sh)/2, which exp() turns into a RELATIVE error of |sh|·2^-24 (f32) — 18 ulp at sh = −36.
+// TwoSum recovers that error exactly (lo) and exp(sh + lo) = exp(sh)·(1 + lo) to first order.
+template <typename C> struct ShExp { C sh, ex; };
+template <typename C> __device__ __forceinline__ ShExp<C> sm_shift_exp(C x, C m) {
+  const C b = -m;
+  const C sh = x + b;
+  if (!(sh > Limits<C>::lowest())) return ShExp<C>{sh, sm_exp<C>(sh)};  // −inf / NaN: nothing to compensate
+  const C xv = sh - b, bv = sh - xv;
+  const C lo = (x - xv) + (b - bv);
+  const C e = sm_exp<C>(sh);
+  if constexpr (std::is_same<C, float>::value) return ShExp<C>{sh, fmaf(e, lo, e)};
+  else return ShExp<C>{sh, fma(e, lo, e)};
+}
 template <typename C> __device__ __forceinline__ C sm_log(C x) {
   if constexpr (std::is_same<C, float>::value) return logf(x); else return log(x);
 }
@@ -116,8 +130,8 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
     if (i < p.nchunks) {
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        const C sh = x[i][k] - mx;
-        const C ex = sm_exp<C>(sh);
+        const ShExp<C> se = sm_shift_exp<C>(x[i][k], mx);
+        const C sh = se.sh, ex = se.ex;
         sum += ex;  // padding lanes: exp(-inf - mx) = 0 (or NaN only if mx itself is -inf/NaN, handled by row)
         x[i][k] = p.log ? sh : ex;
       }
@@ -146,7 +160,16 @@ __device__ __forceinline__ MS<C> ms_combine(MS<C> a, MS<C> b) {
   if (a.s == (C)0) return b;  // identity (also avoids (-inf) - (-inf))
   if (b.s == (C)0) return a;
   const C m = sm_max<C>(a.m, b.m);
-  return MS<C>{m, a.s * sm_exp<C>(a.m - m) + b.s * sm_exp<C>(b.m - m)};
+  return MS<C>{m, a.s * sm_shift_exp<C>(a.m, m).ex + b.s * sm_shift_exp<C>(b.m, m).ex};
+}
+
+// fold one element into a running (max, Σ) pair: one exp per element
+template <typename C>
+__device__ __forceinline__ void ms_push(MS<C>& a, C x) {
+  if (a.s == (C)0) { a.m = x; a.s = (C)1; return; }
+  if (x <= a.m) a.s += sm_shift_exp<C>(x, a.m).ex;
+  else if (x > a.m) { a.s = a.s * sm_shift_exp<C>(a.m, x).ex + (C)1; a.m = x; }
+  else a.s += x;  // NaN element: poison the row as exp(NaN) would
 }
 
 template <typename T>
@@ -165,7 +188,7 @@ softmax_rows_stream(const T* __restrict__ in, typename type_of_dtype<promote_ct(
     MS<C> a{Limits<C>::lowest(), (C)0};
     for (int64_t e = tid; e < p.L; e += kSmThreads) {
       const C x = to_compute<O>(cast<O>(load_one(src + e * p.sa_in)));
-      a = ms_combine<C>(a, MS<C>{x, (C)1});
+      ms_push<C>(a, x);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -180,8 +203,8 @@ softmax_rows_stream(const T* __restrict__ in, typename type_of_dtype<promote_ct(
     const C ssum = r.s, lg = sm_log<C>(r.s);
     for (int64_t e = tid; e < p.L; e += kSmThreads) {
       const C x = to_compute<O>(cast<O>(src[e * p.sa_in]));
-      const C sh = x - r.m;
-      dst[e * p.sa_out] = from_compute<O>(p.log ? sh - lg : sm_exp<C>(sh) / ssum);
+      const ShExp<C> se = sm_shift_exp<C>(x, r.m);
+      dst[e * p.sa_out] = from_compute<O>(p.log ? se.sh - lg : se.ex / ssum);
     }
   }
 }
@@ -201,13 +224,13 @@ softmax_cols(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_o
   MS<C> a{Limits<C>::lowest(), (C)0};
   for (int64_t e = 0; e < p.L; ++e) {
     const C x = to_compute<O>(cast<O>(load_one(src + e * p.sa_in)));
-    a = ms_combine<C>(a, MS<C>{x, (C)1});
+    ms_push<C>(a, x);
   }
   const C ssum = a.s, lg = sm_log<C>(a.s);
   for (int64_t e = 0; e < p.L; ++e) {
     const C x = to_compute<O>(cast<O>(src[e * p.sa_in]));
-    const C sh = x - a.m;
-    dst[e * p.sa_out] = from_compute<O>(p.log ? sh - lg : sm_exp<C>(sh) / ssum);
+    const ShExp<C> se = sm_shift_exp<C>(x, a.m);
+    dst[e * p.sa_out] = from_compute<O>(p.log ? se.sh - lg : se.ex / ssum);
   }
 }
 

@@ -1,6 +1,8 @@
 // unary_inst.cu — one translation unit per FloatUnaryOps op; compiled with
 //   -DHPTB_OPENUM=<hptb_unary_op> -DHPTB_OPNAME=<name>
-// and exports `hptb_unary_<op>(in dtype) -> launcher`.  13 input dtypes × 3 kernels each.
+// and exports `hptb_unary_<op>(in dtype) -> launcher` for the float dtypes (T → T): the vector-only specialised
+// kernels.  Integer / bool inputs (→ f16/f32/f64 by FloatOutUnaryPromote) and unaligned layouts take the
+// runtime-typed kernel (dyn_inst.cu).
 #include "dtypes_x.h"
 #include "elementwise.cuh"
 #include "ops.cuh"
@@ -8,16 +10,14 @@
 
 namespace hptb {
 namespace {
-template <typename A>
+template <typename T>
 struct Inst {
-  static constexpr int odt = promote_ct(dtype_of<A>::value, 0, HPTB_PROMOTE_FLOAT_UNARY);
-  typedef typename type_of_dtype<odt>::type O;
   static hptb_status launch(const MapPlan& plan, cudaStream_t s) {
-    typedef UnaryFn<HPTB_OPENUM, O, A> F;
+    typedef UnaryFn<HPTB_OPENUM, T, T> F;
     F f;
-    f.alpha = (compute_t<O>)plan.alpha;
-    f.beta = (compute_t<O>)plan.beta;
-    return launch_map<1, F, O, A, A>(plan, f, s);
+    f.alpha = (compute_t<T>)plan.alpha;
+    f.beta = (compute_t<T>)plan.beta;
+    return launch_map<1, F, T, T, T>(plan, f, s);
   }
 };
 }  // namespace
@@ -26,10 +26,10 @@ struct Inst {
 extern "C" hptb::MapLauncher HPTB_CAT(hptb_unary_, HPTB_OPNAME)(int in) {
   using namespace hptb;
   switch (in) {
-#define X(T, N, E) \
-  case E: return &Inst<T>::launch;
-    HPTB_FOR_DTYPES(X)
-#undef X
+    case HPTB_F16: return &Inst<f16>::launch;
+    case HPTB_BF16: return &Inst<bf16>::launch;
+    case HPTB_F32: return &Inst<float>::launch;
+    case HPTB_F64: return &Inst<double>::launch;
     default: return nullptr;
   }
 }
