@@ -59,13 +59,16 @@ def units():
     return u
 
 
-def write_ninja():
+def write_ninja(variant="", extra=""):
+    global BUILD
+    if variant:
+        BUILD = os.path.join(ROOT, "build", "variant_" + variant)
     os.makedirs(BUILD, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     lines = [
         "ninja_required_version = 1.3",
         f"nvcc = {NVCC}",
-        f"nvflags = {NVCC_FLAGS}",
+        f"nvflags = {NVCC_FLAGS} {extra}",
         f"cxxflags = {CXX_FLAGS}",
         "rule nvcc",
         "  command = $nvcc $nvflags $defs -MD -MF $out.d -c $in -o $out",
@@ -94,7 +97,7 @@ def write_ninja():
             obj = os.path.join(BUILD, "obj", src[:-4] + ".o")
             lines += [f"build {obj}: cxx {os.path.join(CSRC, src)}"]
             objs.append(obj)
-    lib = os.path.join(LIBDIR, "libhpt_b200.so")
+    lib = os.path.join(LIBDIR, f"libhpt_b200_{variant}.so" if variant else "libhpt_b200.so")
     lines += [f"build {lib}: link {' '.join(objs)}", f"default {lib}", ""]
     with open(os.path.join(BUILD, "build.ninja"), "w") as f:
         f.write("\n".join(lines))
@@ -124,10 +127,17 @@ def main():
         shutil.rmtree(BUILD, ignore_errors=True)
         shutil.rmtree(LIBDIR, ignore_errors=True)
         shutil.rmtree(os.path.join(ROOT, "oracle", "_build"), ignore_errors=True)
-    lib = write_ninja()
+    # tuning builds: `python build.py --variant u8 -DHPTB_RED_UNROLL=8 …` → hpt_b200/lib/libhpt_b200_u8.so
+    variant, extra = "", []
+    args = sys.argv[1:]
+    if "--variant" in args:
+        variant = args[args.index("--variant") + 1]
+        extra = [a for a in args if a.startswith("-D")]
+    lib = write_ninja(variant, " ".join(extra))
     jobs = os.environ.get("HPTB_BUILD_JOBS", str(os.cpu_count() or 4))
     subprocess.check_call(["ninja", "-C", BUILD, "-j", jobs] + (["-v"] if "-v" in sys.argv else []))
-    build_oracle()
+    if not variant:
+        build_oracle()
     print("built", lib)
 
 

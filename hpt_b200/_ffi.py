@@ -8,7 +8,9 @@ import os
 from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhpt_b200.so")
+# HPTB_LIB_VARIANT selects a tuning build (python build.py --variant NAME …), used only by tools/sweep.py
+_VARIANT = os.environ.get("HPTB_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "lib", f"libhpt_b200_{_VARIANT}.so" if _VARIANT else "libhpt_b200.so")
 MAX_DIMS = 8
 
 if not os.path.exists(LIB_PATH):

@@ -7,10 +7,11 @@
 namespace hptb {
 namespace {
 typedef HPTB_OUT O;
-hptb_status launch_binary(const MapPlan& plan, cudaStream_t s) { return launch_map_dyn<2, DynBinaryFn<O>, O>(plan, s); }
-hptb_status launch_cast(const MapPlan& plan, cudaStream_t s) { return launch_map_dyn<1, DynCastFn<O>, O>(plan, s); }
+constexpr int kMaxIn = sizeof(O) >= 4 ? (int)sizeof(O) : 4;  // widest input a binary / unary op with Output O can see
+hptb_status launch_binary(const MapPlan& plan, cudaStream_t s) { return launch_map_dyn<2, kMaxIn, DynBinaryFn<O>, O>(plan, s); }
+hptb_status launch_cast(const MapPlan& plan, cudaStream_t s) { return launch_map_dyn<1, 8, DynCastFn<O>, O>(plan, s); }
 #if HPTB_OUT_FLOAT
-hptb_status launch_unary(const MapPlan& plan, cudaStream_t s) { return launch_map_dyn<1, DynUnaryFn<O>, O>(plan, s); }
+hptb_status launch_unary(const MapPlan& plan, cudaStream_t s) { return launch_map_dyn<1, kMaxIn, DynUnaryFn<O>, O>(plan, s); }
 #endif
 }  // namespace
 }  // namespace hptb

@@ -25,6 +25,9 @@
 namespace hptb {
 
 constexpr int kMapThreads = 256;
+#ifndef HPTB_MAP_UNROLL_SCALE
+#define HPTB_MAP_UNROLL_SCALE 1
+#endif
 constexpr int kMaxOuter = HPTB_MAX_DIMS - 1;
 
 struct RowsParams {
@@ -330,7 +333,7 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
     if (!fits_u32(p.cpr) || p.total_chunks >= (int64_t(1) << 32)) big = true;
     p.use64 = big ? 1 : 0;
     p.cpr_div = FastDiv(big ? 1u : (uint32_t)p.cpr);
-    constexpr int UNROLL = VEC >= 16 ? 1 : VEC >= 8 ? 2 : 4;  // ~16 elements per thread
+    constexpr int UNROLL = (VEC >= 16 ? 1 : VEC >= 8 ? 2 : 4) * HPTB_MAP_UNROLL_SCALE;  // 64 bytes per operand per thread
     int64_t blocks = (p.total_chunks + kMapThreads * UNROLL - 1) / (kMapThreads * UNROLL);
     if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "elementwise: tensor too large for one launch");
     map_rows_kernel<NIN, VEC, UNROLL, F, O, A, B><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, f);

@@ -27,14 +27,14 @@ struct DynExtra {
   double alpha, beta;
 };
 
-// raw storage for N elements of up to 8 bytes
-template <int N> struct alignas(16) RawPack {
-  uint32_t w[N * 2];
+// raw storage for N elements of up to MAXB bytes each (MAXB = 4 or 8)
+template <int N, int MAXB = 8> struct alignas(16) RawPack {
+  uint32_t w[(N * MAXB + 3) / 4 < 2 ? 2 : (N * MAXB + 3) / 4];
 };
 
 // N elements of `esz` bytes from p (aligned to min(16, N·esz)); cached = allocate in L1 (re-read operand)
-template <int N>
-__device__ __forceinline__ void load_raw(RawPack<N>& r, const unsigned char* p, int esz, bool cached) {
+template <int N, int MAXB>
+__device__ __forceinline__ void load_raw(RawPack<N, MAXB>& r, const unsigned char* p, int esz, bool cached) {
 #define HPTB_RAW_CASE(ESZ)                                                                     \
   {                                                                                            \
     constexpr int bytes = N * ESZ;                                                             \
@@ -48,30 +48,36 @@ __device__ __forceinline__ void load_raw(RawPack<N>& r, const unsigned char* p, 
     case 1: HPTB_RAW_CASE(1) break;
     case 2: HPTB_RAW_CASE(2) break;
     case 4: HPTB_RAW_CASE(4) break;
-    default: HPTB_RAW_CASE(8) break;
+    default:
+      if constexpr (MAXB >= 8) HPTB_RAW_CASE(8)
+      break;
   }
 #undef HPTB_RAW_CASE
 }
 
 // place one element (in `one`) at position k of a raw pack (k is a compile-time constant after unrolling)
-template <int N>
-__device__ __forceinline__ void raw_insert(RawPack<N>& r, int k, const RawPack<1>& one, int esz) {
+template <int N, int MAXB>
+__device__ __forceinline__ void raw_insert(RawPack<N, MAXB>& r, int k, const RawPack<1, MAXB>& one, int esz) {
   switch (esz) {
     case 1: { const uint32_t sh = (k & 3) * 8; r.w[k >> 2] = (r.w[k >> 2] & ~(0xffu << sh)) | ((one.w[0] & 0xffu) << sh); } break;
     case 2: { const uint32_t sh = (k & 1) * 16; r.w[k >> 1] = (r.w[k >> 1] & ~(0xffffu << sh)) | ((one.w[0] & 0xffffu) << sh); } break;
     case 4: r.w[k] = one.w[0]; break;
-    default: r.w[2 * k] = one.w[0]; r.w[2 * k + 1] = one.w[1]; break;
+    default:
+      if constexpr (MAXB >= 8) { r.w[2 * k] = one.w[0]; r.w[2 * k + 1] = one.w[1]; }
+      break;
   }
 }
 
 // convert the N raw elements of runtime dtype `dt` to O (Hpt `Cast` semantics)
-template <typename O, int N>
-__device__ __forceinline__ void unpack_raw(O (&v)[N], const RawPack<N>& r, int dt) {
+template <typename O, int N, int MAXB>
+__device__ __forceinline__ void unpack_raw(O (&v)[N], const RawPack<N, MAXB>& r, int dt) {
   switch (dt) {
 #define X(T, NAME, E)                                                              \
   case E: {                                                                        \
-    const T* t = reinterpret_cast<const T*>(r.w);                                  \
-    _Pragma("unroll") for (int k = 0; k < N; ++k) v[k] = cast<O>(t[k]);            \
+    if constexpr (sizeof(T) <= MAXB) {                                             \
+      const T* t = reinterpret_cast<const T*>(r.w);                                \
+      _Pragma("unroll") for (int k = 0; k < N; ++k) v[k] = cast<O>(t[k]);          \
+    }                                                                              \
   } break;
     HPTB_FOR_DTYPES(X)
 #undef X
@@ -122,12 +128,12 @@ struct DynCastFn {
 };
 
 // ---- kernel ------------------------------------------------------------------------------------------------
-template <int NIN, int VEC, int UNROLL, typename Fn, typename O>
+template <int NIN, int VEC, int UNROLL, int MAXB, typename Fn, typename O>
 __global__ void __launch_bounds__(kMapThreads)
 map_dyn_kernel(O* __restrict__ out, const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, RowsParams p,
                DynExtra x) {
   const int64_t c0 = (int64_t)blockIdx.x * (kMapThreads * UNROLL) + threadIdx.x;
-  RawPack<VEC> ra[UNROLL], rb[UNROLL];
+  RawPack<VEC, MAXB> ra[UNROLL], rb[UNROLL];
   int64_t oo[UNROLL];
   int32_t cnt[UNROLL];
   const int esa = x.esz[0], esb = NIN == 2 ? x.esz[1] : 1;
@@ -149,41 +155,41 @@ map_dyn_kernel(O* __restrict__ out, const unsigned char* __restrict__ a, const u
       oo[u] = off[0] + e * p.inner_stride[0];
       const unsigned char* ap = a + (off[1] + e * p.inner_stride[1]) * esa;
       if (VEC == 1 || p.inner_stride[1] == 0) {
-        RawPack<1> one = {{0u, 0u}};
-        load_raw<1>(one, ap, esa, true);
+        RawPack<1, MAXB> one = {{0u, 0u}};
+        load_raw<1, MAXB>(one, ap, esa, true);
         ra[u].w[0] = one.w[0];
         ra[u].w[1] = one.w[1];
       } else if (cnt[u] == VEC) {
-        load_raw<VEC>(ra[u], ap, esa, p.reuse[1] != 0);
+        load_raw<VEC, MAXB>(ra[u], ap, esa, p.reuse[1] != 0);
       } else {  // ragged tail of a 1-D tensor: element-wise
 #pragma unroll
-        for (int k = 0; k < VEC * 2; ++k) ra[u].w[k] = 0u;
+        for (int k = 0; k < (int)(sizeof(ra[u].w) / 4); ++k) ra[u].w[k] = 0u;
 #pragma unroll
         for (int k = 0; k < VEC; ++k)
           if (k < cnt[u]) {
-            RawPack<1> one = {{0u, 0u}};
-            load_raw<1>(one, ap + k * esa, esa, true);
-            raw_insert<VEC>(ra[u], k, one, esa);
+            RawPack<1, MAXB> one = {{0u, 0u}};
+            load_raw<1, MAXB>(one, ap + k * esa, esa, true);
+            raw_insert<VEC, MAXB>(ra[u], k, one, esa);
           }
       }
       if constexpr (NIN == 2) {
         const unsigned char* bp = b + (off[2] + e * p.inner_stride[2]) * esb;
         if (VEC == 1 || p.inner_stride[2] == 0) {
-          RawPack<1> one = {{0u, 0u}};
-          load_raw<1>(one, bp, esb, true);
+          RawPack<1, MAXB> one = {{0u, 0u}};
+          load_raw<1, MAXB>(one, bp, esb, true);
           rb[u].w[0] = one.w[0];
           rb[u].w[1] = one.w[1];
         } else if (cnt[u] == VEC) {
-          load_raw<VEC>(rb[u], bp, esb, p.reuse[2] != 0);
+          load_raw<VEC, MAXB>(rb[u], bp, esb, p.reuse[2] != 0);
         } else {
 #pragma unroll
-          for (int k = 0; k < VEC * 2; ++k) rb[u].w[k] = 0u;
+          for (int k = 0; k < (int)(sizeof(rb[u].w) / 4); ++k) rb[u].w[k] = 0u;
 #pragma unroll
           for (int k = 0; k < VEC; ++k)
             if (k < cnt[u]) {
-              RawPack<1> one = {{0u, 0u}};
-              load_raw<1>(one, bp + k * esb, esb, true);
-              raw_insert<VEC>(rb[u], k, one, esb);
+              RawPack<1, MAXB> one = {{0u, 0u}};
+              load_raw<1, MAXB>(one, bp + k * esb, esb, true);
+              raw_insert<VEC, MAXB>(rb[u], k, one, esb);
             }
         }
       }
@@ -193,13 +199,13 @@ map_dyn_kernel(O* __restrict__ out, const unsigned char* __restrict__ a, const u
   for (int u = 0; u < UNROLL; ++u) {
     if (cnt[u] == 0) continue;
     O va[VEC], vb[VEC];
-    unpack_raw<O, VEC>(va, ra[u], x.dtype[0]);
+    unpack_raw<O, VEC, MAXB>(va, ra[u], x.dtype[0]);
     if (VEC > 1 && p.inner_stride[1] == 0) {
 #pragma unroll
       for (int k = 1; k < VEC; ++k) va[k] = va[0];
     }
     if constexpr (NIN == 2) {
-      unpack_raw<O, VEC>(vb, rb[u], x.dtype[1]);
+      unpack_raw<O, VEC, MAXB>(vb, rb[u], x.dtype[1]);
       if (VEC > 1 && p.inner_stride[2] == 0) {
 #pragma unroll
         for (int k = 1; k < VEC; ++k) vb[k] = vb[0];
@@ -224,7 +230,9 @@ constexpr int dyn_vec_width() {
   return sizeof(O) == 8 ? 2 : 4;
 }
 
-template <int NIN, typename Fn, typename O>
+// MAXB = the widest input element the launcher can be handed: 8 for casts; for binary / unary outputs the
+// promotion tables never pair a narrower Output with an 8-byte input (but i32/u32 ⊕ f16 → f16 is a 4-byte input)
+template <int NIN, int MAXB, typename Fn, typename O>
 hptb_status launch_map_dyn(const MapPlan& plan, cudaStream_t stream) {
   const Collapsed& c = plan.c;
   if (c.numel == 0) return HPTB_OK;
@@ -239,6 +247,7 @@ hptb_status launch_map_dyn(const MapPlan& plan, cudaStream_t stream) {
     if (!dtype_valid(plan.in_dtype[i])) return fail(HPTB_ERR_INVALID, "elementwise: bad input dtype");
     x.dtype[i] = plan.in_dtype[i];
     x.esz[i] = (int32_t)dtype_size(plan.in_dtype[i]);
+    if (x.esz[i] > MAXB) return fail(HPTB_ERR_DTYPE, "elementwise: %s input is wider than this kernel accepts", dtype_name(plan.in_dtype[i]));
     esz[i + 1] = dtype_size(plan.in_dtype[i]);
   }
   x.op = plan.op;
@@ -286,8 +295,8 @@ hptb_status launch_map_dyn(const MapPlan& plan, cudaStream_t stream) {
   constexpr int UNROLL = 4;
   int64_t blocks = (p.total_chunks + kMapThreads * UNROLL - 1) / (kMapThreads * UNROLL);
   if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "elementwise: tensor too large for one launch");
-  if (vec_ok) map_dyn_kernel<NIN, VEC, UNROLL, Fn, O><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, x);
-  else map_dyn_kernel<NIN, 1, UNROLL, Fn, O><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, x);
+  if (vec_ok) map_dyn_kernel<NIN, VEC, UNROLL, MAXB, Fn, O><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, x);
+  else map_dyn_kernel<NIN, 1, UNROLL, MAXB, Fn, O><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, x);
   HPTB_CUDA_CHECK(cudaGetLastError());
   return HPTB_OK;
 }

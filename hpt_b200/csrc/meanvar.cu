@@ -7,44 +7,40 @@
 // Accumulation is (Σx, Σx²) in f64 so that E[x²] − E[x]² does not cancel catastrophically; the two
 // f64 adds per element are far below the HBM-bound budget.  Runs on the same two reduction skeletons.
 #include "dtypes_x.h"
-#include "map_plan.h"
 #include "reduce.cuh"
-
-extern "C" __attribute__((weak)) hptb::MapLauncher hptb_cast_f16(int);
-extern "C" __attribute__((weak)) hptb::MapLauncher hptb_cast_bf16(int);
-extern "C" __attribute__((weak)) hptb::MapLauncher hptb_cast_f32(int);
-extern "C" __attribute__((weak)) hptb::MapLauncher hptb_cast_f64(int);
 
 namespace hptb {
 hptb_status build_reduce_plan(hptb_ctx* ctx, const hptb_tensor* in, const int32_t* axes, int naxes,
                               const hptb_tensor* out, ReducePlan* plan);  // api_reduce.cpp
 namespace {
 
-template <typename O> struct MV {
-  O mean, var;
-};
 struct SQ {
   double s, q;
 };
 
-template <typename T> struct MeanVarOp {
+// Two outputs (mean → out, variance → out2, same layout) written by the reduction kernel itself: one launch.
+template <typename T> struct MeanVarOp : PlainLocal<MeanVarOp<T>, T, SQ> {
   typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type O;
-  typedef MV<O> Out;
+  typedef O Out;
   typedef SQ Acc;
   static constexpr bool kIndexed = false;
+  static constexpr bool kTwoOutputs = true;
   static __device__ __forceinline__ Acc identity() { return SQ{0.0, 0.0}; }
   static __device__ __forceinline__ Acc pre(T x, int64_t) {
     const double v = (double)to_compute<O>(cast<O>(x));
     return SQ{v, v * v};
   }
   static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return SQ{a.s + b.s, a.q + b.q}; }
-  static __device__ __forceinline__ Out post(Acc a, double n) {
+  static __device__ __forceinline__ void store2(Out* mean, Out* var, int64_t off, Acc a, double n) {
     const double m = a.s / n;
     double v = a.q / n - m * m;
     if (v < 0.0) v = 0.0;
     typedef compute_t<O> C;
-    return Out{from_compute<O>((C)m), from_compute<O>((C)v)};
+    mean[off] = from_compute<O>((C)m);
+    var[off] = from_compute<O>((C)v);
   }
+  // unused by a two-output op (red_store never folds), present for the common interface
+  static __device__ __forceinline__ Out post(Acc a, double n) { return from_compute<O>((compute_t<O>)(a.s / n)); }
   static __device__ __forceinline__ Acc from_out(Out) { return identity(); }
 };
 
@@ -71,45 +67,42 @@ extern "C" hptb_status hptb_mean_var(hptb_ctx* ctx, const hptb_tensor* in, const
   bool same = mean_out->ndim == var_out->ndim;
   for (int i = 0; same && i < mean_out->ndim; ++i) same = mean_out->shape[i] == var_out->shape[i];
   if (!same) return fail(HPTB_ERR_SHAPE, "mean_var: mean_out and var_out shapes differ");
-  // reduce into a contiguous temp of (mean, var) pairs shaped like the outputs
-  hptb_tensor tmp = *mean_out;
-  int64_t n = 1;
-  for (int i = tmp.ndim - 1; i >= 0; --i) { tmp.strides[i] = n; n *= tmp.shape[i]; }
-  if (n == 0) return HPTB_OK;
-  const size_t osz = dtype_size(odt);
-  Scratch pairs;
-  HPTB_TRY(pairs.get(ctx, (size_t)n * 2 * osz, stream));
-  tmp.data = pairs.ptr;
+  bool same_layout = true;
+  for (int i = 0; i < mean_out->ndim; ++i)
+    if (mean_out->shape[i] != 1 && mean_out->strides[i] != var_out->strides[i]) same_layout = false;
+  // the kernel writes both results at the same element offset; a var_out with other strides is filled through
+  // a temporary that has mean_out's layout, then gathered with hptb_copy
+  hptb_tensor var_t = *var_out;
+  Scratch tmp;
+  if (!same_layout) {
+    int64_t span = 1;
+    for (int i = 0; i < mean_out->ndim; ++i) {
+      if (mean_out->shape[i] == 0) return HPTB_OK;
+      if (mean_out->strides[i] < 0) return fail(HPTB_ERR_UNSUPPORTED, "mean_var: negative strides in mean_out with differently laid out var_out");
+      span += (mean_out->shape[i] - 1) * mean_out->strides[i];
+    }
+    HPTB_TRY(tmp.get(ctx, (size_t)span * dtype_size(odt), stream));
+    var_t = *mean_out;
+    var_t.data = tmp.ptr;
+  }
   ReducePlan plan;
-  HPTB_TRY(build_reduce_plan(ctx, in, axes, naxes, &tmp, &plan));
+  HPTB_TRY(build_reduce_plan(ctx, in, axes, naxes, mean_out, &plan));
+  plan.out2 = var_t.data;
   plan.fold_out = 0;
-  DeviceGuard g(ctx->device);
-  cudaStream_t s = (cudaStream_t)stream;
   hptb_status st = HPTB_ERR_DTYPE;
-  switch (in->dtype) {
+  {
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (in->dtype) {
 #define X(T, N, E) \
   case E: st = run<T>(plan, s); break;
-    HPTB_FOR_DTYPES(X)
+      HPTB_FOR_DTYPES(X)
 #undef X
-    default: break;
+      default: break;
+    }
   }
   HPTB_TRY(st);
   count_launches(1);
-  // de-interleave into the caller's tensors (any strides) with the strided copy kernels
-  MapLauncher (*getter)(int) = odt == HPTB_F16 ? hptb_cast_f16 : odt == HPTB_BF16 ? hptb_cast_bf16 : odt == HPTB_F32 ? hptb_cast_f32 : hptb_cast_f64;
-  MapLauncher copy = getter ? getter(odt) : nullptr;
-  if (!copy) return fail(HPTB_ERR_DTYPE, "mean_var: copy kernel missing");
-  for (int which = 0; which < 2; ++which) {
-    hptb_tensor* dst = which ? var_out : mean_out;
-    int64_t strides[kMaxOperands][HPTB_MAX_DIMS] = {{0}};
-    for (int i = 0; i < dst->ndim; ++i) { strides[0][i] = dst->strides[i]; strides[1][i] = tmp.strides[i] * 2; }
-    MapPlan mp;
-    collapse(dst->ndim, dst->shape, 2, strides, nullptr, &mp.c);
-    mp.ptr[0] = dst->data;
-    mp.ptr[1] = static_cast<char*>(pairs.ptr) + which * osz;
-    mp.sm_count = ctx->sm_count;
-    HPTB_TRY(copy(mp, s));
-    count_launches(1);
-  }
+  if (!same_layout) HPTB_TRY(hptb_copy(ctx, &var_t, var_out, stream));
   return HPTB_OK;
 }

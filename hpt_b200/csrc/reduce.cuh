@@ -21,6 +21,8 @@
 // Accumulation: f32 for f16/bf16/f32 (the reference sums halves in half precision,
 // reduce_classes.cuh:58-61), f64 for f64, wrapping integer arithmetic in T for ints, OR/AND for bool.
 #pragma once
+#include <cstdlib>
+
 #include "common.h"
 #include "context.h"
 #include "layout.h"
@@ -31,6 +33,9 @@
 namespace hptb {
 
 constexpr int kRedThreads = 256;
+#ifndef HPTB_RED_UNROLL
+#define HPTB_RED_UNROLL 4
+#endif
 constexpr int kRedMaxDims = HPTB_MAX_DIMS;
 
 // ---- op traits ---------------------------------------------------------------------------------------
@@ -82,8 +87,19 @@ template <typename C> __device__ __forceinline__ C red_one() {
   else return (C)1;
 }
 
+// Per-thread running state.  Ordinary reductions keep an Acc; arg reductions keep (value, iteration number) and
+// rebuild the 64-bit element index once, after the loop (PlainLocal / ArgOp below).
+template <typename D, typename T, typename AccT>
+struct PlainLocal {
+  typedef AccT Local;
+  static constexpr bool kTwoOutputs = false;
+  static __device__ __forceinline__ Local local_identity() { return D::identity(); }
+  static __device__ __forceinline__ void accumulate(Local& l, T x, int32_t) { l = D::combine(l, D::pre(x, 0)); }
+  static __device__ __forceinline__ AccT finish(Local l, int64_t, int64_t, int, int) { return l; }
+};
+
 // SUM: common_reduce.rs:32-52 (identity ZERO, combine _add), output dtype T
-template <typename T> struct ReduceOp<HPTB_SUM, T> {
+template <typename T> struct ReduceOp<HPTB_SUM, T> : PlainLocal<ReduceOp<HPTB_SUM, T>, T, compute_t<T>> {
   typedef T Out;
   typedef compute_t<T> Acc;
   static constexpr bool kIndexed = false;
@@ -94,7 +110,7 @@ template <typename T> struct ReduceOp<HPTB_SUM, T> {
   static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
 };
 // PROD: common_reduce.rs:80-99
-template <typename T> struct ReduceOp<HPTB_PROD, T> {
+template <typename T> struct ReduceOp<HPTB_PROD, T> : PlainLocal<ReduceOp<HPTB_PROD, T>, T, compute_t<T>> {
   typedef T Out;
   typedef compute_t<T> Acc;
   static constexpr bool kIndexed = false;
@@ -105,7 +121,7 @@ template <typename T> struct ReduceOp<HPTB_PROD, T> {
   static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
 };
 // SUM_SQUARE: hpt-traits/src/ops/reduce.rs:171-175 (Σ x², in T)
-template <typename T> struct ReduceOp<HPTB_SUM_SQUARE, T> {
+template <typename T> struct ReduceOp<HPTB_SUM_SQUARE, T> : PlainLocal<ReduceOp<HPTB_SUM_SQUARE, T>, T, compute_t<T>> {
   typedef T Out;
   typedef compute_t<T> Acc;
   static constexpr bool kIndexed = false;
@@ -116,7 +132,7 @@ template <typename T> struct ReduceOp<HPTB_SUM_SQUARE, T> {
   static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
 };
 // MAX / MIN: common_reduce.rs:101-168 (identity NEG_INF / INF; f32::max/min ignore NaN)
-template <typename T> struct ReduceOp<HPTB_MAX, T> {
+template <typename T> struct ReduceOp<HPTB_MAX, T> : PlainLocal<ReduceOp<HPTB_MAX, T>, T, compute_t<T>> {
   typedef T Out;
   typedef compute_t<T> Acc;
   static constexpr bool kIndexed = false;
@@ -126,7 +142,7 @@ template <typename T> struct ReduceOp<HPTB_MAX, T> {
   static __device__ __forceinline__ Out post(Acc a, double) { return from_compute<T>(a); }
   static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
 };
-template <typename T> struct ReduceOp<HPTB_MIN, T> {
+template <typename T> struct ReduceOp<HPTB_MIN, T> : PlainLocal<ReduceOp<HPTB_MIN, T>, T, compute_t<T>> {
   typedef T Out;
   typedef compute_t<T> Acc;
   static constexpr bool kIndexed = false;
@@ -138,7 +154,8 @@ template <typename T> struct ReduceOp<HPTB_MIN, T> {
 };
 // MEAN: common_reduce.rs:352-380 — cast to FloatOutBinaryPromote<T,T>, Σ, ÷ n.  (The reference rounds n to
 // the output dtype before dividing; here the division uses the exact count in the compute type.)
-template <typename T> struct ReduceOp<HPTB_MEAN, T> {
+template <typename T> struct ReduceOp<HPTB_MEAN, T>
+    : PlainLocal<ReduceOp<HPTB_MEAN, T>, T, compute_t<typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type>> {
   typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type Out;
   typedef compute_t<Out> Acc;
   static constexpr bool kIndexed = false;
@@ -149,7 +166,8 @@ template <typename T> struct ReduceOp<HPTB_MEAN, T> {
   static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<Out>(o); }
 };
 // LOGSUMEXP: common_reduce.rs:451-480 — ln Σ exp(x), no max shift (as the reference; overflows to +inf alike)
-template <typename T> struct ReduceOp<HPTB_LOGSUMEXP, T> {
+template <typename T> struct ReduceOp<HPTB_LOGSUMEXP, T>
+    : PlainLocal<ReduceOp<HPTB_LOGSUMEXP, T>, T, compute_t<typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type>> {
   typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type Out;
   typedef compute_t<Out> Acc;
   static constexpr bool kIndexed = false;
@@ -196,22 +214,28 @@ template <typename T, bool IS_MAX> struct ArgOp {
   }
   static __device__ __forceinline__ Out post(Acc a, double) { return a.idx; }
   static __device__ __forceinline__ Acc from_out(Out) { return identity(); }
+  // running state of one thread: every accumulator sees strictly increasing indices, so a strict "better" test
+  // keeps the first occurrence; only the 32-bit iteration number is tracked per element and the 64-bit index
+  // (c0 + it·stride)·vec + k is rebuilt once.  it < 0: nothing beat the identity (all NaN / all -inf) → index 0.
+  struct Local {
+    V val;
+    int32_t it;
+  };
+  static constexpr bool kTwoOutputs = false;
+  static __device__ __forceinline__ Local local_identity() {
+    return Local{IS_MAX ? Limits<V>::lowest() : Limits<V>::highest(), -1};
+  }
+  static __device__ __forceinline__ void accumulate(Local& l, T x, int32_t it) {
+    const V v = to_compute<T>(x);
+    if (better(v, l.val)) { l.val = v; l.it = it; }
+  }
+  static __device__ __forceinline__ Acc finish(Local l, int64_t c0, int64_t stride, int vec, int k) {
+    if (l.it < 0) return identity();
+    return Acc{l.val, (c0 + (int64_t)l.it * stride) * vec + k};
+  }
 };
 template <typename T> struct ReduceOp<HPTB_ARGMAX, T> : ArgOp<T, true> {};
 template <typename T> struct ReduceOp<HPTB_ARGMIN, T> : ArgOp<T, false> {};
-
-// per-element accumulate.  Arg reductions: every accumulator sees strictly increasing indices, so a strict
-// "better" test keeps the first occurrence without comparing indices (the full tie rule is only needed when
-// accumulators are combined).
-template <typename Op, typename T>
-__device__ __forceinline__ void red_accumulate(typename Op::Acc& acc, T x, int64_t idx) {
-  if constexpr (Op::kIndexed) {
-    const auto v = to_compute<T>(x);
-    if (Op::better(v, acc.val)) { acc.val = v; acc.idx = idx; }
-  } else {
-    acc = Op::combine(acc, Op::pre(x, idx));
-  }
-}
 
 // ---- launch parameters ---------------------------------------------------------------------------------
 struct DimWalk {
@@ -230,10 +254,12 @@ struct RowsRedParams {
   int64_t inner_stride;
   int64_t cpr;         // chunks per inner run
   int64_t chunks;      // chunks per output = (prod outer) * cpr
-  int64_t S;           // CTAs per output (block variant)
+  int64_t S;           // CTAs per output (only with G == kRedThreads)
   int64_t chunks_per_split;
   double count;        // elements reduced per output
-  int32_t G;           // lanes per output (warp variant)
+  FastDiv cpr_div;     // chunk → (outer index, column)
+  int32_t G;           // threads per output: a power of two, 1..kRedThreads
+  int32_t logG;
   int32_t use64;
   int32_t fold_out;    // combine with the previous contents of out
 };
@@ -250,7 +276,7 @@ struct ColsRedParams {
   int32_t TX;          // lanes along C (power of two ≤ 32)
   int32_t use64;
   int32_t fold_out;
-  int32_t index_dim;   // (arg reduce) unused: the single reduced dim is red.shape[0]
+  int32_t pad;
 };
 
 __device__ __forceinline__ void walk2(int64_t idx, const DimWalk& w, int use64, int64_t& oa, int64_t& ob) {
@@ -321,8 +347,7 @@ __device__ __forceinline__ Acc warp_reduce(Acc v, int width) {
   return v;
 }
 
-// combine S partials for `n` adjacent outputs; the last CTA to take a ticket does the work.
-// returns true in the CTA that must finish.  `scratch` holds [tile][S][n] accumulators.
+// the last CTA (of S) to take a ticket finishes the output group; the counter resets itself for the next launch
 __device__ __forceinline__ bool take_ticket(uint32_t* ticket, uint32_t S) {
   __shared__ uint32_t s_last;
   __threadfence();
@@ -330,7 +355,7 @@ __device__ __forceinline__ bool take_ticket(uint32_t* ticket, uint32_t S) {
   if (threadIdx.x == 0) {
     uint32_t old = atomicAdd(ticket, 1u);
     s_last = (old == S - 1);
-    if (old == S - 1) *ticket = 0;  // self-reset: the buffer is reusable by the next launch on this stream
+    if (old == S - 1) *ticket = 0;
   }
   __syncthreads();
   bool last = s_last != 0;
@@ -338,65 +363,80 @@ __device__ __forceinline__ bool take_ticket(uint32_t* ticket, uint32_t S) {
   return last;
 }
 
+// final write of one output (or of the (mean, var) pair of the two-output extension op)
+template <typename Op>
+__device__ __forceinline__ void red_store(typename Op::Out* out, typename Op::Out* out2, int64_t off, typename Op::Acc a,
+                                          double count, int fold) {
+  if constexpr (Op::kTwoOutputs) {
+    Op::store2(out, out2, off, a, count);
+  } else {
+    if (fold) a = Op::combine(Op::from_out(out[off]), a);
+    out[off] = Op::post(a, count);
+  }
+}
+
 // ---- rows kernel ---------------------------------------------------------------------------------------
-// BLOCK=false: a group of G lanes owns one output (M large, short rows); BLOCK=true: CTA (m, s) reduces split
-// s of output m.  VEC elements per load when the inner run is unit-stride and aligned, else VEC = 1.
-template <typename Op, typename T, int VEC, bool BLOCK>
+// A group of G threads (G = 1..256, power of two; 256/G outputs per CTA) owns one output and walks its
+// chunks with stride G; with S > 1 (few outputs, long rows; G = 256) CTA (m, s) reduces split s of output m
+// and the last CTA to finish combines the S partials.  VEC elements per load when the inner run is
+// unit-stride and aligned, else VEC = 1.
+template <typename Op, typename T, int VEC>
 __global__ void __launch_bounds__(kRedThreads)
-reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out, typename Op::Acc* __restrict__ scratch,
-                   uint32_t* __restrict__ tickets, RowsRedParams p) {
+reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out, typename Op::Out* __restrict__ out2,
+                   typename Op::Acc* __restrict__ scratch, uint32_t* __restrict__ tickets, RowsRedParams p) {
   typedef typename Op::Acc Acc;
-  constexpr int UNROLL = 4;
+  typedef typename Op::Local Local;
+  constexpr int UNROLL = HPTB_RED_UNROLL;
+  __shared__ Acc s_part[kRedThreads / 32];
   const int tid = threadIdx.x;
-  int64_t m, c_begin, c_end, c_step, split = 0;
-  int c_lane;
-  if constexpr (BLOCK) {
-    m = blockIdx.x / p.S;  // S is small; 64-bit division once per CTA
+  const int G = p.G;
+  int64_t m, c_begin, c_end, split = 0;
+  int g;
+  if (p.S > 1) {
+    m = blockIdx.x / p.S;  // 64-bit division once per CTA
     split = blockIdx.x - m * p.S;
     c_begin = split * p.chunks_per_split;
     c_end = c_begin + p.chunks_per_split;
     if (c_end > p.chunks) c_end = p.chunks;
-    c_lane = tid;
-    c_step = kRedThreads;
+    g = tid;
   } else {
-    const int per_cta = kRedThreads / p.G;
-    m = (int64_t)blockIdx.x * per_cta + tid / p.G;
+    m = (((int64_t)blockIdx.x * kRedThreads) >> p.logG) + (tid >> p.logG);
     c_begin = 0;
     c_end = p.chunks;
-    c_lane = tid & (p.G - 1);
-    c_step = p.G;
+    g = tid & (G - 1);
   }
   const bool active = m < p.M;
   int64_t in_off = 0, out_off = 0;
   if (active) walk2(m, p.kept, p.use64, in_off, out_off);
 
-  Acc acc[VEC];
+  Local acc[VEC];
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) acc[k] = Op::identity();
+  for (int k = 0; k < VEC; ++k) acc[k] = Op::local_identity();
 
   if (active) {
     const T* base = in + in_off;
-    for (int64_t c = c_begin + c_lane; c < c_end; c += c_step * UNROLL) {
+    const int64_t step = (int64_t)G * UNROLL;
+    int32_t it = 0;
+    for (int64_t c = c_begin + g; c < c_end; c += step, it += UNROLL) {
       Pack<T, VEC> v[UNROLL];
-      int64_t e0[UNROLL];
       int32_t cnt[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const int64_t cu = c + (int64_t)u * c_step;
+        const int64_t cu = c + (int64_t)u * G;
         cnt[u] = 0;
         if (cu < c_end) {
-          int64_t col = cu, roff = 0, dummy = 0;
+          int64_t col = cu, roff = 0;
           if (p.outer.n > 0) {
             int64_t r;
-            if (!p.use64) { r = p.outer.div[kRedMaxDims - 1].div((uint32_t)cu); }
-            else { r = cu / p.cpr; }
+            if (!p.use64) r = p.cpr_div.div((uint32_t)cu);
+            else r = cu / p.cpr;
             col = cu - r * p.cpr;
-            walk2(r, p.outer, p.use64, roff, dummy);
+            if (p.outer.n == 1) roff = r * p.outer.stride_a[0];
+            else { int64_t dummy = 0; walk2(r, p.outer, p.use64, roff, dummy); }
           }
           const int64_t e = col * VEC;
           const int64_t left = p.L - e;
           cnt[u] = left >= VEC ? VEC : (int32_t)left;
-          e0[u] = e;
           const T* src = base + roff + e * p.inner_stride;
           if (VEC > 1 && cnt[u] == VEC) load_pack<T, VEC>(v[u], src);
           else {
@@ -410,66 +450,62 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
       for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k)
-          if (k < cnt[u]) red_accumulate<Op, T>(acc[k], v[u].v[k], e0[u] + k);
+          if (k < cnt[u]) Op::accumulate(acc[k], v[u].v[k], it + u);
       }
     }
   }
-  Acc a = acc[0];
+  // thread total; for arg reductions the element index of (iteration it, slot k) is ((c_begin + g) + it·G)·VEC + k
+  // (exactly one reduced dim, so chunk number == column)
+  Acc a = Op::finish(acc[0], c_begin + g, G, VEC, 0);
 #pragma unroll
-  for (int k = 1; k < VEC; ++k) a = Op::combine(a, acc[k]);
+  for (int k = 1; k < VEC; ++k) a = Op::combine(a, Op::finish(acc[k], c_begin + g, G, VEC, k));
 
-  if constexpr (!BLOCK) {
-    a = warp_reduce<Op, Acc>(a, p.G);
-    if (active && c_lane == 0) {
-      if (p.fold_out) a = Op::combine(Op::from_out(out[out_off]), a);
-      out[out_off] = Op::post(a, p.count);
-    }
-  } else {
-    __shared__ Acc s_part[kRedThreads / 32];
-    a = warp_reduce<Op, Acc>(a, 32);
-    if ((tid & 31) == 0) s_part[tid >> 5] = a;
+  if (G <= 32) {
+    a = warp_reduce<Op, Acc>(a, G);
+    if (active && g == 0) red_store<Op>(out, out2, out_off, a, p.count, p.fold_out);
+    return;
+  }
+  // G = 64 / 128 / 256: warps_per_out partials per output through shared memory
+  a = warp_reduce<Op, Acc>(a, 32);
+  if ((tid & 31) == 0) s_part[tid >> 5] = a;
+  __syncthreads();
+  if (g == 0) {
+    const int w0 = tid >> 5, nw = G >> 5;
+    a = s_part[w0];
+    for (int w = 1; w < nw; ++w) a = Op::combine(a, s_part[w0 + w]);
+  }
+  if (p.S == 1) {
+    if (active && g == 0) red_store<Op>(out, out2, out_off, a, p.count, p.fold_out);
+    return;
+  }
+  // split outputs (G == kRedThreads, one output per CTA): fixed-slot partials + last-CTA combine → deterministic
+  if (tid == 0) scratch[m * p.S + split] = a;
+  if (take_ticket(tickets + m, (uint32_t)p.S)) {
+    Acc r = Op::identity();
+    for (int64_t s = tid; s < p.S; s += kRedThreads) r = Op::combine(r, load_cg(scratch + m * p.S + s));
+    r = warp_reduce<Op, Acc>(r, 32);
     __syncthreads();
-    if (tid < 32) {
-      a = tid < kRedThreads / 32 ? s_part[tid] : Op::identity();
-      a = warp_reduce<Op, Acc>(a, kRedThreads / 32);
-    }
-    if (p.S == 1) {
-      if (tid == 0) {
-        if (p.fold_out) a = Op::combine(Op::from_out(out[out_off]), a);
-        out[out_off] = Op::post(a, p.count);
-      }
-      return;
-    }
-    if (tid == 0) scratch[m * p.S + split] = a;
-    if (take_ticket(tickets + m, (uint32_t)p.S)) {
-      // fixed-order combine of the S partials by the finishing CTA
-      Acc r = Op::identity();
-      for (int64_t s = tid; s < p.S; s += kRedThreads) r = Op::combine(r, load_cg(scratch + m * p.S + s));
-      // lanes hold interleaved subsets; order within the tree is fixed by lane id → deterministic
-      r = warp_reduce<Op, Acc>(r, 32);
-      __syncthreads();
-      if ((tid & 31) == 0) s_part[tid >> 5] = r;
-      __syncthreads();
-      if (tid < 32) {
-        r = tid < kRedThreads / 32 ? s_part[tid] : Op::identity();
-        r = warp_reduce<Op, Acc>(r, kRedThreads / 32);
-        if (tid == 0) {
-          if (p.fold_out) r = Op::combine(Op::from_out(out[out_off]), r);
-          out[out_off] = Op::post(r, p.count);
-        }
-      }
+    if ((tid & 31) == 0) s_part[tid >> 5] = r;
+    __syncthreads();
+    if (tid == 0) {
+      r = s_part[0];
+      for (int w = 1; w < kRedThreads / 32; ++w) r = Op::combine(r, s_part[w]);
+      red_store<Op>(out, out2, out_off, r, p.count, p.fold_out);
     }
   }
 }
 
 // ---- cols kernel ---------------------------------------------------------------------------------------
+// The contiguous dim is kept: TX lanes run along it (VEC elements each), TY = 256/TX thread rows stride over
+// the reduced space; shared-memory tree over the thread rows; S row-splits per column tile combined by the
+// last CTA.
 template <typename Op, typename T, int VEC>
 __global__ void __launch_bounds__(kRedThreads)
-reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out, typename Op::Acc* __restrict__ scratch,
-                   uint32_t* __restrict__ tickets, ColsRedParams p) {
+reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out, typename Op::Out* __restrict__ out2,
+                   typename Op::Acc* __restrict__ scratch, uint32_t* __restrict__ tickets, ColsRedParams p) {
   typedef typename Op::Acc Acc;
-  typedef typename Op::Out Out;
-  constexpr int UNROLL = 4;
+  typedef typename Op::Local Local;
+  constexpr int UNROLL = HPTB_RED_UNROLL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Acc* sm = reinterpret_cast<Acc*>(smem_raw);  // [TY][TX*VEC]
   const int tid = threadIdx.x;
@@ -491,20 +527,19 @@ reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
   int64_t r_end = r_begin + p.rows_per_split;
   if (r_end > p.R) r_end = p.R;
 
-  Acc acc[VEC];
+  Local acc[VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) acc[j] = Op::identity();
+  for (int j = 0; j < VEC; ++j) acc[j] = Op::local_identity();
   if (col_ok) {
     const T* base = in + in_off + col;
-    for (int64_t r = r_begin + ty; r < r_end; r += (int64_t)TY * UNROLL) {
+    int32_t it = 0;
+    for (int64_t r = r_begin + ty; r < r_end; r += (int64_t)TY * UNROLL, it += UNROLL) {
       Pack<T, VEC> v[UNROLL];
       bool ok[UNROLL];
-      int64_t ri[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         const int64_t ru = r + (int64_t)u * TY;
         ok[u] = ru < r_end;
-        ri[u] = ru;
         if (ok[u]) {
           int64_t roff = 0, dummy = 0;
           if (p.red.n == 1) roff = ru * p.red.stride_a[0];
@@ -522,14 +557,14 @@ reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
         if (!ok[u]) continue;
 #pragma unroll
         for (int j = 0; j < VEC; ++j)
-          if (j < ncol) red_accumulate<Op, T>(acc[j], v[u].v[j], ri[u]);
+          if (j < ncol) Op::accumulate(acc[j], v[u].v[j], it + u);
       }
     }
   }
-  // tree over ty in shared memory
+  // tree over ty in shared memory (arg reductions: row index of iteration it is (r_begin + ty) + it·TY)
   const int W = TX * VEC;
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = acc[j];
+  for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = Op::finish(acc[j], r_begin + ty, TY, 1, 0);
   __syncthreads();
   for (int h = TY >> 1; h > 0; h >>= 1) {
     if (ty < h) {
@@ -541,14 +576,9 @@ reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
     }
     __syncthreads();
   }
-  Out* dst = out + out_off + col;
   if (p.S == 1) {
     if (ty == 0 && col_ok) {
-      for (int j = 0; j < ncol; ++j) {
-        Acc a = sm[tx * VEC + j];
-        if (p.fold_out) a = Op::combine(Op::from_out(dst[j]), a);
-        dst[j] = Op::post(a, p.count);
-      }
+      for (int j = 0; j < ncol; ++j) red_store<Op>(out, out2, out_off + col + j, sm[tx * VEC + j], p.count, p.fold_out);
     }
     return;
   }
@@ -559,17 +589,18 @@ reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
     for (int j = 0; j < VEC; ++j) my[tx * VEC + j] = sm[tx * VEC + j];
   }
   if (take_ticket(tickets + group, (uint32_t)p.S)) {
-    // thread (tx, ty): partial s = ty, ty+TY, … of its columns, then the same shared-memory tree
+    // thread (tx, ty): partials s = ty, ty+TY, … of its columns, then the same shared-memory tree
+    Acc part[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[j] = Op::identity();
+    for (int j = 0; j < VEC; ++j) part[j] = Op::identity();
     for (int64_t s = ty; s < p.S; s += TY) {
       const Acc* src = scratch + (group * p.S + s) * W;
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) acc[j] = Op::combine(acc[j], load_cg(src + tx * VEC + j));
+      for (int j = 0; j < VEC; ++j) part[j] = Op::combine(part[j], load_cg(src + tx * VEC + j));
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = acc[j];
+    for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = part[j];
     __syncthreads();
     for (int h = TY >> 1; h > 0; h >>= 1) {
       if (ty < h) {
@@ -582,17 +613,22 @@ reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
       __syncthreads();
     }
     if (ty == 0 && col_ok) {
-      for (int j = 0; j < ncol; ++j) {
-        Acc a = sm[tx * VEC + j];
-        if (p.fold_out) a = Op::combine(Op::from_out(dst[j]), a);
-        dst[j] = Op::post(a, p.count);
-      }
+      for (int j = 0; j < ncol; ++j) red_store<Op>(out, out2, out_off + col + j, sm[tx * VEC + j], p.count, p.fold_out);
     }
   }
 }
 
 // ---- host launcher -------------------------------------------------------------------------------------------
 inline bool red_fits_u32(int64_t v) { return v >= 0 && v < (int64_t(1) << 31); }
+
+// Launch-shape overrides for tuning sweeps (tools/sweep.py): HPTB_TUNE_G = threads per output of the rows
+// kernel, HPTB_TUNE_S = CTAs per output / per column tile.  Read per launch, only when HPTB_TUNE=1 at load.
+inline int64_t tune_knob(const char* name) {
+  static const bool on = [] { const char* e = getenv("HPTB_TUNE"); return e && e[0] == '1'; }();
+  if (!on) return 0;
+  const char* e = getenv(name);
+  return e ? atoll(e) : 0;
+}
 
 inline void fill_walk(DimWalk& w, const Collapsed& c, const int* dims, int n, bool with_out, bool& big) {
   w.n = n;
@@ -606,6 +642,21 @@ inline void fill_walk(DimWalk& w, const Collapsed& c, const int* dims, int n, bo
   }
 }
 
+// resident CTAs per SM of one kernel instantiation (registers / shared memory decide), asked once
+template <typename K>
+inline int ctas_per_sm(K kernel, size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kRedThreads, smem) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 1;
+  }
+  return n;
+}
+
+// Launch-shape policy.  These kernels are HBM-bound, so what matters is that every SM streams from the first
+// cycle to the last: a grid slightly larger than the number of resident CTA slots runs a second, mostly empty
+// wave (1.3 waves = 65 % efficiency).  So: either ONE balanced wave of fat threads (grid ≤ slots) or many
+// (≥ 4) waves of small CTAs, never in between.
 template <typename Op, typename T>
 hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   typedef typename Op::Acc Acc;
@@ -613,6 +664,7 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   const Collapsed& c = plan.c;
   const T* in = static_cast<const T*>(plan.in);
   Out* out = static_cast<Out*>(plan.out);
+  Out* out2 = static_cast<Out*>(plan.out2);
   constexpr int VECMAX = 16 / sizeof(T) > 8 ? 8 : 16 / sizeof(T);
   const int sms = plan.ctx->sm_count;
 
@@ -664,17 +716,22 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
     const int TY = kRedThreads / TX;
     p.col_tiles = (p.C + (int64_t)TX * vec - 1) / ((int64_t)TX * vec);
     const int64_t groups = p.K * p.col_tiles;
-    // splits: fill ~4 CTAs per SM, but keep ≥ 4 rows per thread
-    int64_t target = (int64_t)sms * 4;
+    const size_t smem = (size_t)kRedThreads * vec * sizeof(Acc);
+    static const int occ_v = ctas_per_sm(reduce_cols_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)>, (size_t)kRedThreads * VECMAX * sizeof(Acc));
+    static const int occ_1 = ctas_per_sm(reduce_cols_kernel<Op, T, 1>, (size_t)kRedThreads * sizeof(Acc));
+    const int64_t slots = (int64_t)sms * (vec > 1 ? occ_v : occ_1);
+    // row splits: fill one wave exactly when the column tiles alone cannot, keeping ≥ 8 rows per thread
     int64_t S = 1;
-    if (groups < target) {
-      S = (target + groups - 1) / groups;
-      int64_t maxS = (p.R + (int64_t)TY * 4 - 1) / ((int64_t)TY * 4);
+    if (groups < slots) {
+      S = slots / groups;
+      int64_t maxS = (p.R + (int64_t)TY * 8 - 1) / ((int64_t)TY * 8);
       if (S > maxS) S = maxS;
       if (S < 1) S = 1;
     }
+    if (int64_t t = tune_knob("HPTB_TUNE_S")) S = t > p.R ? p.R : t;
     p.rows_per_split = (p.R + S - 1) / S;
     S = (p.R + p.rows_per_split - 1) / p.rows_per_split;
+    if (S < 1) S = 1;
     p.S = S;
     if (groups * S > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "reduce: grid too large");
     if (groups * S >= (int64_t(1) << 31) || !red_fits_u32(p.R)) big = true;
@@ -686,13 +743,11 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
       tickets = ctx_tickets(plan.ctx, stream, (size_t)groups);
       if (!tickets) return fail(HPTB_ERR_OOM, "reduce: ticket buffer allocation failed");
     }
-    size_t smem = (size_t)kRedThreads * vec * sizeof(Acc);
     unsigned grid = (unsigned)(groups * S);
-#define HPTB_LAUNCH_COLS(V)                                                                                 \
-  reduce_cols_kernel<Op, T, V><<<grid, kRedThreads, smem, stream>>>(in, out, (Acc*)scratch.ptr, tickets, p)
-    if (vec == VECMAX && VECMAX > 1) HPTB_LAUNCH_COLS(VECMAX);
-    else HPTB_LAUNCH_COLS(1);
-#undef HPTB_LAUNCH_COLS
+    if (vec == VECMAX && VECMAX > 1)
+      reduce_cols_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)><<<grid, kRedThreads, smem, stream>>>(in, out, out2, (Acc*)scratch.ptr, tickets, p);
+    else
+      reduce_cols_kernel<Op, T, 1><<<grid, kRedThreads, smem, stream>>>(in, out, out2, (Acc*)scratch.ptr, tickets, p);
     HPTB_CUDA_CHECK(cudaGetLastError());
     return HPTB_OK;
   }
@@ -730,50 +785,58 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   p.chunks = router * p.cpr;
   if (!red_fits_u32(p.cpr) || p.chunks >= (int64_t(1) << 32) || !red_fits_u32(M)) big = true;
   p.use64 = big ? 1 : 0;
-  p.outer.div[kRedMaxDims - 1] = FastDiv(big ? 1u : (uint32_t)p.cpr);  // chunk → (outer index, col)
+  p.cpr_div = FastDiv(big ? 1u : (uint32_t)p.cpr);
 
-  const bool small = p.chunks <= 32 * 4 && M >= (int64_t)sms * 8;
-  Scratch scratch;
-  uint32_t* tickets = nullptr;
-  unsigned grid;
-  if (small) {
-    int G = 1;
-    while (G < 32 && (int64_t)G * 4 < p.chunks) G <<= 1;
-    p.G = G;
-    p.S = 1;
-    int64_t blocks = (M + (kRedThreads / G) - 1) / (kRedThreads / G);
-    if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "reduce: grid too large");
-    grid = (unsigned)blocks;
+  static const int occ_v = ctas_per_sm(reduce_rows_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)>, 0);
+  static const int occ_1 = ctas_per_sm(reduce_rows_kernel<Op, T, 1>, 0);
+  const int64_t cta_slots = (int64_t)sms * (vec > 1 ? occ_v : occ_1);
+  const int64_t thread_slots = cta_slots * kRedThreads;
+  // finest useful group: every thread still gets ≥ 8 chunks where the row allows it
+  int64_t G = 1;
+  while (G < kRedThreads && G * 8 < p.chunks) G <<= 1;
+  int64_t S = 1;
+  if (M * G >= 4 * thread_slots) {
+    if (G > 32) G = 32;  // many waves anyway: stay inside a warp (no barrier)
   } else {
-    int64_t target = (int64_t)sms * 8;
-    int64_t S = 1;
-    if (M < target) {
-      S = (target + M - 1) / M;
-      int64_t maxS = (p.chunks + kRedThreads * 4 - 1) / (kRedThreads * 4);  // ≥ 4 chunks per thread
+    while (G > 1 && M * G > thread_slots) G >>= 1;  // one balanced wave of fatter threads
+    if (G == kRedThreads && M * kRedThreads * 2 <= thread_slots) {
+      // few outputs, long rows: S CTAs per output, one wave, ≥ 8 chunks per thread
+      S = cta_slots / M;
+      int64_t maxS = (p.chunks + kRedThreads * 8 - 1) / (kRedThreads * 8);
       if (S > maxS) S = maxS;
       if (S < 1) S = 1;
     }
-    p.chunks_per_split = (p.chunks + S - 1) / S;
-    S = (p.chunks + p.chunks_per_split - 1) / p.chunks_per_split;
-    if (S < 1) S = 1;
-    p.S = S;
-    p.G = kRedThreads;
-    if (M * S > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "reduce: grid too large");
-    grid = (unsigned)(M * S);
-    if (S > 1) {
-      HPTB_TRY(scratch.get(plan.ctx, (size_t)(M * S) * sizeof(Acc), stream));
-      tickets = ctx_tickets(plan.ctx, stream, (size_t)M);
-      if (!tickets) return fail(HPTB_ERR_OOM, "reduce: ticket buffer allocation failed");
-    }
   }
-#define HPTB_LAUNCH_ROWS(V)                                                                                    \
-  do {                                                                                                         \
-    if (small) reduce_rows_kernel<Op, T, V, false><<<grid, kRedThreads, 0, stream>>>(in, out, nullptr, nullptr, p); \
-    else reduce_rows_kernel<Op, T, V, true><<<grid, kRedThreads, 0, stream>>>(in, out, (Acc*)scratch.ptr, tickets, p); \
-  } while (0)
-  if (vec == VECMAX && VECMAX > 1) HPTB_LAUNCH_ROWS(VECMAX);
-  else HPTB_LAUNCH_ROWS(1);
-#undef HPTB_LAUNCH_ROWS
+  if (int64_t t = tune_knob("HPTB_TUNE_G")) {
+    G = 1;
+    while (G < t && G < kRedThreads) G <<= 1;
+    S = 1;
+  }
+  if (int64_t t = tune_knob("HPTB_TUNE_S")) {
+    if (G == kRedThreads) S = t > p.chunks ? p.chunks : t;
+  }
+  p.chunks_per_split = (p.chunks + S - 1) / S;
+  S = (p.chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  if (S < 1) S = 1;
+  p.S = S;
+  p.G = (int32_t)G;
+  p.logG = 0;
+  while ((1 << p.logG) < G) ++p.logG;
+  const int64_t per_cta = kRedThreads / G;
+  const int64_t blocks = S > 1 ? M * S : (M + per_cta - 1) / per_cta;
+  if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "reduce: grid too large");
+  Scratch scratch;
+  uint32_t* tickets = nullptr;
+  if (S > 1) {
+    HPTB_TRY(scratch.get(plan.ctx, (size_t)(M * S) * sizeof(Acc), stream));
+    tickets = ctx_tickets(plan.ctx, stream, (size_t)M);
+    if (!tickets) return fail(HPTB_ERR_OOM, "reduce: ticket buffer allocation failed");
+  }
+  const unsigned grid = (unsigned)blocks;
+  if (vec == VECMAX && VECMAX > 1)
+    reduce_rows_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)><<<grid, kRedThreads, 0, stream>>>(in, out, out2, (Acc*)scratch.ptr, tickets, p);
+  else
+    reduce_rows_kernel<Op, T, 1><<<grid, kRedThreads, 0, stream>>>(in, out, out2, (Acc*)scratch.ptr, tickets, p);
   HPTB_CUDA_CHECK(cudaGetLastError());
   return HPTB_OK;
 }

@@ -8,6 +8,7 @@ struct ReducePlan {
   Collapsed c;  // operand 0 = out (stride 0 on reduced dims), operand 1 = in
   const void* in = nullptr;
   void* out = nullptr;
+  void* out2 = nullptr;  // second output of the fused mean/var extension (same layout as out)
   double count = 1.0;
   int fold_out = 0;
   hptb_ctx* ctx = nullptr;
