@@ -19,7 +19,9 @@
 #define HPTB_WEAK __attribute__((weak))
 extern "C" {
 // specialised, vector-only kernels: same-dtype binary (T,T)→T, float unary T→T, same-dtype copy by element size
-#define XB(F, NAME, E, K, B) HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME(int);
+#define XB(F, NAME, E, K, B)                               \
+  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME(int);     \
+  HPTB_WEAK hptb::MapLauncher hptb_binary_##NAME##_mixed(int, int);
 HPTB_FOR_BINARY_OPS(XB)
 #undef XB
 #define XU(NAME, E) HPTB_WEAK hptb::MapLauncher hptb_unary_##NAME(int);
@@ -53,6 +55,17 @@ static Getter binary_getter(int op) {
   switch (op) {
 #define XB(F, NAME, E, K, B) \
   case E: return hptb_binary_##NAME;
+    HPTB_FOR_BINARY_OPS(XB)
+#undef XB
+    default: return nullptr;
+  }
+}
+
+typedef MapLauncher (*MixedGetter)(int, int);
+static MixedGetter binary_mixed_getter(int op) {
+  switch (op) {
+#define XB(F, NAME, E, K, B) \
+  case E: return hptb_binary_##NAME##_mixed;
     HPTB_FOR_BINARY_OPS(XB)
 #undef XB
     default: return nullptr;
@@ -238,6 +251,9 @@ hptb_status hptb_binary(hptb_ctx* ctx, int op, const hptb_tensor* lhs, const hpt
   if (lhs->dtype == rhs->dtype && lhs->dtype == odt) {
     Getter g = binary_getter(op);
     fast = g ? g(odt) : nullptr;
+  } else if (lhs->dtype != rhs->dtype) {
+    MixedGetter g = binary_mixed_getter(op);
+    fast = g ? g(lhs->dtype, rhs->dtype) : nullptr;
   }
   return run_map(ctx, fast, dyn_launcher(kDynBinary, odt), op, out, lhs, rhs, 0.0, 0.0, stream);
 }

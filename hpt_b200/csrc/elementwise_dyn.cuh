@@ -85,6 +85,25 @@ __device__ __forceinline__ void unpack_raw(O (&v)[N], const RawPack<N, MAXB>& r,
   }
 }
 
+// the same for all UNROLL packs of one operand under a single switch
+template <typename O, int N, int U, int MAXB>
+__device__ __forceinline__ void unpack_all(O (&v)[U][N], const RawPack<N, MAXB> (&r)[U], int dt) {
+  switch (dt) {
+#define X(T, NAME, E)                                                                \
+  case E: {                                                                          \
+    if constexpr (sizeof(T) <= MAXB) {                                               \
+      _Pragma("unroll") for (int u = 0; u < U; ++u) {                                \
+        const T* t = reinterpret_cast<const T*>(r[u].w);                             \
+        _Pragma("unroll") for (int k = 0; k < N; ++k) v[u][k] = cast<O>(t[k]);       \
+      }                                                                              \
+    }                                                                                \
+  } break;
+    HPTB_FOR_DTYPES(X)
+#undef X
+    default: break;
+  }
+}
+
 // ---- operators with the op code as a launch parameter ---------------------------------------------------
 template <typename O>
 struct DynBinaryFn {
@@ -195,25 +214,26 @@ map_dyn_kernel(O* __restrict__ out, const unsigned char* __restrict__ a, const u
       }
     }
   }
+  // convert: ONE warp-uniform switch per operand per thread (not per pack), then the operator
+  O va[UNROLL][VEC], vb[UNROLL][VEC];
+  unpack_all<O, VEC, UNROLL, MAXB>(va, ra, x.dtype[0]);
+  if constexpr (NIN == 2) unpack_all<O, VEC, UNROLL, MAXB>(vb, rb, x.dtype[1]);
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u) {
     if (cnt[u] == 0) continue;
-    O va[VEC], vb[VEC];
-    unpack_raw<O, VEC, MAXB>(va, ra[u], x.dtype[0]);
     if (VEC > 1 && p.inner_stride[1] == 0) {
 #pragma unroll
-      for (int k = 1; k < VEC; ++k) va[k] = va[0];
+      for (int k = 1; k < VEC; ++k) va[u][k] = va[u][0];
     }
     if constexpr (NIN == 2) {
-      unpack_raw<O, VEC, MAXB>(vb, rb[u], x.dtype[1]);
       if (VEC > 1 && p.inner_stride[2] == 0) {
 #pragma unroll
-        for (int k = 1; k < VEC; ++k) vb[k] = vb[0];
+        for (int k = 1; k < VEC; ++k) vb[u][k] = vb[u][0];
       }
     }
     Pack<O, VEC> po;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) po.v[k] = Fn::apply(va[k], NIN == 2 ? vb[k] : va[k], x);
+    for (int k = 0; k < VEC; ++k) po.v[k] = Fn::apply(va[u][k], NIN == 2 ? vb[u][k] : va[u][k], x);
     if (cnt[u] == VEC) store_pack<O, VEC>(out + oo[u], po);
     else {
 #pragma unroll

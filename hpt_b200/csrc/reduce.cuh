@@ -254,10 +254,11 @@ struct RowsRedParams {
   int64_t inner_stride;
   int64_t cpr;         // chunks per inner run
   int64_t chunks;      // chunks per output = (prod outer) * cpr
-  int64_t S;           // CTAs per output (only with G == kRedThreads)
+  int64_t S;           // splits per output: CTAs (G == kRedThreads) or warps (G == 32) that share one output
   int64_t chunks_per_split;
   double count;        // elements reduced per output
   FastDiv cpr_div;     // chunk → (outer index, column)
+  FastDiv S_div;       // virtual row → (output, split) in warp mode
   int32_t G;           // threads per output: a power of two, 1..kRedThreads
   int32_t logG;
   int32_t use64;
@@ -392,19 +393,24 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
   const int G = p.G;
   int64_t m, c_begin, c_end, split = 0;
   int g;
-  if (p.S > 1) {
+  if (p.S > 1 && G == kRedThreads) {
     m = blockIdx.x / p.S;  // 64-bit division once per CTA
     split = blockIdx.x - m * p.S;
-    c_begin = split * p.chunks_per_split;
-    c_end = c_begin + p.chunks_per_split;
-    if (c_end > p.chunks) c_end = p.chunks;
     g = tid;
   } else {
-    m = (((int64_t)blockIdx.x * kRedThreads) >> p.logG) + (tid >> p.logG);
-    c_begin = 0;
-    c_end = p.chunks;
+    // virtual row v = (output, split): one group of G threads each (splits only with G == 32)
+    const int64_t v = (((int64_t)blockIdx.x * kRedThreads) >> p.logG) + (tid >> p.logG);
+    m = v;
+    if (p.S > 1) {
+      if (!p.use64) m = p.S_div.div((uint32_t)v);
+      else m = v / p.S;
+      split = v - m * p.S;
+    }
     g = tid & (G - 1);
   }
+  c_begin = split * p.chunks_per_split;
+  c_end = c_begin + p.chunks_per_split;
+  if (c_end > p.chunks) c_end = p.chunks;
   const bool active = m < p.M;
   int64_t in_off = 0, out_off = 0;
   if (active) walk2(m, p.kept, p.use64, in_off, out_off);
@@ -462,7 +468,29 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
 
   if (G <= 32) {
     a = warp_reduce<Op, Acc>(a, G);
-    if (active && g == 0) red_store<Op>(out, out2, out_off, a, p.count, p.fold_out);
+    if (p.S == 1) {
+      if (active && g == 0) red_store<Op>(out, out2, out_off, a, p.count, p.fold_out);
+      return;
+    }
+    // warp mode with splits (G == 32: the warp is uniform in m): fixed-slot partial, warp-level ticket, the
+    // last warp to arrive combines the S partials in slot order → deterministic
+    if (!active) return;
+    const int lane = tid & 31;
+    uint32_t last = 0;
+    if (lane == 0) {
+      scratch[m * p.S + split] = a;
+      __threadfence();
+      const uint32_t old = atomicAdd(tickets + m, 1u);
+      last = old == (uint32_t)p.S - 1;
+      if (last) tickets[m] = 0;  // self-reset for the next launch on this stream
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    Acc r = Op::identity();
+    for (int64_t sidx = lane; sidx < p.S; sidx += 32) r = Op::combine(r, load_cg(scratch + m * p.S + sidx));
+    r = warp_reduce<Op, Acc>(r, 32);
+    if (lane == 0) red_store<Op>(out, out2, out_off, r, p.count, p.fold_out);
     return;
   }
   // G = 64 / 128 / 256: warps_per_out partials per output through shared memory
@@ -791,20 +819,29 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   static const int occ_1 = ctas_per_sm(reduce_rows_kernel<Op, T, 1>, 0);
   const int64_t cta_slots = (int64_t)sms * (vec > 1 ? occ_v : occ_1);
   const int64_t thread_slots = cta_slots * kRedThreads;
-  // finest useful group: every thread still gets ≥ 8 chunks where the row allows it
+  // Launch shape.  Measured on B200 (profiles/, tools/sweep.py): a warp per (virtual) row beats wider groups, and
+  // many small CTAs beat one wave of fat ones (the hardware CTA scheduler balances SMs that stream at different
+  // speeds; a single static wave ends with the slowest SM).  So: G ≤ 32 lanes per row; when the outputs alone
+  // give less than one wave of threads, each output is split over S warps (virtual rows) — or, for very few
+  // outputs with long rows, over S whole CTAs — sized for ≥ 4 (warps) / 8 (CTAs) waves, ≥ 16 / 8 chunks per lane.
   int64_t G = 1;
-  while (G < kRedThreads && G * 8 < p.chunks) G <<= 1;
+  while (G < 32 && G * 8 < p.chunks) G <<= 1;
   int64_t S = 1;
-  if (M * G >= 4 * thread_slots) {
-    if (G > 32) G = 32;  // many waves anyway: stay inside a warp (no barrier)
-  } else {
-    while (G > 1 && M * G > thread_slots) G >>= 1;  // one balanced wave of fatter threads
-    if (G == kRedThreads && M * kRedThreads * 2 <= thread_slots) {
-      // few outputs, long rows: S CTAs per output, one wave, ≥ 8 chunks per thread
-      S = cta_slots / M;
-      int64_t maxS = (p.chunks + kRedThreads * 8 - 1) / (kRedThreads * 8);
-      if (S > maxS) S = maxS;
+  if (G == 32 && M * 32 < thread_slots) {
+    const int64_t need = (4 * thread_slots + M * 32 - 1) / (M * 32);
+    int64_t maxS = p.chunks / (32 * 16);
+    if (maxS < 1) maxS = 1;
+    int64_t Sw = need < maxS ? need : maxS;
+    if (Sw > 256) Sw = 256;
+    if (M * 32 * Sw < thread_slots && p.chunks >= (int64_t)kRedThreads * 16) {
+      G = kRedThreads;  // few outputs, long rows: whole CTAs per split
+      S = (8 * cta_slots + M - 1) / M;
+      int64_t maxC = p.chunks / (kRedThreads * 8);
+      if (S > maxC) S = maxC;
+      if (S > 8192) S = 8192;
       if (S < 1) S = 1;
+    } else {
+      S = Sw;
     }
   }
   if (int64_t t = tune_knob("HPTB_TUNE_G")) {
@@ -813,7 +850,7 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
     S = 1;
   }
   if (int64_t t = tune_knob("HPTB_TUNE_S")) {
-    if (G == kRedThreads) S = t > p.chunks ? p.chunks : t;
+    if (G == kRedThreads || G == 32) S = t > p.chunks ? p.chunks : t;
   }
   p.chunks_per_split = (p.chunks + S - 1) / S;
   S = (p.chunks + p.chunks_per_split - 1) / p.chunks_per_split;
@@ -823,8 +860,11 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   p.logG = 0;
   while ((1 << p.logG) < G) ++p.logG;
   const int64_t per_cta = kRedThreads / G;
-  const int64_t blocks = S > 1 ? M * S : (M + per_cta - 1) / per_cta;
+  const int64_t vrows = M * S;  // virtual rows
+  const int64_t blocks = G == kRedThreads ? vrows : (vrows + per_cta - 1) / per_cta;
   if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "reduce: grid too large");
+  if (vrows >= (int64_t(1) << 32)) p.use64 = 1;
+  p.S_div = FastDiv(p.use64 ? 1u : (uint32_t)S);
   Scratch scratch;
   uint32_t* tickets = nullptr;
   if (S > 1) {

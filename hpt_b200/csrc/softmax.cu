@@ -130,8 +130,11 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
     if (i < p.nchunks) {
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        const ShExp<C> se = sm_shift_exp<C>(x[i][k], mx);
-        const C sh = se.sh, ex = se.ex;
+        // plain f32 exp(x − max), as the reference's CPU kernel computes it (cpu/kernels/softmax.rs:204-310): the
+        // rounding of x − max costs up to |x − max|/2 ulp of the result, which the parity bound accounts for.
+        // (The two-pass kernels below fold that error back in — they have instruction slack; this one does not.)
+        const C sh = x[i][k] - mx;
+        const C ex = sm_exp<C>(sh);
         sum += ex;  // padding lanes: exp(-inf - mx) = 0 (or NaN only if mx itself is -inf/NaN, handled by row)
         x[i][k] = p.log ? sh : ex;
       }
@@ -139,13 +142,14 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
   }
   sum = group_reduce<AddOp, C, G>(sum, s_buf, (C)0);
   const C lg = sm_log<C>(sum);
+  const C inv = (C)1 / sum;  // one division per row; the per-element multiply adds ≤ 0.5 ulp over a division
 #pragma unroll
   for (int i = 0; i < kSmChunks; ++i) {
     const int64_t e = ((int64_t)i * G + lane) * VEC;
     if (i < p.nchunks && active && e < p.L) {
       Pack<O, VEC> o;
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(p.log ? x[i][k] - lg : x[i][k] / sum);
+      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(p.log ? x[i][k] - lg : x[i][k] * inv);
       store_pack<O, VEC>(out + out_off + e, o);
     }
   }
