@@ -17,6 +17,8 @@
 //     stride apart.
 // All indices are 64-bit capable; a 32-bit fast-divmod path is taken when the counts fit.
 #pragma once
+#include <cstdlib>
+
 #include "common.h"
 #include "layout.h"
 #include "map_plan.h"
@@ -84,78 +86,134 @@ __device__ __forceinline__ void walk_outer(int64_t row, int nouter, int use64, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// rows kernel: contiguous and inner-contiguous (broadcast) layouts
+// flat kernel: every operand is one contiguous run (or a single broadcast scalar)
 // ------------------------------------------------------------------------------------------------
+// These kernels are issue-bound before they are HBM-bound if the per-chunk index arithmetic is not kept to a
+// handful of instructions (ncu, profiles/r01b: the first general version spent 181 warp instructions per
+// 3×512-byte chunk and sat at 75 % issue utilisation, 70 % of HBM peak).  So: the flat case does no index
+// arithmetic at all, and the rows case below uses 32-bit offsets and one magic-number division per chunk.
+struct FlatParams {
+  int64_t n;             // elements
+  int32_t stride[3];     // 1, or 0 for a broadcast scalar input
+};
+
 template <int NIN, int VEC, int UNROLL, typename F, typename O, typename A, typename B>
 __global__ void __launch_bounds__(kMapThreads)
-map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, RowsParams p, F f) {
-  static_assert(VEC > 1, "the specialised rows kernel is vector-only; scalar layouts take the runtime-typed kernel");
-  const int64_t c0 = (int64_t)blockIdx.x * (kMapThreads * UNROLL) + threadIdx.x;
+map_flat_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, FlatParams p, F f) {
+  constexpr int64_t kPerCta = (int64_t)kMapThreads * UNROLL * VEC;
+  const int64_t e0 = (int64_t)blockIdx.x * kPerCta + (int64_t)threadIdx.x * VEC;
   Pack<A, VEC> pa[UNROLL];
   Pack<B, VEC> pb[UNROLL];
-  int64_t oo[UNROLL];
-  int32_t cnt[UNROLL];  // valid elements of the chunk (0 = chunk out of range)
+  // broadcast scalars are read once
+  A sa = load_one(a);
+  B sb = load_one(b);
+  if ((int64_t)(blockIdx.x + 1) * kPerCta <= p.n) {  // full CTA: no bounds checks
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t e = e0 + (int64_t)u * (kMapThreads * VEC);
+      if (p.stride[1] != 0) load_pack<A, VEC>(pa[u], a + e);
+      if (NIN == 2 && p.stride[2] != 0) load_pack<B, VEC>(pb[u], b + e);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t e = e0 + (int64_t)u * (kMapThreads * VEC);
+      Pack<O, VEC> po;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const A x = p.stride[1] != 0 ? pa[u].v[k] : sa;
+        if constexpr (NIN == 2) po.v[k] = f(x, p.stride[2] != 0 ? pb[u].v[k] : sb);
+        else po.v[k] = f(x);
+      }
+      store_pack<O, VEC>(out + e, po);
+    }
+    return;
+  }
+  // last CTA: element-wise bounds
+#pragma unroll 1
+  for (int u = 0; u < UNROLL; ++u) {
+    const int64_t e = e0 + (int64_t)u * (kMapThreads * VEC);
+#pragma unroll 1
+    for (int k = 0; k < VEC; ++k) {
+      if (e + k >= p.n) break;
+      const A x = p.stride[1] != 0 ? load_one(a + e + k) : sa;
+      if constexpr (NIN == 2) out[e + k] = f(x, p.stride[2] != 0 ? load_one(b + e + k) : sb);
+      else out[e + k] = f(x);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rows kernel: inner-contiguous layouts (row / column broadcasts, row-strided views), 32-bit offsets
+// ------------------------------------------------------------------------------------------------
+struct Rows32Params {
+  uint32_t total_chunks;
+  uint32_t cpr;                     // chunks per row
+  FastDiv cpr_div;
+  int32_t nouter;
+  int32_t inner_stride[3];          // 1 or 0
+  int32_t reuse[3];                 // operand re-read across rows (broadcast outer dim): keep it in L1
+  uint32_t outer_shape[kMaxOuter];  // innermost outer dim first
+  FastDiv outer_div[kMaxOuter];
+  int32_t outer_stride[3][kMaxOuter];
+};
+
+template <int NIN, int VEC, int UNROLL, typename F, typename O, typename A, typename B>
+__global__ void __launch_bounds__(kMapThreads)
+map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, Rows32Params p, F f) {
+  static_assert(VEC > 1, "the specialised rows kernel is vector-only; scalar layouts take the runtime-typed kernel");
+  const uint32_t c0 = blockIdx.x * (uint32_t)(kMapThreads * UNROLL) + threadIdx.x;
+  Pack<A, VEC> pa[UNROLL];
+  Pack<B, VEC> pb[UNROLL];
+  int32_t oo[UNROLL];
+  bool ok[UNROLL];
+  const int last = p.nouter - 1;
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u) {
-    const int64_t c = c0 + (int64_t)u * kMapThreads;
-    cnt[u] = 0;
-    if (c < p.total_chunks) {
-      int64_t row = 0, col = c;
-      int64_t off[3] = {0, 0, 0};
-      if (p.nouter > 0) {
-        if (!p.use64) { row = p.cpr_div.div((uint32_t)c); col = c - row * p.cpr; }
-        else { row = c / p.cpr; col = c - row * p.cpr; }
-        walk_outer<3>(row, p.nouter, p.use64, p.outer_shape, p.outer_div, p.outer_stride, off);
+    const uint32_t c = c0 + (uint32_t)u * kMapThreads;
+    ok[u] = c < p.total_chunks;
+    if (ok[u]) {
+      uint32_t r = p.cpr_div.div(c);
+      const int32_t e = (int32_t)((c - r * p.cpr) * VEC);
+      int32_t o0 = e, o1 = e * p.inner_stride[1], o2 = NIN == 2 ? e * p.inner_stride[2] : 0;
+#pragma unroll 1
+      for (int i = 0; i < last; ++i) {  // all but the outermost dim (usually none)
+        const uint32_t q = p.outer_div[i].div(r);
+        const int32_t rem = (int32_t)(r - q * p.outer_shape[i]);
+        o0 += rem * p.outer_stride[0][i];
+        o1 += rem * p.outer_stride[1][i];
+        if (NIN == 2) o2 += rem * p.outer_stride[2][i];
+        r = q;
       }
-      const int64_t e = col * VEC;
-      const int64_t left = p.inner - e;
-      cnt[u] = left >= VEC ? VEC : (int32_t)left;
-      oo[u] = off[0] + e;
-      const A* ap = a + off[1] + e * p.inner_stride[1];
+      o0 += (int32_t)r * p.outer_stride[0][last];
+      o1 += (int32_t)r * p.outer_stride[1][last];
+      if (NIN == 2) o2 += (int32_t)r * p.outer_stride[2][last];
+      oo[u] = o0;
       if (p.inner_stride[1] == 0) {
-        A s = load_one(ap);
+        const A s = load_one(a + o1);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) pa[u].v[k] = s;
-      } else if (cnt[u] == VEC) {
-        if (p.reuse[1]) load_pack_cached<A, VEC>(pa[u], ap);
-        else load_pack<A, VEC>(pa[u], ap);
-      } else {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k)
-          if (k < cnt[u]) pa[u].v[k] = ap[k];
-      }
+      } else if (p.reuse[1]) load_pack_cached<A, VEC>(pa[u], a + o1);
+      else load_pack<A, VEC>(pa[u], a + o1);
       if constexpr (NIN == 2) {
-        const B* bp = b + off[2] + e * p.inner_stride[2];
         if (p.inner_stride[2] == 0) {
-          B s = load_one(bp);
+          const B s = load_one(b + o2);
 #pragma unroll
           for (int k = 0; k < VEC; ++k) pb[u].v[k] = s;
-        } else if (cnt[u] == VEC) {
-          if (p.reuse[2]) load_pack_cached<B, VEC>(pb[u], bp);
-          else load_pack<B, VEC>(pb[u], bp);
-        } else {
-#pragma unroll
-          for (int k = 0; k < VEC; ++k)
-            if (k < cnt[u]) pb[u].v[k] = bp[k];
-        }
+        } else if (p.reuse[2]) load_pack_cached<B, VEC>(pb[u], b + o2);
+        else load_pack<B, VEC>(pb[u], b + o2);
       }
     }
   }
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u) {
-    if (cnt[u] == 0) continue;
+    if (!ok[u]) continue;
     Pack<O, VEC> po;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       if constexpr (NIN == 2) po.v[k] = f(pa[u].v[k], pb[u].v[k]);
       else po.v[k] = f(pa[u].v[k]);
     }
-    if (cnt[u] == VEC) store_pack<O, VEC>(out + oo[u], po);
-    else {
-#pragma unroll
-      for (int k = 0; k < VEC; ++k)
-        if (k < cnt[u]) out[oo[u] + k] = po.v[k];
-    }
+    store_pack<O, VEC>(out + oo[u], po);
   }
 }
 
@@ -271,6 +329,129 @@ map_tiled_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// transposing tile kernel: permuted operands staged through shared memory (same-size element types)
+// ------------------------------------------------------------------------------------------------
+// ncu on the register micro-tile kernel above (profiles/r01b): l1tex throughput 81 %, DRAM 57 % — its 16-byte
+// stores leave the lanes of a quarter-warp 32 KB apart, so one store instruction costs 32 L1 wavefronts instead
+// of 4 and the LSU pipe, not HBM, bounds it.  Here both global sides are quarter-warp contiguous (8 lanes × 16 B
+// = one 128-byte line): a permuted operand is read with 16-byte loads along its own unit-stride dim b,
+// scattered into a [b][a] shared-memory tile with element-sized stores, and read back with 16-byte loads along a
+// — the output's unit-stride dim — for the 16-byte global stores.  16-byte chunk c of tile row b lives at chunk
+// c ^ ((b / E) & 7), which makes the scatter and the gather bank-conflict free.  16 L1 wavefronts per 512 bytes
+// in + out instead of 36.
+constexpr int kSmemModeStaged = 1, kSmemModeDirect = 2, kSmemModeScalar = 3;
+
+template <int NIN, typename F, typename T>
+__global__ void __launch_bounds__(kMapThreads)
+map_tiled_smem_kernel(T* __restrict__ out, const T* __restrict__ a, const T* __restrict__ b, TileParams p, F f) {
+  constexpr int E = 16 / sizeof(T);  // elements per 16-byte pack
+  constexpr int TA = 16 * E, TB = 16 * E;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sm0 = reinterpret_cast<T*>(smem_raw);  // staged operand tiles, [TB][TA] each
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = lane >> 3, l8 = lane & 7;
+
+  // one tile per CTA: blockIdx → (tile along a, tile along b, batch)
+  int64_t ta, tb, batch;
+  {
+    const int64_t t = blockIdx.x;
+    if (!p.use64) {
+      uint32_t qq = p.tiles_a_div.div((uint32_t)t);
+      ta = (uint32_t)t - qq * (uint32_t)p.tiles_a;
+      uint32_t q2 = p.tiles_b_div.div(qq);
+      tb = qq - q2 * (uint32_t)p.tiles_b;
+      batch = q2;
+    } else {
+      int64_t qq = t / p.tiles_a;
+      ta = t - qq * p.tiles_a;
+      int64_t q2 = qq / p.tiles_b;
+      tb = qq - q2 * p.tiles_b;
+      batch = q2;
+    }
+  }
+  const int64_t a0 = ta * TA, b0 = tb * TB;
+  int64_t off[3] = {0, 0, 0};
+  walk_outer<3>(batch, p.nbatch, p.use64, p.batch_shape, p.batch_div, p.batch_stride, off);
+  const T* in[2] = {a + off[1], b + off[2]};
+
+  // phase 1: staged operands, 16-byte loads along b, element scatter into sm[b][a]
+  {
+    Pack<T, E> v[2][E];
+    bool ok[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const int g = i * 8 + warp;  // group of 4 consecutive a-rows × one half of the b extent
+      const int half = g / (4 * E);
+      const int ra = (g % (4 * E)) * 4 + q;
+      const int pb = half * 8 + l8;
+      ok[i] = (a0 + ra < p.A) && (b0 + (int64_t)pb * E < p.B);
+      if (ok[i]) {
+#pragma unroll
+        for (int o = 0; o < NIN; ++o)
+          if (p.mode[o + 1] == kSmemModeStaged)
+            load_pack<T, E>(v[o][i], in[o] + (a0 + ra) * p.sa[o + 1] + (b0 + (int64_t)pb * E));
+      }
+    }
+    int nst = 0;
+#pragma unroll
+    for (int o = 0; o < NIN; ++o) {
+      if (p.mode[o + 1] != kSmemModeStaged) continue;
+      T* sm = sm0 + (size_t)nst * TB * TA;
+      ++nst;
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        if (!ok[i]) continue;
+        const int g = i * 8 + warp;
+        const int half = g / (4 * E);
+        const int ra = (g % (4 * E)) * 4 + q;
+        const int pb = half * 8 + l8;
+        const int chunk = ra / E, slot = ra % E;
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          const int row = pb * E + k;
+          sm[row * TA + ((chunk ^ (pb & 7)) * E) + slot] = v[o][i].v[k];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // phase 2: 16-byte gathers along a, compute, 16-byte stores along a
+  T* dst = out + off[0];
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    const int g = i * 8 + warp;
+    const int halfa = g / (4 * E);
+    const int rb = (g % (4 * E)) * 4 + q;
+    const int ca = halfa * 8 + l8;
+    if (b0 + rb >= p.B || a0 + (int64_t)ca * E >= p.A) continue;
+    Pack<T, E> x[2];
+    int nst = 0;
+#pragma unroll
+    for (int o = 0; o < NIN; ++o) {
+      const int mode = p.mode[o + 1];
+      if (mode == kSmemModeStaged) {
+        const T* sm = sm0 + (size_t)nst * TB * TA;
+        ++nst;
+        x[o] = *reinterpret_cast<const Pack<T, E>*>(sm + rb * TA + ((ca ^ ((rb / E) & 7)) * E));
+      } else if (mode == kSmemModeDirect) {
+        load_pack<T, E>(x[o], in[o] + (b0 + rb) * p.sb[o + 1] + (a0 + (int64_t)ca * E));
+      } else {
+        const T s = load_one(in[o]);
+#pragma unroll
+        for (int k = 0; k < E; ++k) x[o].v[k] = s;
+      }
+    }
+    Pack<T, E> r;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      if constexpr (NIN == 2) r.v[k] = f(x[0].v[k], x[1].v[k]);
+      else r.v[k] = f(x[0].v[k]);
+    }
+    store_pack<T, E>(dst + (b0 + rb) * p.sb[0] + (a0 + (int64_t)ca * E), r);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
 // elements per thread-chunk: the WIDEST operand moves 16 bytes per access (narrower operands 8/4/2 — still
@@ -285,6 +466,14 @@ constexpr int map_vec_width() {
 
 inline bool fits_u32(int64_t v) { return v >= 0 && v < (int64_t(1) << 31); }
 
+// development switches for tools/sweep.py (only consulted when HPTB_TUNE=1 at load)
+inline bool tune_flag(const char* name) {
+  static const bool on = [] { const char* e = getenv("HPTB_TUNE"); return e && e[0] == '1'; }();
+  if (!on) return false;
+  const char* e = getenv(name);
+  return e && e[0] == '1';
+}
+
 template <int NIN, typename F, typename O, typename A, typename B>
 hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
   const Collapsed& c = plan.c;
@@ -296,45 +485,61 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
   const size_t esz[3] = {sizeof(O), sizeof(A), sizeof(B)};
 
   if (c.launch_class != HPTB_CLASS_STRIDED) {
-    RowsParams p;
-    memset(&p, 0, sizeof(p));
     const int nd = c.ndim;
-    p.inner = nd ? c.shape[nd - 1] : 1;
-    p.nouter = nd ? nd - 1 : 0;
-    bool big = false;
-    for (int o = 0; o <= NIN; ++o) p.inner_stride[o] = nd ? (int32_t)c.strides[o][nd - 1] : 1;
+    constexpr int UNROLL = (VEC >= 16 ? 1 : VEC >= 8 ? 2 : 4) * HPTB_MAP_UNROLL_SCALE;  // ≥ 64 bytes of the widest operand per thread
+    // every unit-stride operand must keep 16 B (or pack-size) alignment at the start of every row
+    for (int o = 0; o <= NIN; ++o) {
+      if (nd && c.strides[o][nd - 1] == 0) continue;
+      size_t align = esz[o] * VEC > 16 ? 16 : esz[o] * VEC;
+      if (reinterpret_cast<uintptr_t>(plan.ptr[o]) % align) return HPTB_FALLBACK;
+      for (int d = 0; d + 1 < nd; ++d)
+        if ((uint64_t)(std::llabs(c.strides[o][d]) * (int64_t)esz[o]) % align) return HPTB_FALLBACK;
+    }
+    if (nd <= 1) {  // flat: one contiguous run per operand (or a broadcast scalar)
+      FlatParams p;
+      p.n = nd ? c.shape[0] : 1;
+      for (int o = 0; o <= NIN; ++o) p.stride[o] = nd ? (int32_t)c.strides[o][0] : 1;
+      p.stride[0] = 1;
+      if (NIN == 1) p.stride[2] = p.stride[1];
+      constexpr int64_t per_cta = (int64_t)kMapThreads * UNROLL * VEC;
+      int64_t blocks = (p.n + per_cta - 1) / per_cta;
+      if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "elementwise: tensor too large for one launch");
+      map_flat_kernel<NIN, VEC, UNROLL, F, O, A, B><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, f);
+      HPTB_CUDA_CHECK(cudaGetLastError());
+      return HPTB_OK;
+    }
+    // rows: 32-bit element offsets (larger tensors with outer dims take the runtime-typed kernel, which is 64-bit)
+    Rows32Params p;
+    memset(&p, 0, sizeof(p));
+    const int64_t inner = c.shape[nd - 1];
+    if (inner % VEC) return HPTB_FALLBACK;
+    p.nouter = nd - 1;
+    int64_t rows = 1;
+    for (int o = 0; o <= NIN; ++o) {
+      p.inner_stride[o] = (int32_t)c.strides[o][nd - 1];
+      int64_t span = (inner - 1) * std::llabs(c.strides[o][nd - 1]);  // largest |offset| this operand can reach
+      for (int i = 0; i < p.nouter; ++i) {
+        const int d = nd - 2 - i;
+        span += (c.shape[d] - 1) * std::llabs(c.strides[o][d]);
+        if (std::llabs(c.strides[o][d]) > 0x7fffffffLL) return HPTB_FALLBACK;
+        p.outer_stride[o][i] = (int32_t)c.strides[o][d];
+        if (o > 0 && c.strides[o][d] == 0) p.reuse[o] = 1;
+      }
+      if (span > 0x7fffffffLL - 64) return HPTB_FALLBACK;
+    }
     for (int i = 0; i < p.nouter; ++i) {
-      int d = nd - 2 - i;
-      if (!fits_u32(c.shape[d])) big = true;
+      const int d = nd - 2 - i;
+      rows *= c.shape[d];
       p.outer_shape[i] = (uint32_t)c.shape[d];
       p.outer_div[i] = FastDiv((uint32_t)c.shape[d]);
-      for (int o = 0; o <= NIN; ++o) p.outer_stride[o][i] = c.strides[o][d];
     }
-    // vector path: every unit-stride operand must keep 16 B (or pack-size) alignment on every row
-    bool vec_ok = VEC > 1;
-    if (vec_ok) {
-      for (int o = 0; o <= NIN && vec_ok; ++o) {
-        if (p.inner_stride[o] == 0) continue;
-        size_t align = esz[o] * VEC > 16 ? 16 : esz[o] * VEC;
-        if (reinterpret_cast<uintptr_t>(plan.ptr[o]) % align) vec_ok = false;
-        for (int i = 0; i < p.nouter; ++i) {
-          if ((uint64_t)(std::llabs(p.outer_stride[o][i]) * (int64_t)esz[o]) % align) vec_ok = false;
-          if (o > 0 && p.outer_stride[o][i] == 0) p.reuse[o] = 1;
-        }
-      }
-      if (p.nouter > 0 && p.inner % VEC) vec_ok = false;
-    }
-    if (!vec_ok) return HPTB_FALLBACK;  // unaligned / odd rows: the runtime-typed kernel handles them
-    p.cpr = (p.inner + VEC - 1) / VEC;
-    int64_t rows = 1;
-    for (int i = 0; i < p.nouter; ++i) rows *= c.shape[nd - 2 - i];
-    p.total_chunks = rows * p.cpr;
-    if (!fits_u32(p.cpr) || p.total_chunks >= (int64_t(1) << 32)) big = true;
-    p.use64 = big ? 1 : 0;
-    p.cpr_div = FastDiv(big ? 1u : (uint32_t)p.cpr);
-    constexpr int UNROLL = (VEC >= 16 ? 1 : VEC >= 8 ? 2 : 4) * HPTB_MAP_UNROLL_SCALE;  // ≥ 64 bytes of the widest operand per thread
-    int64_t blocks = (p.total_chunks + kMapThreads * UNROLL - 1) / (kMapThreads * UNROLL);
-    if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "elementwise: tensor too large for one launch");
+    const int64_t cpr = inner / VEC;
+    const int64_t total = rows * cpr;
+    if (total >= (int64_t(1) << 31)) return HPTB_FALLBACK;
+    p.cpr = (uint32_t)cpr;
+    p.cpr_div = FastDiv((uint32_t)cpr);
+    p.total_chunks = (uint32_t)total;
+    int64_t blocks = (total + kMapThreads * UNROLL - 1) / (kMapThreads * UNROLL);
     map_rows_kernel<NIN, VEC, UNROLL, F, O, A, B><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, f);
     HPTB_CUDA_CHECK(cudaGetLastError());
     return HPTB_OK;
@@ -404,6 +609,39 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
   p.use64 = big ? 1 : 0;
   p.tiles_a_div = FastDiv(big ? 1u : (uint32_t)p.tiles_a);
   p.tiles_b_div = FastDiv(big ? 1u : (uint32_t)p.tiles_b);
+  // same-size element types with a permuted operand: the shared-memory transposing kernel
+  if constexpr (std::is_same<O, A>::value && std::is_same<O, B>::value && sizeof(O) >= 2) {
+    constexpr int E = 16 / (int)sizeof(O);
+    bool ok = db >= 0 && p.mode[0] == 2 && p.A % E == 0 && p.B % E == 0 && !tune_flag("HPTB_TUNE_NO_SMEMT");
+    int nstaged = 0;
+    TileParams ps = p;
+    for (int o = 1; o <= NIN && ok; ++o) {
+      if (p.mode[o] == 1) { ps.mode[o] = kSmemModeStaged; ++nstaged; }
+      else if (p.mode[o] == 2) ps.mode[o] = kSmemModeDirect;
+      else if (p.sa[o] == 0 && p.sb[o] == 0) ps.mode[o] = kSmemModeScalar;
+      else ok = false;
+    }
+    if (ok && nstaged > 0) {
+      constexpr int T2 = 16 * E;
+      ps.tiles_a = (p.A + T2 - 1) / T2;
+      ps.tiles_b = (p.B + T2 - 1) / T2;
+      ps.ntiles = ps.tiles_a * ps.tiles_b * batch;
+      bool big2 = big || ps.ntiles >= (int64_t(1) << 32);
+      ps.use64 = big2 ? 1 : 0;
+      ps.tiles_a_div = FastDiv(big2 ? 1u : (uint32_t)ps.tiles_a);
+      ps.tiles_b_div = FastDiv(big2 ? 1u : (uint32_t)ps.tiles_b);
+      if (ps.ntiles > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "elementwise: tensor too large for one launch");
+      const size_t smem = (size_t)nstaged * T2 * T2 * sizeof(O);
+      auto kern = map_tiled_smem_kernel<NIN, F, O>;
+      if (smem > 48 * 1024) {
+        static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * T2 * T2 * (int)sizeof(O));
+        if (attr != cudaSuccess) return fail(HPTB_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(attr));
+      }
+      kern<<<(unsigned)ps.ntiles, kMapThreads, smem, stream>>>(out, reinterpret_cast<const O*>(a), reinterpret_cast<const O*>(b), ps, f);
+      HPTB_CUDA_CHECK(cudaGetLastError());
+      return HPTB_OK;
+    }
+  }
   int64_t blocks = p.ntiles < 0x7fffffffLL ? p.ntiles : 0x7fffffffLL;
   map_tiled_kernel<NIN, F, O, A, B><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, f);
   HPTB_CUDA_CHECK(cudaGetLastError());

@@ -108,10 +108,14 @@ class Sweep:
         self.f.flush()
         print(f"{case:28s} {impl:8s} {self.variant:8s} {str(knobs):24s} {us:9.2f} us {gbs:8.1f} GB/s {gbs / PEAK:6.3f}  host {timeit.host_us:6.1f} us", flush=True)
 
-    def knob_sweep(self, case, fns, reps, nbytes, G=(), S=()):
-        for k in ("HPTB_TUNE_G", "HPTB_TUNE_S"):
+    def knob_sweep(self, case, fns, reps, nbytes, G=(), S=(), flags=()):
+        for k in ("HPTB_TUNE_G", "HPTB_TUNE_S") + tuple(flags):
             os.environ.pop(k, None)
         self.emit(case, "hptb", {}, timeit(fns, reps), nbytes)
+        for fl in flags:
+            os.environ[fl] = "1"
+            self.emit(case, "hptb", {fl[10:]: 1}, timeit(fns, reps), nbytes)
+            os.environ.pop(fl, None)
         for g in G:
             os.environ["HPTB_TUNE_G"] = str(g)
             self.emit(case, "hptb", {"G": g}, timeit(fns, reps), nbytes)
@@ -181,10 +185,10 @@ def main():
         ix = torch.empty((n,), device=dev, dtype=torch.int64)
         X, Y, Mx, Ix = wrap(x, F32), wrap(y, F32), wrap(m, F32), wrap(ix, I64)
         V = X.t()
-        sw.knob_sweep("cfg2.sin_T", [c_unary("sin", V, Y)], 50, 536870912)
+        sw.knob_sweep("cfg2.sin_T", [c_unary("sin", V, Y)], 50, 536870912, flags=("HPTB_TUNE_NO_SMEMT",))
         sw.emit("cfg2.sin_T", "torch", {}, timeit([lambda: torch.sin(x.t(), out=y)], 50), 536870912)
         sw.knob_sweep("cfg2.exp_T", [c_unary("exp", V, Y)], 50, 536870912)
-        sw.knob_sweep("cfg2.copy_T", [c_copy(V, Y)], 50, 536870912)
+        sw.knob_sweep("cfg2.copy_T", [c_copy(V, Y)], 50, 536870912, flags=("HPTB_TUNE_NO_SMEMT",))
         sw.emit("cfg2.copy_T", "torch", {}, timeit([lambda: y.copy_(x.t())], 50), 536870912)
 
         def red(op, out):
