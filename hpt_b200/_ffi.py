@@ -82,6 +82,8 @@ SIGNATURES = {
     "hptb_memcpy_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hptb_memcpy_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hptb_memcpy_d2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hptb_memcpy_d2h_async": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hptb_stream_wait_stream": (c_int, [c_void_p, c_void_p, c_void_p]),
     "hptb_host_alloc_pinned": (c_int, [c_size_t, POINTER(c_void_p)]),
     "hptb_host_free_pinned": (c_int, [c_void_p]),
     "hptb_promote": (c_int, [c_int, c_int, c_int]),

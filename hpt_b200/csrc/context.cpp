@@ -277,6 +277,23 @@ hptb_status hptb_memcpy_d2h(hptb_ctx* ctx, void* dst, const void* src, size_t by
   HPTB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   return HPTB_OK;
 }
+hptb_status hptb_memcpy_d2h_async(hptb_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream) {
+  if (!ctx) return fail(HPTB_ERR_INVALID, "memcpy_d2h_async: null ctx");
+  DeviceGuard g(ctx->device);
+  HPTB_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return HPTB_OK;
+}
+hptb_status hptb_stream_wait_stream(hptb_ctx* ctx, void* stream, void* other) {
+  if (!ctx) return fail(HPTB_ERR_INVALID, "stream_wait_stream: null ctx");
+  DeviceGuard g(ctx->device);
+  cudaEvent_t ev;
+  HPTB_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, (cudaStream_t)other);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)stream, ev, 0);
+  cudaEventDestroy(ev);  // released by the runtime once the wait has been satisfied
+  if (e != cudaSuccess) return fail(HPTB_ERR_CUDA, "stream_wait_stream failed: %s", cudaGetErrorString(e));
+  return HPTB_OK;
+}
 hptb_status hptb_memcpy_d2d(hptb_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream) {
   if (!ctx) return fail(HPTB_ERR_INVALID, "memcpy_d2d: null ctx");
   DeviceGuard g(ctx->device);

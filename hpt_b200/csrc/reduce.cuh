@@ -420,44 +420,50 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
   for (int k = 0; k < VEC; ++k) acc[k] = Op::local_identity();
 
   if (active) {
-    // hot loop: 32-bit local chunk counter (a split never holds 2^31 chunks), no partial packs (the host only
-    // picks VEC > 1 when the run length is a multiple of VEC), one pointer add per load in the common case of
-    // a single reduced dim — the loop must stay far below the issue budget of an HBM-bound kernel
+    // Hot loop.  It must stay far below the issue budget of an HBM-bound kernel (ncu, profiles/r01c: 86 warp
+    // instructions per 16-byte pack with a divide per pack; the bf16 NCHW mean sat at 62 % issue utilisation),
+    // so the (run, column) position of a thread is carried incrementally: one add and one compare per pack, the
+    // run offset recomputed only when a run boundary is crossed.  No partial packs (the host picks VEC > 1 only
+    // when the run length is a multiple of VEC); 32-bit local counters (a split never holds 2^31 chunks).
     const T* base = in + in_off;
     const uint32_t n_local = (uint32_t)(c_end - c_begin);
-    const bool simple = p.outer.n == 0;
     const int64_t estride = VEC > 1 ? (int64_t)VEC : p.inner_stride;  // elements between consecutive chunks
-    const T* ptr0 = base + (simple ? c_begin * estride : 0);
+    auto run_offset = [&](int64_t r) -> int64_t {
+      if (p.outer.n == 1) return r * p.outer.stride_a[0];
+      int64_t roff = 0, dummy = 0;
+      walk2(r, p.outer, p.use64, roff, dummy);
+      return roff;
+    };
+    uint32_t col, cpr_eff;
+    int64_t r = 0;
+    const T* runp;
+    if (p.outer.n == 0) {  // one run per output: the split itself is the run, it never wraps
+      col = (uint32_t)g;
+      cpr_eff = 0xffffffffu;
+      runp = base + c_begin * estride;
+    } else {
+      const int64_t cu0 = c_begin + g;
+      r = cu0 / p.cpr;  // once per thread
+      col = (uint32_t)(cu0 - r * p.cpr);
+      cpr_eff = (uint32_t)p.cpr;  // the host guarantees cpr < 2^31 whenever outer dims exist
+      runp = base + run_offset(r);
+    }
     int32_t it = 0;
     for (uint32_t lc = (uint32_t)g; lc < n_local; lc += (uint32_t)G * UNROLL, it += UNROLL) {
       Pack<T, VEC> v[UNROLL];
       bool ok[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const uint32_t lcu = lc + (uint32_t)u * (uint32_t)G;
-        ok[u] = lcu < n_local;
+        ok[u] = lc + (uint32_t)u * (uint32_t)G < n_local;
         if (ok[u]) {
-          const T* src;
-          if (simple) {
-            src = ptr0 + (int64_t)lcu * estride;
-          } else {
-            int64_t r, col, roff = 0;
-            if (!p.use64) {
-              const uint32_t cu = (uint32_t)c_begin + lcu;
-              const uint32_t rr = p.cpr_div.div(cu);
-              col = cu - rr * (uint32_t)p.cpr;
-              r = rr;
-            } else {
-              const int64_t cu = c_begin + lcu;
-              r = cu / p.cpr;
-              col = cu - r * p.cpr;
-            }
-            if (p.outer.n == 1) roff = r * p.outer.stride_a[0];
-            else { int64_t dummy = 0; walk2(r, p.outer, p.use64, roff, dummy); }
-            src = base + roff + col * estride;
-          }
+          const T* src = runp + (int64_t)col * estride;
           if constexpr (VEC > 1) load_pack<T, VEC>(v[u], src);
           else v[u].v[0] = load_one(src);
+        }
+        col += (uint32_t)G;
+        if (col >= cpr_eff) {
+          do { col -= cpr_eff; ++r; } while (col >= cpr_eff);
+          runp = base + run_offset(r);
         }
       }
 #pragma unroll
@@ -547,12 +553,13 @@ reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
   const int tid = threadIdx.x;
   const int TX = p.TX, TY = kRedThreads / TX;
   const int tx = tid & (TX - 1), ty = tid / TX;
-  // blockIdx.x = ((k * col_tiles) + tile) * S + split
+  // blockIdx.x = (split * K + k) * col_tiles + tile: CTAs that run together read ADJACENT column segments of the
+  // same rows (whole rows stream from DRAM page by page) rather than the same columns of far-apart row ranges
   int64_t b = blockIdx.x;
-  const int64_t split = b % p.S;
-  b /= p.S;
   const int64_t tile = b % p.col_tiles;
-  const int64_t k = b / p.col_tiles;
+  b /= p.col_tiles;
+  const int64_t k = b % p.K;
+  const int64_t split = b / p.K;
   const int64_t col = (tile * TX + tx) * VEC;
   const bool col_ok = col < p.C;
   int32_t ncol = 0;
@@ -823,6 +830,7 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   int64_t router = 1;
   for (int i = 1; i < nr; ++i) router *= c.shape[red[i]];
   p.chunks = router * p.cpr;
+  if (nr > 1 && !red_fits_u32(p.cpr)) return fail(HPTB_ERR_UNSUPPORTED, "reduce: a reduced run of more than 2^31 chunks next to other reduced dims");
   if (!red_fits_u32(p.cpr) || p.chunks >= (int64_t(1) << 32) || !red_fits_u32(M)) big = true;
   p.use64 = big ? 1 : 0;
   p.cpr_div = FastDiv(big ? 1u : (uint32_t)p.cpr);

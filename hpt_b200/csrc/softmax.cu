@@ -65,6 +65,20 @@ template <typename C> __device__ __forceinline__ C sm_max(C a, C b) {
   if constexpr (std::is_same<C, float>::value) return fmaxf(a, b); else return fmax(a, b);
 }
 
+// exp for the register-resident kernel: ex2(x·log2e) with the rounding error of the product folded back in
+// (hi + lo = x·log2e to ~2^-48; exp = ex2(hi)·(1 + lo·ln2)), 7 instructions against libdevice expf's 12, same
+// accuracy class (MUFU.EX2 ≤ 2 ulp).  Inputs below −110 (including −inf: masked logits, padding lanes) give 0;
+// NaN propagates.
+__device__ __forceinline__ float sm_exp_fast(float x) {
+  x = x < -110.0f ? -110.0f : x;  // a select, not fmaxf: NaN must survive
+  const float hi = x * 1.4426950408889634f;
+  const float lo = fmaf(x, 1.4426950408889634f, -hi) + x * 1.9259629911266175e-8f;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(hi));
+  return fmaf(e, lo * 0.6931471805599453f, e);
+}
+__device__ __forceinline__ double sm_exp_fast(double x) { return exp(x); }
+
 struct MaxOp {
   template <typename C> static __device__ __forceinline__ C combine(C a, C b) { return sm_max<C>(a, b); }
 };
@@ -91,7 +105,7 @@ __device__ __forceinline__ C group_reduce(C v, C* s_buf, C ident) {
   return v;
 }
 
-template <typename T, int VEC, int G>
+template <typename T, int VEC, int G, bool LOG>
 __global__ void __launch_bounds__(kSmThreads)
 softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
                  SoftmaxParams p) {
@@ -109,8 +123,8 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
   C mx = neg_inf;
 #pragma unroll
   for (int i = 0; i < kSmChunks; ++i) {
-    const int64_t e = ((int64_t)i * G + lane) * VEC;
-    if (i < p.nchunks && active && e < p.L) {
+    const int e = (i * G + lane) * VEC;  // a register-resident row has at most 8·256·VEC elements
+    if (i < p.nchunks && active && e < (int)p.L) {
       Pack<T, VEC> v;
       load_pack<T, VEC>(v, in + in_off + e);
 #pragma unroll
@@ -134,9 +148,9 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
         // rounding of x − max costs up to |x − max|/2 ulp of the result, which the parity bound accounts for.
         // (The two-pass kernels below fold that error back in — they have instruction slack; this one does not.)
         const C sh = x[i][k] - mx;
-        const C ex = sm_exp<C>(sh);
+        const C ex = sm_exp_fast(sh);
         sum += ex;  // padding lanes: exp(-inf - mx) = 0 (or NaN only if mx itself is -inf/NaN, handled by row)
-        x[i][k] = p.log ? sh : ex;
+        x[i][k] = LOG ? sh : ex;
       }
     }
   }
@@ -145,11 +159,11 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
   const C inv = (C)1 / sum;  // one division per row; the per-element multiply adds ≤ 0.5 ulp over a division
 #pragma unroll
   for (int i = 0; i < kSmChunks; ++i) {
-    const int64_t e = ((int64_t)i * G + lane) * VEC;
-    if (i < p.nchunks && active && e < p.L) {
+    const int e = (i * G + lane) * VEC;
+    if (i < p.nchunks && active && e < (int)p.L) {
       Pack<O, VEC> o;
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(p.log ? x[i][k] - lg : x[i][k] * inv);
+      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(LOG ? x[i][k] - lg : x[i][k] * inv);
       store_pack<O, VEC>(out + out_off + e, o);
     }
   }
@@ -287,13 +301,19 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
       p.nchunks = (int)((packs + G - 1) / G);
       int64_t blocks = (M + (kSmThreads / G) - 1) / (kSmThreads / G);
       if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "softmax: grid too large");
+#define HPTB_SM_LAUNCH(V, GG)                                                                                   \
+  do {                                                                                                            \
+    if (log) softmax_rows_reg<T, V, GG, true><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);           \
+    else softmax_rows_reg<T, V, GG, false><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);              \
+  } while (0)
       if (vec > 1) {
-        if (G == 32) softmax_rows_reg<T, VECMAX, 32><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
-        else softmax_rows_reg<T, VECMAX, kSmThreads><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
+        if (G == 32) HPTB_SM_LAUNCH(VECMAX, 32);
+        else HPTB_SM_LAUNCH(VECMAX, kSmThreads);
       } else {
-        if (G == 32) softmax_rows_reg<T, 1, 32><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
-        else softmax_rows_reg<T, 1, kSmThreads><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
+        if (G == 32) HPTB_SM_LAUNCH(1, 32);
+        else HPTB_SM_LAUNCH(1, kSmThreads);
       }
+#undef HPTB_SM_LAUNCH
       HPTB_CUDA_CHECK(cudaGetLastError());
       count_launches(1);
       return HPTB_OK;

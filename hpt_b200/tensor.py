@@ -140,8 +140,9 @@ class Tensor:
         return Tensor(st, st.ptr, dtype, shape, _contig_strides(shape))
 
     @staticmethod
-    def to_cuda(host, device=0, stream=None):
-        """`cpu_tensor.to_cuda::<DEVICE>()` (hpt/src/backends/cpu/tensor_impls.rs:295-313)."""
+    def to_cuda(host, device=0, stream=None, sync=True):
+        """`cpu_tensor.to_cuda::<DEVICE>()` (hpt/src/backends/cpu/tensor_impls.rs:295-313).
+        sync=False (pinned sources only): the upload is only ordered on `stream`."""
         if not isinstance(host, torch.Tensor):
             host = torch.as_tensor(host)
         if host.dtype not in _TORCH_TO_ENUM:
@@ -152,7 +153,8 @@ class Tensor:
         if nbytes:
             check(lib.hptb_memcpy_h2d(t.ctx.handle, c_void_p(t.ptr), c_void_p(host.data_ptr()), nbytes, _s(stream)))
             # pageable source: make the staging complete before the host tensor can be mutated
-            t.ctx.synchronize(stream)
+            if sync or not host.is_pinned():
+                t.ctx.synchronize(stream)
         return t
 
     @staticmethod
@@ -161,7 +163,7 @@ class Tensor:
         return Tensor(_Borrowed(context(device), ptr, keepalive), ptr, dtype, shape,
                       strides if strides is not None else _contig_strides(shape))
 
-    def to_cpu(self, stream=None, out=None):
+    def to_cpu(self, stream=None, out=None, sync=True):
         """`to_cpu::<0>()` (hpt/src/backends/cuda/tensor_impls.rs:142-169): views are gathered first.
         `out` may be a preallocated (e.g. pinned) contiguous host tensor of the right shape and dtype."""
         src = self if self.is_contiguous() else self.contiguous(stream)
@@ -173,7 +175,11 @@ class Tensor:
             host = torch.empty(self.shape, dtype=_TORCH_DTYPES[self.dtype])
         nbytes = host.numel() * host.element_size()
         if nbytes:
-            check(lib.hptb_memcpy_d2h(self.ctx.handle, c_void_p(host.data_ptr()), c_void_p(src.ptr), nbytes, _s(stream)))
+            if sync or out is None or not host.is_pinned():
+                check(lib.hptb_memcpy_d2h(self.ctx.handle, c_void_p(host.data_ptr()), c_void_p(src.ptr), nbytes, _s(stream)))
+            else:  # pinned destination, caller synchronises the stream before reading `out`
+                check(lib.hptb_memcpy_d2h_async(self.ctx.handle, c_void_p(host.data_ptr()), c_void_p(src.ptr), nbytes, _s(stream)))
+                host._hptb_src = src  # keep the device buffer alive until the caller has synchronised
         return host
 
     # ---- metadata ---------------------------------------------------------------------------------

@@ -144,6 +144,12 @@ hptb_status hptb_alloc_selftest(void);
 hptb_status hptb_memcpy_h2d(hptb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, void* stream);
 hptb_status hptb_memcpy_d2h(hptb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes, void* stream);
 hptb_status hptb_memcpy_d2d(hptb_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+/* Asynchronous read-back into PINNED host memory: ordered on `stream`, returns immediately; the host buffer is
+ * valid after hptb_stream_sync (or an event) on that stream.  An addition over the reference's blocking to_cpu
+ * that lets a caller overlap the read-back of one result with the next kernels and the next upload. */
+hptb_status hptb_memcpy_d2h_async(hptb_ctx* ctx, void* dst_pinned_host, const void* src_dev, size_t bytes, void* stream);
+/* Make `stream` wait for everything enqueued so far on `other` (event record + stream wait; no host sync). */
+hptb_status hptb_stream_wait_stream(hptb_ctx* ctx, void* stream, void* other);
 hptb_status hptb_host_alloc_pinned(size_t bytes, void** ptr);
 hptb_status hptb_host_free_pinned(void* ptr);
 

@@ -84,6 +84,8 @@ extern "C" {
     pub fn hptb_memcpy_h2d(ctx: *mut hptb_ctx, dst: *mut c_void, src: *const c_void, bytes: usize, stream: *mut c_void) -> hptb_status;
     pub fn hptb_memcpy_d2h(ctx: *mut hptb_ctx, dst: *mut c_void, src: *const c_void, bytes: usize, stream: *mut c_void) -> hptb_status;
     pub fn hptb_memcpy_d2d(ctx: *mut hptb_ctx, dst: *mut c_void, src: *const c_void, bytes: usize, stream: *mut c_void) -> hptb_status;
+    pub fn hptb_memcpy_d2h_async(ctx: *mut hptb_ctx, dst_pinned: *mut c_void, src: *const c_void, bytes: usize, stream: *mut c_void) -> hptb_status;
+    pub fn hptb_stream_wait_stream(ctx: *mut hptb_ctx, stream: *mut c_void, other: *mut c_void) -> hptb_status;
     pub fn hptb_host_alloc_pinned(bytes: usize, ptr: *mut *mut c_void) -> hptb_status;
     pub fn hptb_host_free_pinned(ptr: *mut c_void) -> hptb_status;
     pub fn hptb_promote(lhs: c_int, rhs: c_int, kind: c_int) -> c_int;
