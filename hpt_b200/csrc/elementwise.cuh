@@ -341,19 +341,111 @@ map_tiled_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restri
 // in + out instead of 36.
 constexpr int kSmemModeStaged = 1, kSmemModeDirect = 2, kSmemModeScalar = 3;
 
+// one tile; pointers are already at the tile origin, in-tile offsets are 32-bit (the host checks the strides)
+template <int NIN, typename F, typename T, bool FULL>
+__device__ __forceinline__ void smem_tile_body(T* __restrict__ dst, const T* __restrict__ in0, const T* __restrict__ in1,
+                                               const int32_t (&sa)[3], const int32_t (&sb)[3], const int32_t (&mode)[3],
+                                               int rem_a, int rem_b, T* __restrict__ sm0, F f) {
+  constexpr int E = 16 / sizeof(T);
+  constexpr int TA = 16 * E;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = lane >> 3, l8 = lane & 7;
+  const T* in[2] = {in0, in1};
+  // phase 1: staged operands — 16-byte loads along b, element scatter into sm[b][a]
+  {
+    Pack<T, E> v[2][E];
+    bool ok[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const int g = i * 8 + warp;  // group of 4 consecutive a-rows × one half of the b extent
+      const int ra = (g % (4 * E)) * 4 + q;
+      const int pb = (g / (4 * E)) * 8 + l8;
+      ok[i] = FULL || (ra < rem_a && pb * E < rem_b);
+      if (ok[i]) {
+#pragma unroll
+        for (int o = 0; o < NIN; ++o)
+          if (NIN == 1 || mode[o + 1] == kSmemModeStaged) load_pack<T, E>(v[o][i], in[o] + (int64_t)ra * sa[o + 1] + pb * E);
+      }
+    }
+    int nst = 0;
+#pragma unroll
+    for (int o = 0; o < NIN; ++o) {
+      if (NIN == 2 && mode[o + 1] != kSmemModeStaged) continue;
+      T* sm = sm0 + nst * (TA * TA);
+      ++nst;
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        if (!ok[i]) continue;
+        const int g = i * 8 + warp;
+        const int ra = (g % (4 * E)) * 4 + q;
+        const int pb = (g / (4 * E)) * 8 + l8;
+        T* d = sm + (pb * E) * TA + (((ra / E) ^ (pb & 7)) * E) + (ra % E);
+#pragma unroll
+        for (int k = 0; k < E; ++k) d[k * TA] = v[o][i].v[k];
+      }
+    }
+  }
+  __syncthreads();
+  // phase 2: 16-byte gathers along a, compute, 16-byte stores along a
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    const int g = i * 8 + warp;
+    const int rb = (g % (4 * E)) * 4 + q;
+    const int ca = (g / (4 * E)) * 8 + l8;
+    if (!FULL && (rb >= rem_b || ca * E >= rem_a)) continue;
+    Pack<T, E> x[2];
+    int nst = 0;
+#pragma unroll
+    for (int o = 0; o < NIN; ++o) {
+      if (NIN == 1 || mode[o + 1] == kSmemModeStaged) {
+        const T* sm = sm0 + nst * (TA * TA);
+        ++nst;
+        x[o] = *reinterpret_cast<const Pack<T, E>*>(sm + rb * TA + ((ca ^ ((rb / E) & 7)) * E));
+      } else if (mode[o + 1] == kSmemModeDirect) {
+        load_pack<T, E>(x[o], in[o] + (int64_t)rb * sb[o + 1] + ca * E);
+      } else {
+        const T s = load_one(in[o]);
+#pragma unroll
+        for (int k = 0; k < E; ++k) x[o].v[k] = s;
+      }
+    }
+    Pack<T, E> r;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      if constexpr (NIN == 2) r.v[k] = f(x[0].v[k], x[1].v[k]);
+      else r.v[k] = f(x[0].v[k]);
+    }
+    store_pack<T, E>(dst + (int64_t)rb * sb[0] + ca * E, r);
+  }
+}
+
+struct SmemTileParams {
+  int64_t A, B;
+  int64_t tiles_a, tiles_b;
+  int32_t sa[3], sb[3];  // element strides along a and b (|stride| < 2^31, checked on the host)
+  int32_t mode[3];
+  int32_t nbatch, use64;
+  uint32_t batch_shape[kMaxOuter];
+  FastDiv batch_div[kMaxOuter];
+  FastDiv tiles_a_div, tiles_b_div;
+  int64_t batch_stride[3][kMaxOuter];
+};
+
 template <int NIN, typename F, typename T>
 __global__ void __launch_bounds__(kMapThreads)
-map_tiled_smem_kernel(T* __restrict__ out, const T* __restrict__ a, const T* __restrict__ b, TileParams p, F f) {
+map_tiled_smem_kernel(T* __restrict__ out, const T* __restrict__ a, const T* __restrict__ b, SmemTileParams p, F f) {
   constexpr int E = 16 / sizeof(T);  // elements per 16-byte pack
   constexpr int TA = 16 * E, TB = 16 * E;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sm0 = reinterpret_cast<T*>(smem_raw);  // staged operand tiles, [TB][TA] each
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = lane >> 3, l8 = lane & 7;
-
-  // one tile per CTA: blockIdx → (tile along a, tile along b, batch)
+  // one tile per CTA.  Usual case: a 3-D grid (tile along a, tile along b, batch) — no division; grids whose
+  // y/z extents exceed 65535 fall back to a linear index
   int64_t ta, tb, batch;
-  {
+  if (gridDim.y > 1 || gridDim.z > 1 || p.use64 == 2) {
+    ta = blockIdx.x;
+    tb = blockIdx.y;
+    batch = blockIdx.z;
+  } else {
     const int64_t t = blockIdx.x;
     if (!p.use64) {
       uint32_t qq = p.tiles_a_div.div((uint32_t)t);
@@ -371,84 +463,13 @@ map_tiled_smem_kernel(T* __restrict__ out, const T* __restrict__ a, const T* __r
   }
   const int64_t a0 = ta * TA, b0 = tb * TB;
   int64_t off[3] = {0, 0, 0};
-  walk_outer<3>(batch, p.nbatch, p.use64, p.batch_shape, p.batch_div, p.batch_stride, off);
-  const T* in[2] = {a + off[1], b + off[2]};
-
-  // phase 1: staged operands, 16-byte loads along b, element scatter into sm[b][a]
-  {
-    Pack<T, E> v[2][E];
-    bool ok[E];
-#pragma unroll
-    for (int i = 0; i < E; ++i) {
-      const int g = i * 8 + warp;  // group of 4 consecutive a-rows × one half of the b extent
-      const int half = g / (4 * E);
-      const int ra = (g % (4 * E)) * 4 + q;
-      const int pb = half * 8 + l8;
-      ok[i] = (a0 + ra < p.A) && (b0 + (int64_t)pb * E < p.B);
-      if (ok[i]) {
-#pragma unroll
-        for (int o = 0; o < NIN; ++o)
-          if (p.mode[o + 1] == kSmemModeStaged)
-            load_pack<T, E>(v[o][i], in[o] + (a0 + ra) * p.sa[o + 1] + (b0 + (int64_t)pb * E));
-      }
-    }
-    int nst = 0;
-#pragma unroll
-    for (int o = 0; o < NIN; ++o) {
-      if (p.mode[o + 1] != kSmemModeStaged) continue;
-      T* sm = sm0 + (size_t)nst * TB * TA;
-      ++nst;
-#pragma unroll
-      for (int i = 0; i < E; ++i) {
-        if (!ok[i]) continue;
-        const int g = i * 8 + warp;
-        const int half = g / (4 * E);
-        const int ra = (g % (4 * E)) * 4 + q;
-        const int pb = half * 8 + l8;
-        const int chunk = ra / E, slot = ra % E;
-#pragma unroll
-        for (int k = 0; k < E; ++k) {
-          const int row = pb * E + k;
-          sm[row * TA + ((chunk ^ (pb & 7)) * E) + slot] = v[o][i].v[k];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // phase 2: 16-byte gathers along a, compute, 16-byte stores along a
-  T* dst = out + off[0];
-#pragma unroll
-  for (int i = 0; i < E; ++i) {
-    const int g = i * 8 + warp;
-    const int halfa = g / (4 * E);
-    const int rb = (g % (4 * E)) * 4 + q;
-    const int ca = halfa * 8 + l8;
-    if (b0 + rb >= p.B || a0 + (int64_t)ca * E >= p.A) continue;
-    Pack<T, E> x[2];
-    int nst = 0;
-#pragma unroll
-    for (int o = 0; o < NIN; ++o) {
-      const int mode = p.mode[o + 1];
-      if (mode == kSmemModeStaged) {
-        const T* sm = sm0 + (size_t)nst * TB * TA;
-        ++nst;
-        x[o] = *reinterpret_cast<const Pack<T, E>*>(sm + rb * TA + ((ca ^ ((rb / E) & 7)) * E));
-      } else if (mode == kSmemModeDirect) {
-        load_pack<T, E>(x[o], in[o] + (b0 + rb) * p.sb[o + 1] + (a0 + (int64_t)ca * E));
-      } else {
-        const T s = load_one(in[o]);
-#pragma unroll
-        for (int k = 0; k < E; ++k) x[o].v[k] = s;
-      }
-    }
-    Pack<T, E> r;
-#pragma unroll
-    for (int k = 0; k < E; ++k) {
-      if constexpr (NIN == 2) r.v[k] = f(x[0].v[k], x[1].v[k]);
-      else r.v[k] = f(x[0].v[k]);
-    }
-    store_pack<T, E>(dst + (b0 + rb) * p.sb[0] + (a0 + (int64_t)ca * E), r);
-  }
+  if (p.nbatch > 0) walk_outer<3>(batch, p.nbatch, p.use64 == 1, p.batch_shape, p.batch_div, p.batch_stride, off);
+  T* dst = out + off[0] + a0 * p.sa[0] + b0 * p.sb[0];
+  const T* in0 = a + off[1] + a0 * p.sa[1] + b0 * p.sb[1];
+  const T* in1 = b + off[2] + a0 * p.sa[2] + b0 * p.sb[2];
+  const int64_t ra64 = p.A - a0, rb64 = p.B - b0;
+  if (ra64 >= TA && rb64 >= TB) smem_tile_body<NIN, F, T, true>(dst, in0, in1, p.sa, p.sb, p.mode, TA, TB, sm0, f);
+  else smem_tile_body<NIN, F, T, false>(dst, in0, in1, p.sa, p.sb, p.mode, (int)(ra64 < TA ? ra64 : TA), (int)(rb64 < TB ? rb64 : TB), sm0, f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -621,23 +642,41 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
       else if (p.sa[o] == 0 && p.sb[o] == 0) ps.mode[o] = kSmemModeScalar;
       else ok = false;
     }
+    for (int o = 0; o <= NIN && ok; ++o)
+      if (std::llabs(p.sa[o]) > 0x7fffffffLL || std::llabs(p.sb[o]) > 0x7fffffffLL) ok = false;
     if (ok && nstaged > 0) {
       constexpr int T2 = 16 * E;
-      ps.tiles_a = (p.A + T2 - 1) / T2;
-      ps.tiles_b = (p.B + T2 - 1) / T2;
-      ps.ntiles = ps.tiles_a * ps.tiles_b * batch;
-      bool big2 = big || ps.ntiles >= (int64_t(1) << 32);
-      ps.use64 = big2 ? 1 : 0;
-      ps.tiles_a_div = FastDiv(big2 ? 1u : (uint32_t)ps.tiles_a);
-      ps.tiles_b_div = FastDiv(big2 ? 1u : (uint32_t)ps.tiles_b);
-      if (ps.ntiles > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "elementwise: tensor too large for one launch");
+      SmemTileParams q;
+      memset(&q, 0, sizeof(q));
+      q.A = p.A;
+      q.B = p.B;
+      for (int o = 0; o < 3; ++o) { q.sa[o] = (int32_t)p.sa[o]; q.sb[o] = (int32_t)p.sb[o]; q.mode[o] = ps.mode[o]; }
+      q.nbatch = p.nbatch;
+      for (int i = 0; i < kMaxOuter; ++i) {
+        q.batch_shape[i] = p.batch_shape[i];
+        q.batch_div[i] = p.batch_div[i];
+        for (int o = 0; o < 3; ++o) q.batch_stride[o][i] = p.batch_stride[o][i];
+      }
+      q.tiles_a = (p.A + T2 - 1) / T2;
+      q.tiles_b = (p.B + T2 - 1) / T2;
+      const int64_t ntiles = q.tiles_a * q.tiles_b * batch;
+      const bool big2 = big || ntiles >= (int64_t(1) << 32);
+      q.use64 = big2 ? 1 : 0;
+      q.tiles_a_div = FastDiv(big2 ? 1u : (uint32_t)q.tiles_a);
+      q.tiles_b_div = FastDiv(big2 ? 1u : (uint32_t)q.tiles_b);
+      if (ntiles > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "elementwise: tensor too large for one launch");
       const size_t smem = (size_t)nstaged * T2 * T2 * sizeof(O);
       auto kern = map_tiled_smem_kernel<NIN, F, O>;
       if (smem > 48 * 1024) {
         static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * T2 * T2 * (int)sizeof(O));
         if (attr != cudaSuccess) return fail(HPTB_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(attr));
       }
-      kern<<<(unsigned)ps.ntiles, kMapThreads, smem, stream>>>(out, reinterpret_cast<const O*>(a), reinterpret_cast<const O*>(b), ps, f);
+      dim3 grid((unsigned)ntiles, 1, 1);
+      if (q.tiles_a <= 0x7fffffffLL && q.tiles_b <= 65535 && batch <= 65535) {
+        grid = dim3((unsigned)q.tiles_a, (unsigned)q.tiles_b, (unsigned)batch);
+        q.use64 = 2;  // 3-D grid: blockIdx is the tile coordinate (walk_outer then takes the 32-bit path: batch < 65536)
+      }
+      kern<<<grid, kMapThreads, smem, stream>>>(out, reinterpret_cast<const O*>(a), reinterpret_cast<const O*>(b), q, f);
       HPTB_CUDA_CHECK(cudaGetLastError());
       return HPTB_OK;
     }

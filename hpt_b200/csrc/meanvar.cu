@@ -31,6 +31,28 @@ template <typename T> struct MeanVarOp : PlainLocal<MeanVarOp<T>, T, SQ> {
     return SQ{v, v * v};
   }
   static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return SQ{a.s + b.s, a.q + b.q}; }
+  // Half-precision inputs: x and x² are exact in f32 (8 / 11-bit significands), so the Σx and Σx² of ONE pack are
+  // formed with f32 adds (≤ 7 roundings of 2^-24, far below the inputs' own precision) and only the two pack
+  // sums go through the f64 pipe: 0.5 instead of 3 f64 instructions per element (ncu, profiles/r01c: the
+  // all-f64 version ran at 0.40 of HBM peak against 0.70 for the plain mean).  f32 / f64 / integer inputs keep
+  // per-element f64 accumulation — their squares are not exact in f32.
+  template <int VEC>
+  static __device__ __forceinline__ void accumulate_pack(SQ (&acc)[VEC], const Pack<T, VEC>& v, int32_t) {
+    if constexpr (is_half<T>::value && VEC >= 2) {
+      float s = 0.0f, q = 0.0f;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float x = to_compute<T>(v.v[k]);
+        s += x;
+        q = fmaf(x, x, q);
+      }
+      acc[0].s += (double)s;
+      acc[0].q += (double)q;
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = combine(acc[k], pre(v.v[k], 0));
+    }
+  }
   static __device__ __forceinline__ void store2(Out* mean, Out* var, int64_t off, Acc a, double n) {
     const double m = a.s / n;
     double v = a.q / n - m * m;

@@ -96,6 +96,12 @@ struct PlainLocal {
   static __device__ __forceinline__ Local local_identity() { return D::identity(); }
   static __device__ __forceinline__ void accumulate(Local& l, T x, int32_t) { l = D::combine(l, D::pre(x, 0)); }
   static __device__ __forceinline__ AccT finish(Local l, int64_t, int64_t, int, int) { return l; }
+  // one loaded pack into the VEC per-slot accumulators (ops may override to pre-combine a pack more cheaply)
+  template <int VEC>
+  static __device__ __forceinline__ void accumulate_pack(Local (&acc)[VEC], const Pack<T, VEC>& v, int32_t it) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) D::accumulate(acc[k], v.v[k], it);
+  }
 };
 
 // SUM: common_reduce.rs:32-52 (identity ZERO, combine _add), output dtype T
@@ -232,6 +238,11 @@ template <typename T, bool IS_MAX> struct ArgOp {
   static __device__ __forceinline__ Acc finish(Local l, int64_t c0, int64_t stride, int vec, int k) {
     if (l.it < 0) return identity();
     return Acc{l.val, (c0 + (int64_t)l.it * stride) * vec + k};
+  }
+  template <int VEC>
+  static __device__ __forceinline__ void accumulate_pack(Local (&acc)[VEC], const Pack<T, VEC>& v, int32_t it) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) accumulate(acc[k], v.v[k], it);
   }
 };
 template <typename T> struct ReduceOp<HPTB_ARGMAX, T> : ArgOp<T, true> {};
@@ -469,8 +480,7 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         if (!ok[u]) continue;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) Op::accumulate(acc[k], v[u].v[k], it + u);
+        Op::template accumulate_pack<VEC>(acc, v[u], it + u);
       }
     }
   }
@@ -763,12 +773,12 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
     static const int occ_v = ctas_per_sm(reduce_cols_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)>, (size_t)kRedThreads * VECMAX * sizeof(Acc));
     static const int occ_1 = ctas_per_sm(reduce_cols_kernel<Op, T, 1>, (size_t)kRedThreads * sizeof(Acc));
     const int64_t slots = (int64_t)sms * (vec > 1 ? occ_v : occ_1);
-    // row splits: at least one full wave when the column tiles alone cannot fill it, and no more than ~256 rows
-    // per thread row (measured: 17 GB sum(axis 0) reaches 0.92 of peak with 74–128 splits vs 0.80 with 4)
+    // row splits: at least one full wave when the column tiles alone cannot fill it, and no more than ~512 rows
+    // per thread row (measured: 17 GB sum(axis 0) reaches 0.92 of peak with 37–74 splits vs 0.80 with 4)
     int64_t S = 1;
     if (groups < slots) S = slots / groups;
     {
-      int64_t byrows = p.R / ((int64_t)TY * 256);
+      int64_t byrows = p.R / ((int64_t)TY * 512);
       if (byrows > S) S = byrows;
       int64_t maxS = (p.R + (int64_t)TY * 8 - 1) / ((int64_t)TY * 8);
       if (S > maxS) S = maxS;
@@ -844,12 +854,12 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   // speeds; a single static wave ends with the slowest SM).  So: G ≤ 32 lanes per row; when the outputs alone
   // give less than a quarter wave of threads (the split costs a fence + ticket per warp: measured slower than
   // S = 1 from half a wave up), each output is split over S warps (virtual rows) — or, for very few
-  // outputs with long rows, over S whole CTAs — sized for ≥ 4 (warps) / 8 (CTAs) waves, ≥ 16 / 8 chunks per lane.
+  // outputs with long rows, over S whole CTAs — sized for one wave (warps) / 8 waves (CTAs), ≥ 16 / 8 chunks per lane.
   int64_t G = 1;
   while (G < 32 && G * 8 < p.chunks) G <<= 1;
   int64_t S = 1;
   if (G == 32 && M * 32 * 4 < thread_slots) {
-    const int64_t need = (4 * thread_slots + M * 32 - 1) / (M * 32);
+    const int64_t need = (thread_slots + M * 32 - 1) / (M * 32);  // one wave of warps: each split costs a fence + ticket
     int64_t maxS = p.chunks / (32 * 16);
     if (maxS < 1) maxS = 1;
     int64_t Sw = need < maxS ? need : maxS;
