@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "common.h"
+#include "launch.cuh"
 #include "layout.h"
 #include "map_plan.h"
 #include "scalar.cuh"
@@ -100,6 +101,7 @@ struct FlatParams {
 template <int NIN, int VEC, int UNROLL, typename F, typename O, typename A, typename B>
 __global__ void __launch_bounds__(kMapThreads)
 map_flat_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, FlatParams p, F f) {
+  pdl_prologue();
   constexpr int64_t kPerCta = (int64_t)kMapThreads * UNROLL * VEC;
   const int64_t e0 = (int64_t)blockIdx.x * kPerCta + (int64_t)threadIdx.x * VEC;
   Pack<A, VEC> pa[UNROLL];
@@ -160,6 +162,7 @@ struct Rows32Params {
 template <int NIN, int VEC, int UNROLL, typename F, typename O, typename A, typename B>
 __global__ void __launch_bounds__(kMapThreads)
 map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, Rows32Params p, F f) {
+  pdl_prologue();
   static_assert(VEC > 1, "the specialised rows kernel is vector-only; scalar layouts take the runtime-typed kernel");
   const uint32_t c0 = blockIdx.x * (uint32_t)(kMapThreads * UNROLL) + threadIdx.x;
   Pack<A, VEC> pa[UNROLL];
@@ -265,6 +268,7 @@ __device__ __forceinline__ void load_micro(X (&v)[MA][MB], const X* __restrict__
 template <int NIN, typename F, typename O, typename A, typename B>
 __global__ void __launch_bounds__(kMapThreads)
 map_tiled_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, TileParams p, F f) {
+  pdl_prologue();
   typedef TileGeom<O, A, B> G;
   constexpr int MA = G::MA, MB = G::MB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -434,6 +438,7 @@ struct SmemTileParams {
 template <int NIN, typename F, typename T>
 __global__ void __launch_bounds__(kMapThreads)
 map_tiled_smem_kernel(T* __restrict__ out, const T* __restrict__ a, const T* __restrict__ b, SmemTileParams p, F f) {
+  pdl_prologue();
   constexpr int E = 16 / sizeof(T);  // elements per 16-byte pack
   constexpr int TA = 16 * E, TB = 16 * E;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -525,8 +530,7 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
       constexpr int64_t per_cta = (int64_t)kMapThreads * UNROLL * VEC;
       int64_t blocks = (p.n + per_cta - 1) / per_cta;
       if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "elementwise: tensor too large for one launch");
-      map_flat_kernel<NIN, VEC, UNROLL, F, O, A, B><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, f);
-      HPTB_CUDA_CHECK(cudaGetLastError());
+      HPTB_CUDA_CHECK(launch_kernel(map_flat_kernel<NIN, VEC, UNROLL, F, O, A, B>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, f));
       return HPTB_OK;
     }
     // rows: 32-bit element offsets (larger tensors with outer dims take the runtime-typed kernel, which is 64-bit)
@@ -561,8 +565,7 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
     p.cpr_div = FastDiv((uint32_t)cpr);
     p.total_chunks = (uint32_t)total;
     int64_t blocks = (total + kMapThreads * UNROLL - 1) / (kMapThreads * UNROLL);
-    map_rows_kernel<NIN, VEC, UNROLL, F, O, A, B><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, f);
-    HPTB_CUDA_CHECK(cudaGetLastError());
+    HPTB_CUDA_CHECK(launch_kernel(map_rows_kernel<NIN, VEC, UNROLL, F, O, A, B>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, f));
     return HPTB_OK;
   }
 
@@ -676,14 +679,12 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
         grid = dim3((unsigned)q.tiles_a, (unsigned)q.tiles_b, (unsigned)batch);
         q.use64 = 2;  // 3-D grid: blockIdx is the tile coordinate (walk_outer then takes the 32-bit path: batch < 65536)
       }
-      kern<<<grid, kMapThreads, smem, stream>>>(out, reinterpret_cast<const O*>(a), reinterpret_cast<const O*>(b), q, f);
-      HPTB_CUDA_CHECK(cudaGetLastError());
+      HPTB_CUDA_CHECK(launch_kernel(kern, grid, dim3(kMapThreads), smem, stream, out, reinterpret_cast<const O*>(a), reinterpret_cast<const O*>(b), q, f));
       return HPTB_OK;
     }
   }
   int64_t blocks = p.ntiles < 0x7fffffffLL ? p.ntiles : 0x7fffffffLL;
-  map_tiled_kernel<NIN, F, O, A, B><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, f);
-  HPTB_CUDA_CHECK(cudaGetLastError());
+  HPTB_CUDA_CHECK(launch_kernel(map_tiled_kernel<NIN, F, O, A, B>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, f));
   return HPTB_OK;
 }
 

@@ -151,6 +151,7 @@ template <int NIN, int VEC, int UNROLL, int MAXB, typename Fn, typename O>
 __global__ void __launch_bounds__(kMapThreads)
 map_dyn_kernel(O* __restrict__ out, const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, RowsParams p,
                DynExtra x) {
+  pdl_prologue();
   const int64_t c0 = (int64_t)blockIdx.x * (kMapThreads * UNROLL) + threadIdx.x;
   RawPack<VEC, MAXB> ra[UNROLL], rb[UNROLL];
   int64_t oo[UNROLL];
@@ -315,9 +316,8 @@ hptb_status launch_map_dyn(const MapPlan& plan, cudaStream_t stream) {
   constexpr int UNROLL = 4;
   int64_t blocks = (p.total_chunks + kMapThreads * UNROLL - 1) / (kMapThreads * UNROLL);
   if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "elementwise: tensor too large for one launch");
-  if (vec_ok) map_dyn_kernel<NIN, VEC, UNROLL, MAXB, Fn, O><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, x);
-  else map_dyn_kernel<NIN, 1, UNROLL, MAXB, Fn, O><<<(unsigned)blocks, kMapThreads, 0, stream>>>(out, a, b, p, x);
-  HPTB_CUDA_CHECK(cudaGetLastError());
+  if (vec_ok) HPTB_CUDA_CHECK(launch_kernel(map_dyn_kernel<NIN, VEC, UNROLL, MAXB, Fn, O>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, x));
+  else HPTB_CUDA_CHECK(launch_kernel(map_dyn_kernel<NIN, 1, UNROLL, MAXB, Fn, O>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, x));
   return HPTB_OK;
 }
 

@@ -25,6 +25,7 @@
 
 #include "common.h"
 #include "context.h"
+#include "launch.cuh"
 #include "layout.h"
 #include "promote.h"
 #include "reduce_plan.h"
@@ -396,6 +397,7 @@ template <typename Op, typename T, int VEC>
 __global__ void __launch_bounds__(kRedThreads)
 reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out, typename Op::Out* __restrict__ out2,
                    typename Op::Acc* __restrict__ scratch, uint32_t* __restrict__ tickets, RowsRedParams p) {
+  pdl_prologue();
   typedef typename Op::Acc Acc;
   typedef typename Op::Local Local;
   constexpr int UNROLL = HPTB_RED_UNROLL;
@@ -555,6 +557,7 @@ template <typename Op, typename T, int VEC>
 __global__ void __launch_bounds__(kRedThreads)
 reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out, typename Op::Out* __restrict__ out2,
                    typename Op::Acc* __restrict__ scratch, uint32_t* __restrict__ tickets, ColsRedParams p) {
+  pdl_prologue();
   typedef typename Op::Acc Acc;
   typedef typename Op::Local Local;
   constexpr int UNROLL = HPTB_RED_UNROLL;
@@ -802,10 +805,9 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
     }
     unsigned grid = (unsigned)(groups * S);
     if (vec == VECMAX && VECMAX > 1)
-      reduce_cols_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)><<<grid, kRedThreads, smem, stream>>>(in, out, out2, (Acc*)scratch.ptr, tickets, p);
+      HPTB_CUDA_CHECK(launch_kernel(reduce_cols_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)>, dim3(grid), dim3(kRedThreads), smem, stream, in, out, out2, (Acc*)scratch.ptr, tickets, p));
     else
-      reduce_cols_kernel<Op, T, 1><<<grid, kRedThreads, smem, stream>>>(in, out, out2, (Acc*)scratch.ptr, tickets, p);
-    HPTB_CUDA_CHECK(cudaGetLastError());
+      HPTB_CUDA_CHECK(launch_kernel(reduce_cols_kernel<Op, T, 1>, dim3(grid), dim3(kRedThreads), smem, stream, in, out, out2, (Acc*)scratch.ptr, tickets, p));
     return HPTB_OK;
   }
 
@@ -859,7 +861,7 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   while (G < 32 && G * 8 < p.chunks) G <<= 1;
   int64_t S = 1;
   if (G == 32 && M * 32 * 4 < thread_slots) {
-    const int64_t need = (thread_slots + M * 32 - 1) / (M * 32);  // one wave of warps: each split costs a fence + ticket
+    const int64_t need = thread_slots / (M * 32);  // at most ONE wave of warps (640 CTAs on 592 slots ran 37 % slower than 576)
     int64_t maxS = p.chunks / (32 * 16);
     if (maxS < 1) maxS = 1;
     int64_t Sw = need < maxS ? need : maxS;
@@ -907,10 +909,9 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   }
   const unsigned grid = (unsigned)blocks;
   if (vec == VECMAX && VECMAX > 1)
-    reduce_rows_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)><<<grid, kRedThreads, 0, stream>>>(in, out, out2, (Acc*)scratch.ptr, tickets, p);
+    HPTB_CUDA_CHECK(launch_kernel(reduce_rows_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)>, dim3(grid), dim3(kRedThreads), 0, stream, in, out, out2, (Acc*)scratch.ptr, tickets, p));
   else
-    reduce_rows_kernel<Op, T, 1><<<grid, kRedThreads, 0, stream>>>(in, out, out2, (Acc*)scratch.ptr, tickets, p);
-  HPTB_CUDA_CHECK(cudaGetLastError());
+    HPTB_CUDA_CHECK(launch_kernel(reduce_rows_kernel<Op, T, 1>, dim3(grid), dim3(kRedThreads), 0, stream, in, out, out2, (Acc*)scratch.ptr, tickets, p));
   return HPTB_OK;
 }
 

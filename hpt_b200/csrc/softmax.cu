@@ -109,6 +109,7 @@ template <typename T, int VEC, int G, bool LOG>
 __global__ void __launch_bounds__(kSmThreads)
 softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
                  SoftmaxParams p) {
+  pdl_prologue();
   typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type O;
   typedef compute_t<O> C;
   __shared__ C s_buf[kSmThreads / 32];
@@ -194,6 +195,7 @@ template <typename T>
 __global__ void __launch_bounds__(kSmThreads)
 softmax_rows_stream(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
                     SoftmaxParams p) {
+  pdl_prologue();
   typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type O;
   typedef compute_t<O> C;
   __shared__ C s_m[kSmThreads / 32], s_s[kSmThreads / 32];
@@ -231,6 +233,7 @@ template <typename T>
 __global__ void __launch_bounds__(kSmThreads)
 softmax_cols(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
              SoftmaxParams p) {
+  pdl_prologue();
   typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type O;
   typedef compute_t<O> C;
   const int64_t col = (int64_t)blockIdx.x * kSmThreads + threadIdx.x;
@@ -303,8 +306,8 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
       if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "softmax: grid too large");
 #define HPTB_SM_LAUNCH(V, GG)                                                                                   \
   do {                                                                                                            \
-    if (log) softmax_rows_reg<T, V, GG, true><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);           \
-    else softmax_rows_reg<T, V, GG, false><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);              \
+    if (log) HPTB_CUDA_CHECK(launch_kernel(softmax_rows_reg<T, V, GG, true>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p)); \
+    else HPTB_CUDA_CHECK(launch_kernel(softmax_rows_reg<T, V, GG, false>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p)); \
   } while (0)
       if (vec > 1) {
         if (G == 32) HPTB_SM_LAUNCH(VECMAX, 32);
@@ -324,10 +327,10 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
   if (cols_ok) {
     int64_t blocks = (M + kSmThreads - 1) / kSmThreads;
     if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "softmax: grid too large");
-    softmax_cols<T><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
+    HPTB_CUDA_CHECK(launch_kernel(softmax_cols<T>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p));
   } else {
     int64_t blocks = M < (int64_t)ctx->sm_count * 16 ? M : (int64_t)ctx->sm_count * 16;
-    softmax_rows_stream<T><<<(unsigned)blocks, kSmThreads, 0, stream>>>(in, out, p);
+    HPTB_CUDA_CHECK(launch_kernel(softmax_rows_stream<T>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p));
   }
   HPTB_CUDA_CHECK(cudaGetLastError());
   count_launches(1);
