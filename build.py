@@ -53,14 +53,16 @@ def units():
         u.append((f"dyn_{short}", "dyn_inst.cu", f"-DHPTB_OUT={cty} -DHPTB_OUTNAME={short} -DHPTB_OUT_FLOAT={is_float}"))
     for name in REDUCE_OPS:
         u.append((f"reduce_{name}", "reduce_inst.cu", f"-DHPTB_OPENUM=HPTB_{name.upper()} -DHPTB_OPNAME={name}"))
-    for src in ("softmax.cu", "misc.cu", "meanvar.cu"):
+    for src in ("softmax.cu", "misc.cu", "meanvar.cu", "sharded.cu"):
         if os.path.exists(os.path.join(CSRC, src)):
             u.append((src[:-3], src, ""))
     return u
 
 
-def write_ninja(variant="", extra=""):
+def write_ninja(variant="", extra="", only=()):
+    """`only`: unit-name prefixes that get the variant's flags; the other units reuse the default build's objects."""
     global BUILD
+    default_obj = os.path.join(BUILD, "obj")
     if variant:
         BUILD = os.path.join(ROOT, "build", "variant_" + variant)
     os.makedirs(BUILD, exist_ok=True)
@@ -89,11 +91,17 @@ def write_ninja(variant="", extra=""):
     ]
     objs = []
     for name, src, defs in units():
+        if variant and only and not any(name.startswith(o) for o in only):
+            objs.append(os.path.join(default_obj, name + ".o"))  # built by the default configuration
+            continue
         obj = os.path.join(BUILD, "obj", name + ".o")
         lines += [f"build {obj}: nvcc {os.path.join(CSRC, src)}", f"  defs = {defs}"]
         objs.append(obj)
     for src in sorted(os.listdir(CSRC)):
         if src.endswith(".cpp"):
+            if variant and only:
+                objs.append(os.path.join(default_obj, src[:-4] + ".o"))
+                continue
             obj = os.path.join(BUILD, "obj", src[:-4] + ".o")
             lines += [f"build {obj}: cxx {os.path.join(CSRC, src)}"]
             objs.append(obj)
@@ -128,12 +136,15 @@ def main():
         shutil.rmtree(LIBDIR, ignore_errors=True)
         shutil.rmtree(os.path.join(ROOT, "oracle", "_build"), ignore_errors=True)
     # tuning builds: `python build.py --variant u8 -DHPTB_RED_UNROLL=8 …` → hpt_b200/lib/libhpt_b200_u8.so
-    variant, extra = "", []
+    # `--only reduce,meanvar` limits the variant's flags to those units (the rest is taken from the default build)
+    variant, extra, only = "", [], ()
     args = sys.argv[1:]
     if "--variant" in args:
         variant = args[args.index("--variant") + 1]
         extra = [a for a in args if a.startswith("-D")]
-    lib = write_ninja(variant, " ".join(extra))
+        if "--only" in args:
+            only = tuple(args[args.index("--only") + 1].split(","))
+    lib = write_ninja(variant, " ".join(extra), only)
     jobs = os.environ.get("HPTB_BUILD_JOBS", str(os.cpu_count() or 4))
     subprocess.check_call(["ninja", "-C", BUILD, "-j", jobs] + (["-v"] if "-v" in sys.argv else []))
     if not variant:

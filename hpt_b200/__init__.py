@@ -6,6 +6,7 @@ libhpt_b200.so (include/hpt_b200.h).  Importing this package requires the built 
 from . import _ffi
 from ._ffi import (BF16, BOOL, F16, F32, F64, I8, I16, I32, I64, U8, U16, U32, U64, DTYPE_NAMES, HptError, lib)
 from .tensor import Context, Tensor, context, get_stream, set_stream
+from .sharded import Comm, ShardedTensor, shard_bounds, shard_plan
 
-__all__ = ["Tensor", "Context", "context", "set_stream", "get_stream", "HptError", "lib", "DTYPE_NAMES",
+__all__ = ["Tensor", "Context", "Comm", "ShardedTensor", "shard_bounds", "shard_plan", "context", "set_stream", "get_stream", "HptError", "lib", "DTYPE_NAMES",
            "BOOL", "I8", "I16", "I32", "I64", "U8", "U16", "U32", "U64", "F16", "BF16", "F32", "F64"]

@@ -52,6 +52,14 @@ class HptbCollapsePlan(Structure):
                 ("shape", c_int64 * MAX_DIMS), ("strides", (c_int64 * MAX_DIMS) * 4), ("reduced", c_uint8 * MAX_DIMS)]
 
 
+class HptbShardPlan(Structure):
+    _fields_ = [("crosses", c_int32), ("collective", c_int32), ("pre_exp", c_int32), ("post_ln", c_int32),
+                ("global_count", c_int32)]
+
+
+COLLECTIVES = ["none", "allreduce_sum", "allreduce_prod", "allreduce_max", "allreduce_min", "allgather_arg"]
+
+
 class HptError(RuntimeError):
     """A non-zero hptb_status.  `.status` is the code; shape/axis/dtype errors mirror Hpt's
     TensorError::{Shape, Param, Kernel} (hpt-common/src/error/*.rs)."""
@@ -104,6 +112,8 @@ SIGNATURES = {
     "hptb_comm_unique_id": (c_int, [c_void_p]),
     "hptb_comm_init_rank": (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(c_void_p)]),
     "hptb_comm_destroy": (c_int, [c_void_p]),
+    "hptb_shard_bounds": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
+    "hptb_shard_plan_reduce": (c_int, [c_int, POINTER(c_int32), c_int, c_int, c_int, POINTER(HptbShardPlan)]),
     "hptb_allreduce": (c_int, [c_void_p, c_int, _T, c_void_p]),
     "hptb_reduce_sharded": (c_int, [c_void_p, c_int, _T, POINTER(c_int32), c_int, c_int, c_int64, c_int64, _T, c_void_p]),
 }

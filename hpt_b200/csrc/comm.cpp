@@ -20,6 +20,9 @@ extern "C" hptb_status hptb_unary(hptb_ctx*, int, const hptb_tensor*, hptb_tenso
 namespace hptb {
 hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, hptb_tensor* out,
                         int init_out, double count_override, void* stream);  // api_reduce.cpp
+hptb_status arg_combine(int dtype, bool is_max, const void* vals, const int64_t* idx, int k, int64_t M, int64_t* out,
+                        cudaStream_t s);                                      // sharded.cu
+hptb_status add_offset_i64(int64_t* p, int64_t off, int64_t n, cudaStream_t s);
 }
 
 namespace hptb {
@@ -38,6 +41,9 @@ struct Nccl {
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
 };
@@ -56,8 +62,12 @@ Nccl& nccl() {
     n.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(n.handle, "ncclCommInitRank");
     n.CommDestroy = (int (*)(ncclComm_t))dlsym(n.handle, "ncclCommDestroy");
     n.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclAllReduce");
+    n.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclAllGather");
+    n.GroupStart = (int (*)())dlsym(n.handle, "ncclGroupStart");
+    n.GroupEnd = (int (*)())dlsym(n.handle, "ncclGroupEnd");
     n.GetErrorString = (const char* (*)(int))dlsym(n.handle, "ncclGetErrorString");
-    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllReduce && n.GetErrorString;
+    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllReduce && n.AllGather && n.GroupStart && n.GroupEnd &&
+           n.GetErrorString;
   });
   return n;
 }
@@ -139,6 +149,34 @@ hptb_status hptb_comm_destroy(hptb_comm* comm) {
   return HPTB_OK;
 }
 
+hptb_status hptb_shard_bounds(int64_t n, int world, int rank, int64_t* offset, int64_t* len) {
+  if (!offset || !len) return fail(HPTB_ERR_INVALID, "shard_bounds: null argument");
+  if (n < 0 || world < 1 || rank < 0 || rank >= world) return fail(HPTB_ERR_INVALID, "shard_bounds: bad rank %d of %d", rank, world);
+  const int64_t base = n / world, rem = n % world;
+  *offset = base * rank + (rank < rem ? rank : rem);
+  *len = base + (rank < rem ? 1 : 0);
+  return HPTB_OK;
+}
+
+hptb_status hptb_shard_plan_reduce(int op, const int32_t* axes, int naxes, int shard_axis, int world, hptb_shard_plan* plan) {
+  if (!plan || (!axes && naxes)) return fail(HPTB_ERR_INVALID, "shard_plan_reduce: null argument");
+  if (op < 0 || op >= HPTB_REDUCE_COUNT) return fail(HPTB_ERR_INVALID, "shard_plan_reduce: bad op %d", op);
+  memset(plan, 0, sizeof(*plan));
+  for (int i = 0; i < naxes; ++i) plan->crosses |= axes[i] == shard_axis;
+  if (!plan->crosses || world <= 1) return HPTB_OK;
+  switch (op) {
+    case HPTB_SUM: case HPTB_SUM_SQUARE: plan->collective = HPTB_COLL_ALLREDUCE_SUM; break;
+    case HPTB_MEAN: plan->collective = HPTB_COLL_ALLREDUCE_SUM; plan->global_count = 1; break;
+    case HPTB_LOGSUMEXP: plan->collective = HPTB_COLL_ALLREDUCE_SUM; plan->pre_exp = 1; plan->post_ln = 1; break;
+    case HPTB_PROD: plan->collective = HPTB_COLL_ALLREDUCE_PROD; break;
+    case HPTB_MAX: plan->collective = HPTB_COLL_ALLREDUCE_MAX; break;
+    case HPTB_MIN: plan->collective = HPTB_COLL_ALLREDUCE_MIN; break;
+    case HPTB_ARGMAX: case HPTB_ARGMIN: plan->collective = HPTB_COLL_ALLGATHER_ARG; break;
+    default: return fail(HPTB_ERR_INVALID, "shard_plan_reduce: op %d has no sharded form", op);
+  }
+  return HPTB_OK;
+}
+
 hptb_status hptb_allreduce(hptb_comm* comm, int op, hptb_tensor* t, void* stream) {
   if (!comm) return fail(HPTB_ERR_INVALID, "allreduce: null comm");
   HPTB_TRY(validate_tensor(t, "allreduce tensor"));
@@ -166,14 +204,55 @@ hptb_status hptb_reduce_sharded(hptb_comm* comm, int op, const hptb_tensor* shar
   HPTB_TRY(validate_tensor(shard, "reduce_sharded shard"));
   HPTB_TRY(validate_tensor(out, "reduce_sharded out"));
   if (shard_axis < 0 || shard_axis >= shard->ndim) return fail(HPTB_ERR_AXIS, "reduce_sharded: shard axis %d out of range", shard_axis);
-  (void)shard_offset;
-  bool crosses = false;
-  for (int i = 0; i < naxes; ++i) crosses |= axes[i] == shard_axis;
-  if (!crosses || comm->nranks == 1) return hptb_reduce(comm->ctx, op, shard, axes, naxes, out, 1, stream);
-  if (op == HPTB_ARGMAX || op == HPTB_ARGMIN)
-    return fail(HPTB_ERR_UNSUPPORTED, "reduce_sharded: arg reductions across the shard axis are not implemented yet");
+  if (op < 0 || op >= HPTB_REDUCE_COUNT) return fail(HPTB_ERR_INVALID, "reduce_sharded: bad op %d", op);
+  if (!axes && naxes) return fail(HPTB_ERR_INVALID, "reduce_sharded: null axes");
+  hptb_shard_plan sp;
+  HPTB_TRY(hptb_shard_plan_reduce(op, axes, naxes, shard_axis, comm->nranks, &sp));
+  const bool crosses = sp.crosses != 0;
+  const bool is_arg = op == HPTB_ARGMAX || op == HPTB_ARGMIN;
+  if (!crosses || comm->nranks == 1) {
+    HPTB_TRY(hptb_reduce(comm->ctx, op, shard, axes, naxes, out, 1, stream));
+    // a lone rank may still hold a shard that does not start at 0 (indices are GLOBAL along the shard axis)
+    if (is_arg && crosses && shard_offset != 0 && is_contiguous(*out)) {
+      DeviceGuard g(comm->ctx->device);
+      count_launches(1);
+      return add_offset_i64((int64_t*)out->data, shard_offset, numel(*out), (cudaStream_t)stream);
+    }
+    return HPTB_OK;
+  }
   if (!is_contiguous(*out)) return fail(HPTB_ERR_SHAPE, "reduce_sharded: out must be contiguous when partials are exchanged");
-  if (op == HPTB_MEAN) {
+  if (is_arg) {
+    // (extreme value, global index) per rank → all-gather → rank-ordered strict combine (sharded.cu)
+    if (naxes != 1) return fail(HPTB_ERR_AXIS, "argmax/argmin take exactly one axis (got %d)", naxes);
+    if (out->dtype != HPTB_I64) return fail(HPTB_ERR_DTYPE, "reduce_sharded: out dtype is %s, expected i64", dtype_name(out->dtype));
+    const int64_t M = numel(*out);
+    if (M == 0) return HPTB_OK;
+    const size_t esz = dtype_size(shard->dtype);
+    const int k = comm->nranks;
+    Scratch sv, sva, sia;
+    HPTB_TRY(sv.get(comm->ctx, (size_t)M * esz, stream));
+    HPTB_TRY(sva.get(comm->ctx, (size_t)M * esz * k, stream));
+    HPTB_TRY(sia.get(comm->ctx, (size_t)M * sizeof(int64_t) * k, stream));
+    hptb_tensor val = *out;
+    val.data = sv.ptr;
+    val.dtype = shard->dtype;
+    HPTB_TRY(hptb_reduce(comm->ctx, op == HPTB_ARGMAX ? HPTB_MAX : HPTB_MIN, shard, axes, naxes, &val, 1, stream));
+    HPTB_TRY(hptb_reduce(comm->ctx, op, shard, axes, naxes, out, 1, stream));
+    DeviceGuard g(comm->ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    HPTB_TRY(add_offset_i64((int64_t*)out->data, shard_offset, M, s));
+    int rc = nccl().GroupStart();
+    if (rc != ncclSuccess) return nccl_fail("ncclGroupStart", rc);
+    rc = nccl().AllGather(sv.ptr, sva.ptr, (size_t)M * esz, ncclInt8, comm->comm, s);
+    if (rc == ncclSuccess) rc = nccl().AllGather(out->data, sia.ptr, (size_t)M * sizeof(int64_t), ncclInt8, comm->comm, s);
+    int rc2 = nccl().GroupEnd();
+    if (rc != ncclSuccess) return nccl_fail("ncclAllGather", rc);
+    if (rc2 != ncclSuccess) return nccl_fail("ncclGroupEnd", rc2);
+    HPTB_TRY(arg_combine(shard->dtype, op == HPTB_ARGMAX, sva.ptr, (const int64_t*)sia.ptr, k, M, (int64_t*)out->data, s));
+    count_launches(shard_offset != 0 ? 2 : 1);
+    return HPTB_OK;
+  }
+  if (sp.global_count) {
     // each rank computes Σ_local / n_GLOBAL, the allreduce-sum of those is the global mean
     double count = (double)global_axis_len;
     for (int i = 0; i < naxes; ++i)
@@ -181,7 +260,7 @@ hptb_status hptb_reduce_sharded(hptb_comm* comm, int op, const hptb_tensor* shar
     HPTB_TRY(reduce_impl(comm->ctx, HPTB_MEAN, shard, axes, naxes, out, 1, count, stream));
     return hptb_allreduce(comm, HPTB_SUM, out, stream);
   }
-  if (op == HPTB_LOGSUMEXP) {
+  if (sp.pre_exp) {
     HPTB_TRY(hptb_reduce(comm->ctx, HPTB_LOGSUMEXP, shard, axes, naxes, out, 1, stream));
     HPTB_TRY(hptb_unary(comm->ctx, HPTB_EXP, out, out, 0, 0, stream));  // back to Σ exp (naive domain, as the reference)
     HPTB_TRY(hptb_allreduce(comm, HPTB_SUM, out, stream));

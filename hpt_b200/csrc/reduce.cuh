@@ -37,6 +37,12 @@ constexpr int kRedThreads = 256;
 #ifndef HPTB_RED_UNROLL
 #define HPTB_RED_UNROLL 4
 #endif
+#ifndef HPTB_LEAN_MINB
+#define HPTB_LEAN_MINB 6
+#endif
+#ifndef HPTB_RED_PIPE
+#define HPTB_RED_PIPE 0
+#endif
 constexpr int kRedMaxDims = HPTB_MAX_DIMS;
 
 // ---- op traits ---------------------------------------------------------------------------------------
@@ -462,6 +468,67 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
       runp = base + run_offset(r);
     }
     int32_t it = 0;
+#if HPTB_RED_PIPE
+    // Software pipeline: the loads of batch k+1 are issued BEFORE batch k is consumed, so every thread keeps
+    // UNROLL..2·UNROLL 16-byte loads in flight for the whole loop instead of oscillating between UNROLL and 0
+    // (bytes in flight per SM, not issue slots, bound these kernels: Little's law needs ≈ 45 KB per SM).
+    // Full batches carry no predicates; the ≤ UNROLL-1 leftover chunks of a thread are handled one by one.
+    auto next_src = [&]() -> const T* {
+      const T* src = runp + (int64_t)col * estride;
+      col += (uint32_t)G;
+      if (col >= cpr_eff) {
+        do { col -= cpr_eff; ++r; } while (col >= cpr_eff);
+        runp = base + run_offset(r);
+      }
+      return src;
+    };
+    auto load_batch = [&](Pack<T, VEC> (&v)[UNROLL]) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const T* src = next_src();
+        if constexpr (VEC > 1) load_pack<T, VEC>(v[u], src);
+        else v[u].v[0] = load_one(src);
+      }
+    };
+    auto consume = [&](const Pack<T, VEC> (&v)[UNROLL]) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) Op::template accumulate_pack<VEC>(acc, v[u], it + u);
+      it += UNROLL;
+    };
+    const uint32_t mine = (uint32_t)g < n_local ? (n_local - (uint32_t)g + (uint32_t)G - 1) / (uint32_t)G : 0u;  // chunks of this thread
+    uint32_t batches = mine / UNROLL;
+    const uint32_t tail = mine - batches * UNROLL;
+    Pack<T, VEC> va[UNROLL], vb[UNROLL];
+    if (batches) load_batch(va);
+    while (batches >= 2) {
+      load_batch(vb);
+      consume(va);
+      --batches;
+      if (batches >= 2) {
+        load_batch(va);
+        consume(vb);
+        --batches;
+      } else {
+        consume(vb);
+        batches = 0;
+      }
+    }
+    if (batches) consume(va);
+    if (tail) {
+      Pack<T, VEC> vt[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL - 1; ++u) {
+        if ((uint32_t)u < tail) {
+          const T* src = next_src();
+          if constexpr (VEC > 1) load_pack<T, VEC>(vt[u], src);
+          else vt[u].v[0] = load_one(src);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL - 1; ++u)
+        if ((uint32_t)u < tail) Op::template accumulate_pack<VEC>(acc, vt[u], it + u);
+    }
+#else
     for (uint32_t lc = (uint32_t)g; lc < n_local; lc += (uint32_t)G * UNROLL, it += UNROLL) {
       Pack<T, VEC> v[UNROLL];
       bool ok[UNROLL];
@@ -485,6 +552,7 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
         Op::template accumulate_pack<VEC>(acc, v[u], it + u);
       }
     }
+#endif
   }
   // thread total; for arg reductions the element index of (iteration it, slot k) is ((c_begin + g) + it·G)·VEC + k
   // (exactly one reduced dim, so chunk number == column)
@@ -546,6 +614,81 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
       for (int w = 1; w < kRedThreads / 32; ++w) r = Op::combine(r, s_part[w]);
       red_store<Op>(out, out2, out_off, r, p.count, p.fold_out);
     }
+  }
+}
+
+
+// ---- lean rows kernel ------------------------------------------------------------------------------------
+// The common case — every output is ONE unit-stride, 16-byte-aligned run (last-axis reductions, the axis-0
+// reduction of a transposed view, softmax statistics) and there are enough outputs to fill the GPU without
+// splitting them — gets a kernel stripped to what that case needs: 32-bit counters, no run tracking, no split /
+// ticket code.  tools/microbench/stream_reduce.cu (profiles/r01c_microbench_stream_reduce.txt) showed what
+// matters for these 10–40 µs jobs: registers.  At ≤ 32 registers 8 CTAs (2048 threads) are resident per SM, so
+// twice the bytes are in flight per SM compared with the 62-register general kernel, and short-lived CTAs that
+// issue ALL of a thread's loads before the first use beat long-lived warps that walk a row in dependent round
+// trips (f32 [4096,4096] row sums: 12.3 µs CTA-per-row vs 14.4 µs warp-per-row; [16384,16384]: 7.28 vs 6.54 TB/s).
+struct LeanRowsParams {
+  int64_t M;           // outputs
+  int64_t in_stride;   // elements between the starts of consecutive rows
+  int64_t out_stride;
+  double count;
+  uint32_t cpr;        // 16-byte chunks per row
+  int32_t logG;        // log2 of the threads per row (5..8 → warp .. CTA per row; < 5 for short rows)
+  int32_t fold_out;
+};
+
+// resident CTAs per SM the register allocation must allow: 6 (≤ 40 registers) for plain 4-byte accumulators — 8
+// (≤ 32 registers) spills 8–48 bytes per thread and measured no faster (profiles/r01d_sweep.txt, variant mb6)
+template <typename Op>
+constexpr int lean_min_blocks() { return (Op::kIndexed || sizeof(typename Op::Acc) > 4) ? 5 : HPTB_LEAN_MINB; }
+
+template <typename Op, typename T, int VEC>
+__global__ void __launch_bounds__(kRedThreads, lean_min_blocks<Op>())
+reduce_rows_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out, typename Op::Out* __restrict__ out2,
+                        LeanRowsParams p) {
+  pdl_prologue();
+  typedef typename Op::Acc Acc;
+  typedef typename Op::Local Local;
+  constexpr int UNROLL = HPTB_RED_UNROLL;
+  __shared__ Acc s_part[kRedThreads / 32];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t G = 1u << p.logG;
+  const uint32_t g = tid & (G - 1);
+  const int64_t m = (((int64_t)blockIdx.x * kRedThreads) >> p.logG) + (tid >> p.logG);
+  const bool active = m < p.M;
+  Local acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = Op::local_identity();
+  if (active) {
+    const T* row = in + m * p.in_stride;
+    const uint32_t cpr = p.cpr;
+    int32_t it = 0;
+    for (uint32_t c = g; c < cpr; c += G * UNROLL, it += UNROLL) {
+      Pack<T, VEC> v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (c + (uint32_t)u * G < cpr) load_pack<T, VEC>(v[u], row + (size_t)(c + (uint32_t)u * G) * VEC);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (c + (uint32_t)u * G < cpr) Op::template accumulate_pack<VEC>(acc, v[u], it + u);
+    }
+  }
+  Acc a = Op::finish(acc[0], g, G, VEC, 0);
+#pragma unroll
+  for (int k = 1; k < VEC; ++k) a = Op::combine(a, Op::finish(acc[k], g, G, VEC, k));
+  if (G <= 32) {
+    a = warp_reduce<Op, Acc>(a, (int)G);
+    if (active && g == 0) red_store<Op>(out, out2, m * p.out_stride, a, p.count, p.fold_out);
+    return;
+  }
+  a = warp_reduce<Op, Acc>(a, 32);
+  if ((tid & 31) == 0) s_part[tid >> 5] = a;
+  __syncthreads();
+  if (g == 0 && active) {
+    const int w0 = tid >> 5, nw = G >> 5;
+    a = s_part[w0];
+    for (int w = 1; w < nw; ++w) a = Op::combine(a, s_part[w0 + w]);
+    red_store<Op>(out, out2, m * p.out_stride, a, p.count, p.fold_out);
   }
 }
 
@@ -847,36 +990,60 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   p.use64 = big ? 1 : 0;
   p.cpr_div = FastDiv(big ? 1u : (uint32_t)p.cpr);
 
+  // lean path: one aligned unit-stride run per output, ≤ 1 kept dim, enough outputs that no split is needed
+  if constexpr (VECMAX > 1) {
+    if (vec == VECMAX && nr == 1 && nk <= 1 && !big && !tune_knob("HPTB_TUNE_NOLEAN")) {
+      static const int occ_l = ctas_per_sm(reduce_rows_lean_kernel<Op, T, VECMAX>, 0);
+      const int64_t lean_slots = (int64_t)sms * occ_l;
+      // threads per row: each thread should own about one batch of UNROLL chunks (all its loads in flight at
+      // once); rows shorter than 32·UNROLL chunks share a warp
+      int logG = 8;
+      while (logG > 0 && ((int64_t)1 << logG) * HPTB_RED_UNROLL > p.cpr) --logG;
+      if (Op::kIndexed && logG > 6 && M * 64 >= lean_slots * kRedThreads) logG = 6;  // (value, index) pairs: cheaper combine
+      if (int64_t t = tune_knob("HPTB_TUNE_G")) { logG = 0; while ((1 << logG) < t && logG < 8) ++logG; }
+      const int64_t lean_blocks = (M + (kRedThreads >> logG) - 1) / (kRedThreads >> logG);
+      // enough CTAs for every SM slot (otherwise the general kernel splits the outputs), or rows so short that
+      // splitting could not help anyway
+      if ((lean_blocks >= lean_slots || p.cpr <= 4 * kRedThreads * HPTB_RED_UNROLL) && lean_blocks >= sms && lean_blocks <= 0x7fffffffLL &&
+          !tune_knob("HPTB_TUNE_S")) {
+        LeanRowsParams q;
+        memset(&q, 0, sizeof(q));
+        q.M = M;
+        q.in_stride = nk ? c.strides[1][kept[0]] : 0;
+        q.out_stride = nk ? c.strides[0][kept[0]] : 0;
+        q.count = plan.count;
+        q.cpr = (uint32_t)p.cpr;
+        q.logG = logG;
+        q.fold_out = plan.fold_out;
+        HPTB_CUDA_CHECK(launch_kernel(reduce_rows_lean_kernel<Op, T, VECMAX>, dim3((unsigned)lean_blocks), dim3(kRedThreads), 0, stream, in, out, out2, q));
+        return HPTB_OK;
+      }
+    }
+  }
   static const int occ_v = ctas_per_sm(reduce_rows_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)>, 0);
   static const int occ_1 = ctas_per_sm(reduce_rows_kernel<Op, T, 1>, 0);
   const int64_t cta_slots = (int64_t)sms * (vec > 1 ? occ_v : occ_1);
   const int64_t thread_slots = cta_slots * kRedThreads;
-  // Launch shape.  Measured on B200 (profiles/, tools/sweep.py): a warp per (virtual) row beats wider groups, and
-  // many small CTAs beat one wave of fat ones (the hardware CTA scheduler balances SMs that stream at different
-  // speeds; a single static wave ends with the slowest SM).  So: G ≤ 32 lanes per row; when the outputs alone
-  // give less than a quarter wave of threads (the split costs a fence + ticket per warp: measured slower than
-  // S = 1 from half a wave up), each output is split over S warps (virtual rows) — or, for very few
-  // outputs with long rows, over S whole CTAs — sized for one wave (warps) / 8 waves (CTAs), ≥ 16 / 8 chunks per lane.
+  // Launch shape (profiles/r01d_sweep.txt, tools/microbench/stream_reduce.cu).  What these HBM-bound kernels need
+  // is every thread issuing one batch of UNROLL independent 16-byte loads as early as possible and the hardware
+  // CTA scheduler — not a static partition — balancing the SMs: so G = the largest power of two that still gives
+  // every thread a full batch (a whole CTA per output from 1024 chunks up), and outputs are split over S CTAs
+  // only when the outputs alone cannot fill the resident CTA slots AND every split keeps ≥ 64 chunks per thread
+  // (bf16 NCHW channel mean, 512 outputs × 25088 chunks: S = 1 → 38 µs, S = 2 → 42 µs, S = 10 → 55 µs; the full
+  // sum of 17 GB: 8 waves of CTAs → 7.3 TB/s).  Arg reductions carry a (value, index) pair through the cross-warp
+  // combine and prefer G = 64 (transposed f32 [8192,8192] argmax: G = 64 → 41.4 µs, G = 256 → 46.6 µs).
   int64_t G = 1;
-  while (G < 32 && G * 8 < p.chunks) G <<= 1;
+  while (G < kRedThreads && G * 2 * HPTB_RED_UNROLL <= p.chunks) G <<= 1;
   int64_t S = 1;
-  if (G == 32 && M * 32 * 4 < thread_slots) {
-    const int64_t need = thread_slots / (M * 32);  // at most ONE wave of warps (640 CTAs on 592 slots ran 37 % slower than 576)
-    int64_t maxS = p.chunks / (32 * 16);
-    if (maxS < 1) maxS = 1;
-    int64_t Sw = need < maxS ? need : maxS;
-    if (Sw > 256) Sw = 256;
-    if (M * 32 * Sw < thread_slots && p.chunks >= (int64_t)kRedThreads * 16) {
-      G = kRedThreads;  // few outputs, long rows: whole CTAs per split
-      S = (8 * cta_slots + M - 1) / M;
-      int64_t maxC = p.chunks / (kRedThreads * 8);
-      if (S > maxC) S = maxC;
-      if (S > 8192) S = 8192;
-      if (S < 1) S = 1;
-    } else {
-      S = Sw;
-    }
+  if (G == kRedThreads && M < cta_slots) {
+    S = (8 * cta_slots + M - 1) / M;
+    const int64_t maxC = p.chunks / (kRedThreads * 64);
+    if (S > maxC) S = maxC;
+    if (S > 8192) S = 8192;
+    if (S < 1) S = 1;
   }
+  if (Op::kIndexed && S == 1 && G > 64 && M * 64 >= thread_slots) G = 64;
+  (void)thread_slots;
   if (int64_t t = tune_knob("HPTB_TUNE_G")) {
     G = 1;
     while (G < t && G < kRedThreads) G <<= 1;

@@ -217,6 +217,29 @@ hptb_status hptb_fill(hptb_ctx* ctx, hptb_tensor* out, const void* scalar, void*
 hptb_status hptb_comm_unique_id(void* id128);                          /* rank 0, then broadcast out of band */
 hptb_status hptb_comm_init_rank(hptb_ctx* ctx, int nranks, int rank, const void* id128, hptb_comm** out);
 hptb_status hptb_comm_destroy(hptb_comm* comm);
+/* Outer-axis sharding helpers (pure host code, usable without a GPU).
+ * hptb_shard_bounds: rank r of `world` owns rows [offset, offset+len) of an axis of length n — contiguous
+ * blocks, the first n % world ranks one row longer.
+ * hptb_shard_plan_reduce: what hptb_reduce_sharded does for (op, axes, shard_axis): whether the reduction crosses
+ * the shard axis, which collective combines the per-rank partials and which post-op follows. */
+typedef enum hptb_collective {
+  HPTB_COLL_NONE = 0,           /* the reduced axes do not include the shard axis: purely local */
+  HPTB_COLL_ALLREDUCE_SUM = 1,  /* sum, sum_square; mean (local Σ ÷ GLOBAL count); logsumexp (on exp of the local value) */
+  HPTB_COLL_ALLREDUCE_PROD = 2,
+  HPTB_COLL_ALLREDUCE_MAX = 3,
+  HPTB_COLL_ALLREDUCE_MIN = 4,
+  HPTB_COLL_ALLGATHER_ARG = 5   /* argmax/argmin: all-gather (extreme value, global index), rank-ordered strict combine */
+} hptb_collective;
+typedef struct hptb_shard_plan {
+  int32_t crosses;      /* 1 if shard_axis is among the reduced axes */
+  int32_t collective;   /* hptb_collective */
+  int32_t pre_exp;      /* 1: exp() the local result before the collective (logsumexp) */
+  int32_t post_ln;      /* 1: ln() after the collective (logsumexp) */
+  int32_t global_count; /* 1: the local op divides by the GLOBAL element count (mean) */
+} hptb_shard_plan;
+hptb_status hptb_shard_bounds(int64_t n, int world, int rank, int64_t* offset, int64_t* len);
+hptb_status hptb_shard_plan_reduce(int op, const int32_t* axes, int naxes, int shard_axis, int world,
+                                   hptb_shard_plan* plan);
 /* Combine per-rank partials in place.  op = HPTB_SUM / HPTB_MAX / HPTB_MIN / HPTB_PROD. */
 hptb_status hptb_allreduce(hptb_comm* comm, int op, hptb_tensor* inout, void* stream);
 /* Reduction of a tensor sharded along axis `shard_axis` (each rank passes its own shard).  Reduces

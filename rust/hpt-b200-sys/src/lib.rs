@@ -64,6 +64,8 @@ pub struct hptb_collapse_plan {
 
 #[repr(C)] pub struct hptb_ctx { _private: [u8; 0] }
 #[repr(C)] pub struct hptb_comm { _private: [u8; 0] }
+#[repr(C)] #[derive(Clone, Copy, Debug, Default)]
+pub struct hptb_shard_plan { pub crosses: i32, pub collective: i32, pub pre_exp: i32, pub post_ln: i32, pub global_count: i32 }
 
 extern "C" {
     pub fn hptb_version() -> c_int;
@@ -114,6 +116,9 @@ extern "C" {
     pub fn hptb_comm_init_rank(ctx: *mut hptb_ctx, nranks: c_int, rank: c_int, id128: *const c_void,
                                out: *mut *mut hptb_comm) -> hptb_status;
     pub fn hptb_comm_destroy(comm: *mut hptb_comm) -> hptb_status;
+    pub fn hptb_shard_bounds(n: i64, world: c_int, rank: c_int, offset: *mut i64, len: *mut i64) -> hptb_status;
+    pub fn hptb_shard_plan_reduce(op: c_int, axes: *const i32, naxes: c_int, shard_axis: c_int, world: c_int,
+                                  plan: *mut hptb_shard_plan) -> hptb_status;
     pub fn hptb_allreduce(comm: *mut hptb_comm, op: c_int, inout: *mut hptb_tensor, stream: *mut c_void) -> hptb_status;
     pub fn hptb_reduce_sharded(comm: *mut hptb_comm, op: c_int, shard: *const hptb_tensor, axes: *const i32, naxes: c_int,
                                shard_axis: c_int, shard_offset: i64, global_axis_len: i64, out: *mut hptb_tensor,

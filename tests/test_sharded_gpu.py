@@ -1,0 +1,39 @@
+"""Multi-GPU parity of the sharded reductions (NCCL over NVLink), one process per GPU via torch.distributed.run.
+Skipped on boxes with fewer than 2 GPUs (the single-GPU driver run); `gpurun --gpus 2` exercises it."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_sharded_reductions_two_ranks():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29400 + os.getpid() % 500), os.path.join(ROOT, "tests", "sharded_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-4000:] + "\n" + r.stderr[-4000:]
+    assert r.stdout.count("sharded ok") == 2, r.stdout[-2000:]
+
+
+@pytest.mark.gpu
+def test_single_rank_comm_offsets_arg_indices():
+    """world = 1: no exchange, but argmax over the shard axis still reports GLOBAL indices (offset added)."""
+    import numpy as np
+    import hpt_b200 as hb
+    ctx = hb.context(0)
+    try:
+        comm = hb.Comm(ctx, 1, 0, hb.Comm.unique_id())
+    except hb.HptError as ex:
+        pytest.skip(f"NCCL unavailable: {ex}")
+    x = np.random.default_rng(3).standard_normal((9, 5)).astype(np.float32)
+    X = hb.ShardedTensor(hb.Tensor.to_cuda(torch.from_numpy(x)), comm, 0, 100, 40)
+    got = X.argmax(0).to_cpu().numpy()
+    np.testing.assert_array_equal(got, x.argmax(axis=0) + 40)
+    np.testing.assert_allclose(X.sum([0]).to_cpu().numpy(), x.sum(axis=0), rtol=1e-5, atol=1e-5)
+    comm.destroy()

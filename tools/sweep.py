@@ -108,7 +108,7 @@ class Sweep:
         self.f.flush()
         print(f"{case:28s} {impl:8s} {self.variant:8s} {str(knobs):24s} {us:9.2f} us {gbs:8.1f} GB/s {gbs / PEAK:6.3f}  host {timeit.host_us:6.1f} us", flush=True)
 
-    def knob_sweep(self, case, fns, reps, nbytes, G=(), S=(), flags=()):
+    def knob_sweep(self, case, fns, reps, nbytes, G=(), S=(), flags=(), GS=()):
         for k in ("HPTB_TUNE_G", "HPTB_TUNE_S") + tuple(flags):
             os.environ.pop(k, None)
         self.emit(case, "hptb", {}, timeit(fns, reps), nbytes)
@@ -123,6 +123,11 @@ class Sweep:
         for s in S:
             os.environ["HPTB_TUNE_S"] = str(s)
             self.emit(case, "hptb", {"S": s}, timeit(fns, reps), nbytes)
+        os.environ.pop("HPTB_TUNE_S", None)
+        for g, s_ in GS:
+            os.environ["HPTB_TUNE_G"], os.environ["HPTB_TUNE_S"] = str(g), str(s_)
+            self.emit(case, "hptb", {"G": g, "S": s_}, timeit(fns, reps), nbytes)
+        os.environ.pop("HPTB_TUNE_G", None)
         os.environ.pop("HPTB_TUNE_S", None)
 
 
@@ -162,7 +167,7 @@ def main():
         sw.emit("cfg1.add_bcast", "torch", {}, timeit([lambda i=i: torch.add(a[i], b[i], out=c[i]) for i in range(R)], 200), 134234112)
         sw.knob_sweep("cfg1.add_same", [c_binary("add", A[i], A[(i + 1) % R], C[i]) for i in range(R)], 200, 3 * 67108864)
         sw.emit("cfg1.add_same", "torch", {}, timeit([lambda i=i: torch.add(a[i], a[(i + 1) % R], out=c[i]) for i in range(R)], 200), 3 * 67108864)
-        sw.knob_sweep("cfg1.sum_axis1", [c_reduce("sum", A[i], [1], S_[i]) for i in range(R)], 200, 67125248, G=(32, 64), S=(1, 2, 4))
+        sw.knob_sweep("cfg1.sum_axis1", [c_reduce("sum", A[i], [1], S_[i]) for i in range(R)], 200, 67125248, G=(32, 64, 128, 256), flags=("HPTB_TUNE_NOLEAN",))
         sw.emit("cfg1.sum_axis1", "torch", {}, timeit([lambda i=i: torch.sum(a[i], 1, out=s[i]) for i in range(R)], 200), 67125248)
         sw.knob_sweep("cfg1.sum_axis0", [c_reduce("sum", A[i], [0], S_[i]) for i in range(R)], 200, 67125248, S=(1, 4, 9, 18, 37))
         sw.emit("cfg1.sum_axis0", "torch", {}, timeit([lambda i=i: torch.sum(a[i], 0, out=s[i]) for i in range(R)], 200), 67125248)
@@ -194,9 +199,9 @@ def main():
         def red(op, out):
             ax = (_ffi.c_int32 * 1)(0)
             _ffi.check(hb.lib.hptb_reduce(V.ctx.handle, _ffi.REDUCE_OPS[op], _ffi.byref(V._c()), ax, 1, _ffi.byref(out._c()), 1, hb.get_stream()))
-        sw.knob_sweep("cfg2.max_T0", [c_reduce("max", V, [0], Mx)], 50, 268468224, G=(32, 64), S=(1, 2, 4, 8))
+        sw.knob_sweep("cfg2.max_T0", [c_reduce("max", V, [0], Mx)], 50, 268468224, G=(32, 64, 128, 256), flags=("HPTB_TUNE_NOLEAN",))
         sw.emit("cfg2.max_T0", "torch", {}, timeit([lambda: torch.amax(x.t(), 0, out=m)], 50), 268468224)
-        sw.knob_sweep("cfg2.argmax_T0", [c_reduce("argmax", V, [0], Ix)], 50, 268500992, G=(32, 64), S=(1, 2, 4, 8))
+        sw.knob_sweep("cfg2.argmax_T0", [c_reduce("argmax", V, [0], Ix)], 50, 268500992, G=(32, 64, 128, 256), flags=("HPTB_TUNE_NOLEAN",))
         sw.emit("cfg2.argmax_T0", "torch", {}, timeit([lambda: torch.argmax(x.t(), 0, out=ix)], 50), 268500992)
         # the same reductions on the contiguous tensor over axis 0 (cols kernel)
         def redc(op, out):
@@ -220,7 +225,8 @@ def main():
         def meanvar(i):
             ax = (_ffi.c_int32 * 3)(0, 1, 2)
             _ffi.check(hb.lib.hptb_mean_var(V[i].ctx.handle, _ffi.byref(V[i]._c()), ax, 3, _ffi.byref(o[i]._c()), _ffi.byref(o2[i]._c()), hb.get_stream()))
-        sw.knob_sweep("cfg3.mean_bf16", [c_reduce("mean", V[i], [0, 1, 2], o[i]) for i in range(2)], 100, 205521920, S=(8, 16, 32, 49, 64, 98, 128))
+        sw.knob_sweep("cfg3.mean_bf16", [c_reduce("mean", V[i], [0, 1, 2], o[i]) for i in range(2)], 100, 205521920, S=(4, 8, 16),
+                      GS=((256, 1), (256, 2), (256, 3), (256, 4), (256, 8), (128, 1), (64, 1)))
         sw.emit("cfg3.mean_bf16", "torch", {}, timeit([lambda i=i: x[i].mean((0, 2, 3)) for i in range(2)], 100), 205521920)
         sw.knob_sweep("cfg3.meanvar_bf16", [c_meanvar(V[i], [0, 1, 2], o[i], o2[i]) for i in range(2)], 100, 205522944, S=(16, 49, 64, 128))
         sw.emit("cfg3.meanvar_bf16", "torch", {}, timeit([lambda i=i: torch.var_mean(x[i], (0, 2, 3), correction=0) for i in range(2)], 100), 205522944)
@@ -239,7 +245,7 @@ def main():
             _ffi.check(hb.lib.hptb_reduce(X[i].ctx.handle, _ffi.REDUCE_OPS["logsumexp"], _ffi.byref(X[i]._c()), ax, 1, _ffi.byref(L[i]._c()), 1, hb.get_stream()))
         sw.knob_sweep("cfg4.softmax", [c_softmax(X[i], 2, Y[i]) for i in range(R)], 200, 134217728)
         sw.emit("cfg4.softmax", "torch", {}, timeit([lambda i=i: torch.softmax(x[i], -1, out=y[i]) for i in range(R)], 200), 134217728)
-        sw.knob_sweep("cfg4.logsumexp", [c_reduce("logsumexp", X[i], [2], L[i]) for i in range(R)], 200, 67125248, G=(32, 64), S=(1, 2, 4))
+        sw.knob_sweep("cfg4.logsumexp", [c_reduce("logsumexp", X[i], [2], L[i]) for i in range(R)], 200, 67125248, G=(32, 64, 128, 256), flags=("HPTB_TUNE_NOLEAN",))
         sw.emit("cfg4.logsumexp", "torch", {}, timeit([lambda i=i: torch.logsumexp(x[i], -1, out=l[i]) for i in range(R)], 200), 67125248)
         kt = torch.randint(-1000, 1000, (4096,), generator=g, device=dev, dtype=torch.int64)
         K = wrap(kt, I64)
