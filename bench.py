@@ -298,7 +298,7 @@ def run_ours(args):
     kernels = []
     for (name, _, nbytes), ms in zip(ops, per_op_ms):
         gbs = nbytes / (ms * 1e-3) / 1e9
-        kernels.append({"op": name, "kernel": "map_tiled_smem_kernel" if name in ("sin", "exp") else "reduce_rows_kernel",
+        kernels.append({"op": name, "kernel": "map_tiled_smem_kernel" if name in ("sin", "exp") else "reduce_rows_lean_kernel",
                         "us": round(ms * 1e3, 2), "algorithmic_bytes": nbytes, "gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
                         "share_of_step": round(ms / sum(per_op_ms), 4)})
     # dominant kernel: the transposing tile map (sin + exp launches, 60 % of the step)

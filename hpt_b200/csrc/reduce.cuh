@@ -187,7 +187,7 @@ template <typename T> struct ReduceOp<HPTB_LOGSUMEXP, T>
   static __device__ __forceinline__ Acc identity() { return (Acc)0; }
   static __device__ __forceinline__ Acc pre(T x, int64_t) {
     Acc c = to_compute<Out>(cast<Out>(x));
-    if constexpr (std::is_same<Acc, float>::value) return expf(c);
+    if constexpr (std::is_same<Acc, float>::value) return fast_expf_ovf(c);  // ≤ 2 ulp, 9 instructions (scalar.cuh)
     else return exp(c);
   }
   static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return a + b; }
@@ -629,27 +629,36 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
 // trips (f32 [4096,4096] row sums: 12.3 µs CTA-per-row vs 14.4 µs warp-per-row; [16384,16384]: 7.28 vs 6.54 TB/s).
 struct LeanRowsParams {
   int64_t M;           // outputs
-  int64_t in_stride;   // elements between the starts of consecutive rows
+  int64_t in_stride;   // elements between the first runs of consecutive outputs
   int64_t out_stride;
+  int64_t run_stride;  // MULTI: elements between consecutive runs of one output (the second reduced dim)
   double count;
-  uint32_t cpr;        // 16-byte chunks per row
-  int32_t logG;        // log2 of the threads per row (5..8 → warp .. CTA per row; < 5 for short rows)
+  uint32_t cpr;        // 16-byte chunks per run
+  uint32_t chunks;     // chunks per output (= cpr unless MULTI)
+  int32_t logG;        // log2 of the threads per output (8 = a whole CTA)
   int32_t fold_out;
 };
 
 // resident CTAs per SM the register allocation must allow: 6 (≤ 40 registers) for plain 4-byte accumulators — 8
 // (≤ 32 registers) spills 8–48 bytes per thread and measured no faster (profiles/r01d_sweep.txt, variant mb6)
-template <typename Op>
-constexpr int lean_min_blocks() { return (Op::kIndexed || sizeof(typename Op::Acc) > 4) ? 5 : HPTB_LEAN_MINB; }
+template <typename Op, bool MULTI>
+constexpr int lean_min_blocks() {
+  return (MULTI || sizeof(typename Op::Local) > 8) ? 4 : (Op::kIndexed || sizeof(typename Op::Local) > 4) ? 5 : HPTB_LEAN_MINB;
+}
 
-template <typename Op, typename T, int VEC>
-__global__ void __launch_bounds__(kRedThreads, lean_min_blocks<Op>())
+// MULTI: an output is `chunks / cpr` runs of cpr chunks, run_stride apart (NCHW channel statistics: 64 runs of
+// 3136 contiguous elements per channel).  A thread walks the flattened (run, column) chunk space with stride G and
+// carries its position incrementally: one add and one compare per chunk.  Such outputs are long and usually few
+// (512 channels → 3.5 CTAs per SM), so the MULTI kernel keeps 2·UNROLL loads in flight per thread instead of
+// relying on resident CTAs for memory-level parallelism.
+template <typename Op, typename T, int VEC, bool MULTI>
+__global__ void __launch_bounds__(kRedThreads, lean_min_blocks<Op, MULTI>())
 reduce_rows_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out, typename Op::Out* __restrict__ out2,
                         LeanRowsParams p) {
   pdl_prologue();
   typedef typename Op::Acc Acc;
   typedef typename Op::Local Local;
-  constexpr int UNROLL = HPTB_RED_UNROLL;
+  constexpr int UNROLL = MULTI ? 2 * HPTB_RED_UNROLL : HPTB_RED_UNROLL;
   __shared__ Acc s_part[kRedThreads / 32];
   const uint32_t tid = threadIdx.x;
   const uint32_t G = 1u << p.logG;
@@ -661,16 +670,34 @@ reduce_rows_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__
   for (int k = 0; k < VEC; ++k) acc[k] = Op::local_identity();
   if (active) {
     const T* row = in + m * p.in_stride;
-    const uint32_t cpr = p.cpr;
+    const uint32_t n = MULTI ? p.chunks : p.cpr;
     int32_t it = 0;
-    for (uint32_t c = g; c < cpr; c += G * UNROLL, it += UNROLL) {
-      Pack<T, VEC> v[UNROLL];
+    if constexpr (!MULTI) {
+      for (uint32_t c = g; c < n; c += G * UNROLL, it += UNROLL) {
+        Pack<T, VEC> v[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u)
-        if (c + (uint32_t)u * G < cpr) load_pack<T, VEC>(v[u], row + (size_t)(c + (uint32_t)u * G) * VEC);
+        for (int u = 0; u < UNROLL; ++u)
+          if (c + (uint32_t)u * G < n) load_pack<T, VEC>(v[u], row + (size_t)(c + (uint32_t)u * G) * VEC);
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u)
-        if (c + (uint32_t)u * G < cpr) Op::template accumulate_pack<VEC>(acc, v[u], it + u);
+        for (int u = 0; u < UNROLL; ++u)
+          if (c + (uint32_t)u * G < n) Op::template accumulate_pack<VEC>(acc, v[u], it + u);
+      }
+    } else {
+      const uint32_t cpr = p.cpr;
+      uint32_t col = g % cpr;
+      const T* runp = row + (int64_t)(g / cpr) * p.run_stride;
+      for (uint32_t c = g; c < n; c += G * UNROLL) {
+        Pack<T, VEC> v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          if (c + (uint32_t)u * G < n) load_pack<T, VEC>(v[u], runp + (size_t)col * VEC);
+          col += G;
+          while (col >= cpr) { col -= cpr; runp += p.run_stride; }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          if (c + (uint32_t)u * G < n) Op::template accumulate_pack<VEC>(acc, v[u], 0);
+      }
     }
   }
   Acc a = Op::finish(acc[0], g, G, VEC, 0);
@@ -990,36 +1017,6 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   p.use64 = big ? 1 : 0;
   p.cpr_div = FastDiv(big ? 1u : (uint32_t)p.cpr);
 
-  // lean path: one aligned unit-stride run per output, ≤ 1 kept dim, enough outputs that no split is needed
-  if constexpr (VECMAX > 1) {
-    if (vec == VECMAX && nr == 1 && nk <= 1 && !big && !tune_knob("HPTB_TUNE_NOLEAN")) {
-      static const int occ_l = ctas_per_sm(reduce_rows_lean_kernel<Op, T, VECMAX>, 0);
-      const int64_t lean_slots = (int64_t)sms * occ_l;
-      // threads per row: each thread should own about one batch of UNROLL chunks (all its loads in flight at
-      // once); rows shorter than 32·UNROLL chunks share a warp
-      int logG = 8;
-      while (logG > 0 && ((int64_t)1 << logG) * HPTB_RED_UNROLL > p.cpr) --logG;
-      if (Op::kIndexed && logG > 6 && M * 64 >= lean_slots * kRedThreads) logG = 6;  // (value, index) pairs: cheaper combine
-      if (int64_t t = tune_knob("HPTB_TUNE_G")) { logG = 0; while ((1 << logG) < t && logG < 8) ++logG; }
-      const int64_t lean_blocks = (M + (kRedThreads >> logG) - 1) / (kRedThreads >> logG);
-      // enough CTAs for every SM slot (otherwise the general kernel splits the outputs), or rows so short that
-      // splitting could not help anyway
-      if ((lean_blocks >= lean_slots || p.cpr <= 4 * kRedThreads * HPTB_RED_UNROLL) && lean_blocks >= sms && lean_blocks <= 0x7fffffffLL &&
-          !tune_knob("HPTB_TUNE_S")) {
-        LeanRowsParams q;
-        memset(&q, 0, sizeof(q));
-        q.M = M;
-        q.in_stride = nk ? c.strides[1][kept[0]] : 0;
-        q.out_stride = nk ? c.strides[0][kept[0]] : 0;
-        q.count = plan.count;
-        q.cpr = (uint32_t)p.cpr;
-        q.logG = logG;
-        q.fold_out = plan.fold_out;
-        HPTB_CUDA_CHECK(launch_kernel(reduce_rows_lean_kernel<Op, T, VECMAX>, dim3((unsigned)lean_blocks), dim3(kRedThreads), 0, stream, in, out, out2, q));
-        return HPTB_OK;
-      }
-    }
-  }
   static const int occ_v = ctas_per_sm(reduce_rows_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)>, 0);
   static const int occ_1 = ctas_per_sm(reduce_rows_kernel<Op, T, 1>, 0);
   const int64_t cta_slots = (int64_t)sms * (vec > 1 ? occ_v : occ_1);
@@ -1051,6 +1048,35 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   }
   if (int64_t t = tune_knob("HPTB_TUNE_S")) {
     if (G == kRedThreads || G == 32) S = t > p.chunks ? p.chunks : t;
+  }
+  // lean path: unsplit outputs made of aligned unit-stride runs (one run, or runs along ONE more reduced dim),
+  // ≤ 1 kept dim, 32-bit counters
+  if constexpr (VECMAX > 1) {
+    const bool multi = nr == 2;
+    if (S == 1 && vec == VECMAX && nr >= 1 && nr <= 2 && nk <= 1 && !big && !(multi && Op::kIndexed) && p.chunks < (int64_t(1) << 31) &&
+        !tune_knob("HPTB_TUNE_NOLEAN")) {
+      int logG = 0;
+      while ((1 << logG) < G) ++logG;
+      const int64_t lean_blocks = (M + (kRedThreads >> logG) - 1) / (kRedThreads >> logG);
+      if (lean_blocks <= 0x7fffffffLL) {
+        LeanRowsParams q;
+        memset(&q, 0, sizeof(q));
+        q.M = M;
+        q.in_stride = nk ? c.strides[1][kept[0]] : 0;
+        q.out_stride = nk ? c.strides[0][kept[0]] : 0;
+        q.run_stride = multi ? c.strides[1][red[1]] : 0;
+        q.count = plan.count;
+        q.cpr = (uint32_t)p.cpr;
+        q.chunks = (uint32_t)p.chunks;
+        q.logG = logG;
+        q.fold_out = plan.fold_out;
+        if (multi)
+          HPTB_CUDA_CHECK(launch_kernel(reduce_rows_lean_kernel<Op, T, VECMAX, true>, dim3((unsigned)lean_blocks), dim3(kRedThreads), 0, stream, in, out, out2, q));
+        else
+          HPTB_CUDA_CHECK(launch_kernel(reduce_rows_lean_kernel<Op, T, VECMAX, false>, dim3((unsigned)lean_blocks), dim3(kRedThreads), 0, stream, in, out, out2, q));
+        return HPTB_OK;
+      }
+    }
   }
   p.chunks_per_split = (p.chunks + S - 1) / S;
   S = (p.chunks + p.chunks_per_split - 1) / p.chunks_per_split;

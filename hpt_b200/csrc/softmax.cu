@@ -65,18 +65,8 @@ template <typename C> __device__ __forceinline__ C sm_max(C a, C b) {
   if constexpr (std::is_same<C, float>::value) return fmaxf(a, b); else return fmax(a, b);
 }
 
-// exp for the register-resident kernel: ex2(x·log2e) with the rounding error of the product folded back in
-// (hi + lo = x·log2e to ~2^-48; exp = ex2(hi)·(1 + lo·ln2)), 7 instructions against libdevice expf's 12, same
-// accuracy class (MUFU.EX2 ≤ 2 ulp).  Inputs below −110 (including −inf: masked logits, padding lanes) give 0;
-// NaN propagates.
-__device__ __forceinline__ float sm_exp_fast(float x) {
-  x = x < -110.0f ? -110.0f : x;  // a select, not fmaxf: NaN must survive
-  const float hi = x * 1.4426950408889634f;
-  const float lo = fmaf(x, 1.4426950408889634f, -hi) + x * 1.9259629911266175e-8f;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(hi));
-  return fmaf(e, lo * 0.6931471805599453f, e);
-}
+// exp for the register-resident kernel: fast_expf (scalar.cuh)
+__device__ __forceinline__ float sm_exp_fast(float x) { return fast_expf(x); }
 __device__ __forceinline__ double sm_exp_fast(double x) { return exp(x); }
 
 struct MaxOp {
@@ -105,7 +95,9 @@ __device__ __forceinline__ C group_reduce(C v, C* s_buf, C ident) {
   return v;
 }
 
-template <typename T, int VEC, int G, bool LOG>
+// NCH = packs per thread the row needs (a template parameter, so that a 4-pack row does not carry the registers
+// and predicated instructions of an 8-pack one: 4096-element f32 rows went from 48 to ≤ 40 registers, 5 → 6 CTAs/SM)
+template <typename T, int VEC, int G, bool LOG, int NCH>
 __global__ void __launch_bounds__(kSmThreads)
 softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
                  SoftmaxParams p) {
@@ -120,10 +112,10 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
   int64_t in_off = 0, out_off = 0;
   if (active) walk2(row, p.kept, p.use64, in_off, out_off);
   const C neg_inf = Limits<C>::lowest();
-  C x[kSmChunks][VEC];
+  C x[NCH][VEC];
   C mx = neg_inf;
 #pragma unroll
-  for (int i = 0; i < kSmChunks; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     const int e = (i * G + lane) * VEC;  // a register-resident row has at most 8·256·VEC elements
     if (i < p.nchunks && active && e < (int)p.L) {
       Pack<T, VEC> v;
@@ -141,7 +133,7 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
   mx = group_reduce<MaxOp, C, G>(mx, s_buf, neg_inf);
   C sum = (C)0;
 #pragma unroll
-  for (int i = 0; i < kSmChunks; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     if (i < p.nchunks) {
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
@@ -159,7 +151,7 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
   const C lg = sm_log<C>(sum);
   const C inv = (C)1 / sum;  // one division per row; the per-element multiply adds ≤ 0.5 ulp over a division
 #pragma unroll
-  for (int i = 0; i < kSmChunks; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     const int e = (i * G + lane) * VEC;
     if (i < p.nchunks && active && e < (int)p.L) {
       Pack<O, VEC> o;
@@ -304,10 +296,16 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
       p.nchunks = (int)((packs + G - 1) / G);
       int64_t blocks = (M + (kSmThreads / G) - 1) / (kSmThreads / G);
       if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "softmax: grid too large");
-#define HPTB_SM_LAUNCH(V, GG)                                                                                   \
+#define HPTB_SM_LAUNCH2(V, GG, N)                                                                               \
   do {                                                                                                            \
-    if (log) HPTB_CUDA_CHECK(launch_kernel(softmax_rows_reg<T, V, GG, true>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p)); \
-    else HPTB_CUDA_CHECK(launch_kernel(softmax_rows_reg<T, V, GG, false>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p)); \
+    if (log) HPTB_CUDA_CHECK(launch_kernel(softmax_rows_reg<T, V, GG, true, N>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p)); \
+    else HPTB_CUDA_CHECK(launch_kernel(softmax_rows_reg<T, V, GG, false, N>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p)); \
+  } while (0)
+#define HPTB_SM_LAUNCH(V, GG)                              \
+  do {                                                     \
+    if (GG == 32 || p.nchunks <= 2) HPTB_SM_LAUNCH2(V, GG, (GG == 32 ? 4 : 2)); \
+    else if (p.nchunks <= 4) HPTB_SM_LAUNCH2(V, GG, 4);    \
+    else HPTB_SM_LAUNCH2(V, GG, kSmChunks);                \
   } while (0)
       if (vec > 1) {
         if (G == 32) HPTB_SM_LAUNCH(VECMAX, 32);
@@ -317,6 +315,7 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
         else HPTB_SM_LAUNCH(1, kSmThreads);
       }
 #undef HPTB_SM_LAUNCH
+#undef HPTB_SM_LAUNCH2
       HPTB_CUDA_CHECK(cudaGetLastError());
       count_launches(1);
       return HPTB_OK;

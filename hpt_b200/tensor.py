@@ -128,6 +128,7 @@ class Tensor:
         self.dtype = int(dtype)
         self.shape = tuple(int(s) for s in shape)
         self.strides = tuple(int(s) for s in strides)
+        self._cstruct = None  # hptb_tensor image, built once (a Tensor's pointer, shape and strides never change)
 
     # ---- creation / transfer -----------------------------------------------------------------
     @staticmethod
@@ -206,7 +207,10 @@ class Tensor:
         return True
 
     def _c(self):
-        return make_tensor(self.ptr, self.dtype, self.shape, self.strides)
+        c = self._cstruct
+        if c is None:
+            c = self._cstruct = make_tensor(self.ptr, self.dtype, self.shape, self.strides)
+        return c
 
     def __repr__(self):
         return f"Tensor<{_ffi.DTYPE_NAMES[self.dtype]}, Cuda, {self.ctx.device}>(shape={self.shape}, strides={self.strides})"

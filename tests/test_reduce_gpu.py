@@ -213,3 +213,38 @@ def test_bench_config_shapes_reduced(hb):
     _check(hb, "sum", y, "f32", [0])
     z = rand(rng, (8, 128, 4096), "f32")
     _check(hb, "logsumexp", z, "f32", [-1])
+
+
+@pytest.mark.gpu
+def test_logsumexp_overflow_and_special_values(hb):
+    """naive ln Σ exp as the reference (common_reduce.rs:451-480): large inputs overflow to +inf (not NaN),
+    -inf contributes 0, NaN poisons its row; covers the lean, multi-run and split launch shapes."""
+    rng = np.random.default_rng(31)
+    x = rand(rng, (64, 4096), "f32")
+    x[0, 5] = 100.0          # exp overflows f32
+    x[1, 7] = np.inf
+    x[2, :] = -np.inf        # Σ exp = 0 → ln 0 = -inf
+    x[3, 9] = np.nan
+    x[4, 100] = 88.9         # just above the overflow threshold of a single exp
+    x[5, :] = -200.0         # every exp underflows
+    _check(hb, "logsumexp", x, "f32", [1])
+    y = rand(rng, (6, 16, 520), "f32")
+    y[1, 3, 7] = 95.0
+    _check(hb, "logsumexp", y, "f32", [0, 2])      # kept middle dim: runs along one more reduced dim
+    _check(hb, "logsumexp", y, "f32", [0, 1, 2])   # one output: split over CTAs
+    h = rand(rng, (32, 2048), "bf16")
+    _check(hb, "logsumexp", h, "bf16", [1])
+
+
+@pytest.mark.gpu
+def test_multi_run_outputs_match(hb):
+    """NCHW channel statistics shape class (config 3 at reduced size): every output is many unit-stride runs."""
+    rng = np.random.default_rng(32)
+    for d in ("bf16", "f16", "f32", "i32"):
+        x = rand(rng, (6, 40, 14, 14), d)
+        perm = lambda t: t.permute([0, 2, 3, 1]) if hasattr(t, "storage") else np.transpose(t, (0, 2, 3, 1))
+        for op in ("mean", "sum", "max", "sum_square"):
+            _check(hb, op, x, d, [0, 1, 2], view=perm)
+    x = rand(rng, (3, 7, 1000), "f32")  # runs longer than one CTA pass, odd run counts
+    _check(hb, "sum", x, "f32", [0, 2])
+    _check(hb, "mean", x, "f32", [0, 2])
