@@ -351,7 +351,23 @@ def extra_rows(hb, torch, dist, world, rank, local, stream, peak):
     return run_rows(hb, torch, dist, world, rank, local, stream, peak)
 
 
+def _claim_stdout():
+    """The driver parses ONE JSON line from stdout; NCCL and friends print banners there ("NCCL version …").
+    Keep a private handle on the real stdout for the JSON line and point fd 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    global print
+    out = _claim_stdout()
+    _print = print
+
+    def print(*a, **k):  # noqa: A001 — the JSON line goes to the real stdout
+        k.pop("flush", None)
+        _print(*a, file=out, flush=True, **k)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -25,11 +25,15 @@ DTYPES = [("b8", "bool"), ("int8_t", "i8"), ("int16_t", "i16"), ("int32_t", "i32
           ("uint8_t", "u8"), ("uint16_t", "u16"), ("uint32_t", "u32"), ("uint64_t", "u64"),
           ("f16", "f16"), ("bf16", "bf16"), ("float", "f32"), ("double", "f64")]
 BINARY_OPS = [("OpAdd", "add", 0, 1), ("OpSub", "sub", 0, 0), ("OpMul", "mul", 0, 1), ("OpRem", "rem", 0, 0),
-              ("OpDiv", "div", 1, 0), ("OpMax", "maximum", 0, 1), ("OpMin", "minimum", 0, 1)]
+              ("OpDiv", "div", 1, 0), ("OpMax", "maximum", 0, 1), ("OpMin", "minimum", 0, 1),
+              ("OpPow", "pow", 1, 0), ("OpHypot", "hypot", 1, 0)]
+NORMAL_UNARY_OPS = ["floor", "ceil", "round", "trunc", "abs", "neg", "sign", "square", "relu", "relu6", "leaky_relu",
+                    "clamp", "bitnot"]
 UNARY_OPS = ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh",
              "exp", "exp2", "exp10", "ln", "log2", "log10", "sqrt", "cbrt", "recip", "erf", "sigmoid", "gelu",
              "selu", "elu", "celu", "mish", "softplus", "softsign", "hard_sigmoid", "hard_swish"]
-REDUCE_OPS = ["sum", "mean", "max", "min", "argmax", "argmin", "logsumexp", "sum_square", "prod"]
+REDUCE_OPS = ["sum", "mean", "max", "min", "argmax", "argmin", "logsumexp", "sum_square", "prod",
+              "reducel1", "nansum", "nanprod", "all", "any", "reducel2", "reducel3"]
 
 NVCC_FLAGS = ("-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr "
               "-Xfatbin -compress-all -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xcudafe --diag_suppress=177 "
@@ -46,6 +50,8 @@ def units():
                   f"-DHPTB_OP={fn} -DHPTB_OPNAME={name} -DHPTB_KIND={kind} -DHPTB_BOOL_OK={bool_ok}"))
     for name in UNARY_OPS:
         u.append((f"unary_{name}", "unary_inst.cu", f"-DHPTB_OPENUM=HPTB_{name.upper()} -DHPTB_OPNAME={name}"))
+    for name in NORMAL_UNARY_OPS:
+        u.append((f"nunary_{name}", "nunary_inst.cu", f"-DHPTB_OPENUM=HPTB_{name.upper()} -DHPTB_OPNAME={name}"))
     u.append(("copy_same", "cast_inst.cu", ""))
     # runtime-typed kernels: one unit per OUTPUT dtype (mixed-dtype binary, integer-input unary, astype)
     for cty, short in DTYPES:

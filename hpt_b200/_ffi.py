@@ -24,13 +24,19 @@ BOOL, I8, I16, I32, I64, U8, U16, U32, U64, F16, BF16, F32, F64 = range(13)
 DTYPE_NAMES = ["bool", "i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "f16", "bf16", "f32", "f64"]
 DTYPE_SIZES = [1, 1, 2, 4, 8, 1, 2, 4, 8, 2, 2, 4, 8]
 
-BINARY_OPS = {"add": 0, "sub": 1, "mul": 2, "rem": 3, "div": 4, "maximum": 5, "minimum": 6}
+BINARY_OPS = {"add": 0, "sub": 1, "mul": 2, "rem": 3, "div": 4, "maximum": 5, "minimum": 6, "pow": 7, "hypot": 8,
+              "bitand": 9, "bitor": 10, "bitxor": 11, "shl": 12, "shr": 13}
+CMP_OPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
 UNARY_OPS = {n: i for i, n in enumerate([
     "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh",
     "exp", "exp2", "exp10", "ln", "log2", "log10", "sqrt", "cbrt", "recip", "erf", "sigmoid", "gelu",
-    "selu", "elu", "celu", "mish", "softplus", "softsign", "hard_sigmoid", "hard_swish"])}
+    "selu", "elu", "celu", "mish", "softplus", "softsign", "hard_sigmoid", "hard_swish",
+    # NormalUaryOps (+ bitnot): output dtype = input dtype
+    "floor", "ceil", "round", "trunc", "abs", "neg", "sign", "square", "relu", "relu6", "leaky_relu", "clamp", "bitnot"])}
+FLOAT_UNARY_COUNT = UNARY_OPS["floor"]
 REDUCE_OPS = {"sum": 0, "mean": 1, "max": 2, "min": 3, "argmax": 4, "argmin": 5, "logsumexp": 6,
-              "sum_square": 7, "prod": 8}
+              "sum_square": 7, "prod": 8, "reducel1": 9, "nansum": 10, "nanprod": 11, "all": 12, "any": 13,
+              "reducel2": 14, "reducel3": 15}
 PROMOTE_NORMAL, PROMOTE_FLOAT_BINARY, PROMOTE_FLOAT_UNARY = 0, 1, 2
 
 STATUS_NAMES = {0: "OK", 1: "SHAPE", 2: "DTYPE", 3: "AXIS", 4: "INVALID", 5: "CUDA", 6: "OOM", 7: "NCCL",
@@ -103,6 +109,7 @@ SIGNATURES = {
     "hptb_reduce_shape": (c_int, [POINTER(c_int64), c_int, POINTER(c_int32), c_int, c_int, POINTER(c_int64), POINTER(c_int)]),
     "hptb_collapse": (c_int, [POINTER(_T), c_int, POINTER(c_uint8), POINTER(HptbCollapsePlan)]),
     "hptb_binary": (c_int, [c_void_p, c_int, _T, _T, _T, c_void_p]),
+    "hptb_compare": (c_int, [c_void_p, c_int, _T, _T, _T, c_void_p]),
     "hptb_unary": (c_int, [c_void_p, c_int, _T, _T, c_double, c_double, c_void_p]),
     "hptb_reduce": (c_int, [c_void_p, c_int, _T, POINTER(c_int32), c_int, _T, c_int, c_void_p]),
     "hptb_mean_var": (c_int, [c_void_p, _T, POINTER(c_int32), c_int, _T, _T, c_void_p]),

@@ -27,12 +27,17 @@ HPTB_FOR_BINARY_OPS(XB)
 #define XU(NAME, E) HPTB_WEAK hptb::MapLauncher hptb_unary_##NAME(int);
 HPTB_FOR_UNARY_OPS(XU)
 #undef XU
+// NormalUaryOps: T → T for every dtype
+#define XU(NAME, E) HPTB_WEAK hptb::MapLauncher hptb_nunary_##NAME(int);
+HPTB_FOR_NORMAL_UNARY_OPS(XU)
+#undef XU
 HPTB_WEAK hptb::MapLauncher hptb_copy_same(int);
 // runtime-typed kernels, one set per OUTPUT dtype (mixed-dtype pairs, integer-input unary, astype, odd layouts)
 #define XD(T, N, E)                                      \
   HPTB_WEAK hptb::MapLauncher hptb_dyn_binary_##N(void); \
   HPTB_WEAK hptb::MapLauncher hptb_dyn_cast_##N(void);   \
-  HPTB_WEAK hptb::MapLauncher hptb_dyn_unary_##N(void);
+  HPTB_WEAK hptb::MapLauncher hptb_dyn_unary_##N(void);  \
+  HPTB_WEAK hptb::MapLauncher hptb_dyn_cmp_##N(void);
 HPTB_FOR_DTYPES(XD)
 #undef XD
 }
@@ -78,16 +83,20 @@ static Getter unary_getter(int op) {
   case E: return hptb_unary_##NAME;
     HPTB_FOR_UNARY_OPS(XU)
 #undef XU
+#define XU(NAME, E) \
+  case E: return hptb_nunary_##NAME;
+    HPTB_FOR_NORMAL_UNARY_OPS(XU)
+#undef XU
     default: return nullptr;
   }
 }
 
-enum DynKind { kDynBinary, kDynCast, kDynUnary };
+enum DynKind { kDynBinary, kDynCast, kDynUnary, kDynCmp };
 static MapLauncher dyn_launcher(DynKind kind, int out_dtype) {
   DynGetter g = nullptr;
   switch (out_dtype) {
 #define XD(T, N, E) \
-  case E: g = kind == kDynBinary ? hptb_dyn_binary_##N : kind == kDynCast ? hptb_dyn_cast_##N : hptb_dyn_unary_##N; break;
+  case E: g = kind == kDynBinary ? hptb_dyn_binary_##N : kind == kDynCast ? hptb_dyn_cast_##N : kind == kDynUnary ? hptb_dyn_unary_##N : hptb_dyn_cmp_##N; break;
     HPTB_FOR_DTYPES(XD)
 #undef XD
     default: break;
@@ -95,7 +104,11 @@ static MapLauncher dyn_launcher(DynKind kind, int out_dtype) {
   return g ? g() : nullptr;
 }
 
-static int binary_kind(int op) { return op == HPTB_DIV ? HPTB_PROMOTE_FLOAT_BINARY : HPTB_PROMOTE_NORMAL; }
+static int binary_kind(int op) {
+  return (op == HPTB_DIV || op == HPTB_POW || op == HPTB_HYPOT) ? HPTB_PROMOTE_FLOAT_BINARY : HPTB_PROMOTE_NORMAL;
+}
+static bool is_bit_op(int op) { return op >= HPTB_BITAND && op <= HPTB_SHR; }
+static bool is_int_or_bool(int dt) { return dt >= HPTB_BOOL && dt <= HPTB_U64; }
 
 // shared tail of every elementwise entry: broadcast inputs to out's shape, collapse, launch.  `fast` (may be
 // null) is the specialised same-dtype launcher; it may decline a layout (HPTB_FALLBACK), and `dyn` — the
@@ -139,12 +152,15 @@ int hptb_promote(int lhs, int rhs, int kind) { return promote(lhs, rhs, kind); }
 
 int hptb_binary_out_dtype(int op, int lhs, int rhs) {
   if (op < 0 || op >= HPTB_BINARY_COUNT) return -1;
+  if (is_bit_op(op) && !(is_int_or_bool(lhs) && is_int_or_bool(rhs))) return -1;  // BitWiseOut: integer / bool only
   int o = promote(lhs, rhs, binary_kind(op));
   if (o == HPTB_BOOL && (op == HPTB_SUB || op == HPTB_REM || op == HPTB_DIV)) return -1;  // _bool.rs:31-49 panics
   return o;
 }
 int hptb_unary_out_dtype(int op, int in) {
-  if (op < 0 || op >= HPTB_UNARY_COUNT) return -1;
+  if (op < 0 || op >= HPTB_UNARY_COUNT || !dtype_valid(in)) return -1;
+  if (op == HPTB_BITNOT) return is_int_or_bool(in) ? in : -1;
+  if (op >= HPTB_FLOAT_UNARY_COUNT) return in;  // NormalUaryOps: T → T
   return promote(in, in, HPTB_PROMOTE_FLOAT_UNARY);
 }
 
@@ -258,6 +274,25 @@ hptb_status hptb_binary(hptb_ctx* ctx, int op, const hptb_tensor* lhs, const hpt
   return run_map(ctx, fast, dyn_launcher(kDynBinary, odt), op, out, lhs, rhs, 0.0, 0.0, stream);
 }
 
+hptb_status hptb_compare(hptb_ctx* ctx, int op, const hptb_tensor* lhs, const hptb_tensor* rhs, hptb_tensor* out,
+                         void* stream) {
+  if (!ctx) return fail(HPTB_ERR_INVALID, "compare: null ctx");
+  if (op < 0 || op >= HPTB_CMP_COUNT) return fail(HPTB_ERR_INVALID, "compare: bad op %d", op);
+  HPTB_TRY(validate_tensor(lhs, "compare lhs"));
+  HPTB_TRY(validate_tensor(rhs, "compare rhs"));
+  HPTB_TRY(validate_tensor(out, "compare out"));
+  if (out->dtype != HPTB_BOOL) return fail(HPTB_ERR_DTYPE, "compare: out dtype is %s, expected bool", dtype_name(out->dtype));
+  const int pdt = promote(lhs->dtype, rhs->dtype, HPTB_PROMOTE_NORMAL);  // the type the comparison runs in
+  if (pdt < 0) return fail(HPTB_ERR_DTYPE, "compare: bad operand dtype");
+  int64_t bshape[HPTB_MAX_DIMS];
+  int bn = 0;
+  HPTB_TRY(broadcast_shape(lhs->shape, lhs->ndim, rhs->shape, rhs->ndim, bshape, &bn));
+  bool same = bn == out->ndim;
+  for (int i = 0; same && i < bn; ++i) same = bshape[i] == out->shape[i];
+  if (!same) return fail(HPTB_ERR_SHAPE, "compare: out shape does not equal the broadcast shape of the operands");
+  return run_map(ctx, nullptr, dyn_launcher(kDynCmp, pdt), op, out, lhs, rhs, 0.0, 0.0, stream);
+}
+
 hptb_status hptb_unary(hptb_ctx* ctx, int op, const hptb_tensor* in, hptb_tensor* out, double alpha, double beta,
                        void* stream) {
   if (!ctx) return fail(HPTB_ERR_INVALID, "unary: null ctx");
@@ -265,6 +300,8 @@ hptb_status hptb_unary(hptb_ctx* ctx, int op, const hptb_tensor* in, hptb_tensor
   HPTB_TRY(validate_tensor(in, "unary in"));
   HPTB_TRY(validate_tensor(out, "unary out"));
   int odt = hptb_unary_out_dtype(op, in->dtype);
+  if (odt < 0) return fail(HPTB_ERR_DTYPE, "unary op %d is not supported for %s", op, dtype_name(in->dtype));
+  if (op == HPTB_CLAMP && !(alpha <= beta)) return fail(HPTB_ERR_INVALID, "clamp: min must be <= max and neither may be NaN");
   if (out->dtype != odt)
     return fail(HPTB_ERR_DTYPE, "unary: out dtype is %s but %s promotes to %s", dtype_name(out->dtype), dtype_name(in->dtype),
                 dtype_name(odt));

@@ -23,6 +23,13 @@ HPTB_WEAK hptb::ReduceLauncher hptb_reduce_argmin(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_logsumexp(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_sum_square(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_prod(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_reducel1(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_nansum(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_nanprod(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_all(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_any(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_reducel2(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_reducel3(int);
 }
 
 namespace hptb {
@@ -94,6 +101,13 @@ static ReduceLauncher reduce_launcher(int op, int dt) {
     case HPTB_LOGSUMEXP: g = hptb_reduce_logsumexp; break;
     case HPTB_SUM_SQUARE: g = hptb_reduce_sum_square; break;
     case HPTB_PROD: g = hptb_reduce_prod; break;
+    case HPTB_REDUCEL1: g = hptb_reduce_reducel1; break;
+    case HPTB_NANSUM: g = hptb_reduce_nansum; break;
+    case HPTB_NANPROD: g = hptb_reduce_nanprod; break;
+    case HPTB_ALL: g = hptb_reduce_all; break;
+    case HPTB_ANY: g = hptb_reduce_any; break;
+    case HPTB_REDUCEL2: g = hptb_reduce_reducel2; break;
+    case HPTB_REDUCEL3: g = hptb_reduce_reducel3; break;
     default: break;
   }
   return g ? g(dt) : nullptr;
@@ -149,8 +163,10 @@ extern "C" {
 int hptb_reduce_out_dtype(int op, int in) {
   if (!dtype_valid(in)) return -1;
   switch (op) {
-    case HPTB_SUM: case HPTB_MAX: case HPTB_MIN: case HPTB_SUM_SQUARE: case HPTB_PROD: return in;
-    case HPTB_MEAN: case HPTB_LOGSUMEXP: return kFloatOutBinary[in][in];
+    case HPTB_SUM: case HPTB_MAX: case HPTB_MIN: case HPTB_SUM_SQUARE: case HPTB_PROD:
+    case HPTB_REDUCEL1: case HPTB_NANSUM: case HPTB_NANPROD: return in;
+    case HPTB_ALL: case HPTB_ANY: return HPTB_BOOL;
+    case HPTB_MEAN: case HPTB_LOGSUMEXP: case HPTB_REDUCEL2: case HPTB_REDUCEL3: return kFloatOutBinary[in][in];
     case HPTB_ARGMAX: case HPTB_ARGMIN: return HPTB_I64;
     default: return -1;
   }

@@ -165,14 +165,17 @@ hptb_status hptb_shard_plan_reduce(int op, const int32_t* axes, int naxes, int s
   for (int i = 0; i < naxes; ++i) plan->crosses |= axes[i] == shard_axis;
   if (!plan->crosses || world <= 1) return HPTB_OK;
   switch (op) {
-    case HPTB_SUM: case HPTB_SUM_SQUARE: plan->collective = HPTB_COLL_ALLREDUCE_SUM; break;
+    case HPTB_SUM: case HPTB_SUM_SQUARE: case HPTB_REDUCEL1: case HPTB_NANSUM: plan->collective = HPTB_COLL_ALLREDUCE_SUM; break;
+    case HPTB_NANPROD: plan->collective = HPTB_COLL_ALLREDUCE_PROD; break;
+    case HPTB_ANY: plan->collective = HPTB_COLL_ALLREDUCE_MAX; break;  // OR of 0/1 bytes
+    case HPTB_ALL: plan->collective = HPTB_COLL_ALLREDUCE_MIN; break;  // AND of 0/1 bytes
     case HPTB_MEAN: plan->collective = HPTB_COLL_ALLREDUCE_SUM; plan->global_count = 1; break;
     case HPTB_LOGSUMEXP: plan->collective = HPTB_COLL_ALLREDUCE_SUM; plan->pre_exp = 1; plan->post_ln = 1; break;
     case HPTB_PROD: plan->collective = HPTB_COLL_ALLREDUCE_PROD; break;
     case HPTB_MAX: plan->collective = HPTB_COLL_ALLREDUCE_MAX; break;
     case HPTB_MIN: plan->collective = HPTB_COLL_ALLREDUCE_MIN; break;
     case HPTB_ARGMAX: case HPTB_ARGMIN: plan->collective = HPTB_COLL_ALLGATHER_ARG; break;
-    default: return fail(HPTB_ERR_INVALID, "shard_plan_reduce: op %d has no sharded form", op);
+    default: return fail(HPTB_ERR_UNSUPPORTED, "shard_plan_reduce: op %d across the shard axis is not implemented (reduce locally and combine)", op);
   }
   return HPTB_OK;
 }
@@ -185,10 +188,11 @@ hptb_status hptb_allreduce(hptb_comm* comm, int op, hptb_tensor* t, void* stream
   if (ndt < 0) return fail(HPTB_ERR_DTYPE, "allreduce: NCCL has no type for %s", dtype_name(t->dtype));
   int nop;
   switch (op) {
-    case HPTB_SUM: case HPTB_SUM_SQUARE: case HPTB_MEAN: nop = t->dtype == HPTB_BOOL ? ncclMax : ncclSum; break;  // bool add = OR
-    case HPTB_PROD: nop = t->dtype == HPTB_BOOL ? ncclMin : ncclProd; break;                                     // bool mul = AND
-    case HPTB_MAX: nop = ncclMax; break;
-    case HPTB_MIN: nop = ncclMin; break;
+    case HPTB_SUM: case HPTB_SUM_SQUARE: case HPTB_MEAN: case HPTB_REDUCEL1: case HPTB_NANSUM:
+      nop = t->dtype == HPTB_BOOL ? ncclMax : ncclSum; break;  // bool add = OR
+    case HPTB_PROD: case HPTB_NANPROD: nop = t->dtype == HPTB_BOOL ? ncclMin : ncclProd; break;  // bool mul = AND
+    case HPTB_MAX: case HPTB_ANY: nop = ncclMax; break;
+    case HPTB_MIN: case HPTB_ALL: nop = ncclMin; break;
     default: return fail(HPTB_ERR_INVALID, "allreduce: op %d has no collective form", op);
   }
   if (comm->nranks == 1) return HPTB_OK;

@@ -13,7 +13,7 @@
 #define HPTB_FOR_BINARY_OPS(X)                                                       \
   X(OpAdd, add, HPTB_ADD, 0, 1) X(OpSub, sub, HPTB_SUB, 0, 0) X(OpMul, mul, HPTB_MUL, 0, 1) \
   X(OpRem, rem, HPTB_REM, 0, 0) X(OpDiv, div, HPTB_DIV, 1, 0) X(OpMax, maximum, HPTB_MAXIMUM, 0, 1) \
-  X(OpMin, minimum, HPTB_MINIMUM, 0, 1)
+  X(OpMin, minimum, HPTB_MINIMUM, 0, 1) X(OpPow, pow, HPTB_POW, 1, 0) X(OpHypot, hypot, HPTB_HYPOT, 1, 0)
 
 // unary ops: X(name, enum)
 #define HPTB_FOR_UNARY_OPS(X)                                                                  \
@@ -25,3 +25,9 @@
   X(sigmoid, HPTB_SIGMOID) X(gelu, HPTB_GELU) X(selu, HPTB_SELU) X(elu, HPTB_ELU)              \
   X(celu, HPTB_CELU) X(mish, HPTB_MISH) X(softplus, HPTB_SOFTPLUS) X(softsign, HPTB_SOFTSIGN)  \
   X(hard_sigmoid, HPTB_HARD_SIGMOID) X(hard_swish, HPTB_HARD_SWISH)
+
+// NormalUaryOps (+ BITNOT): X(name, enum) — out dtype = in dtype
+#define HPTB_FOR_NORMAL_UNARY_OPS(X)                                                                   \
+  X(floor, HPTB_FLOOR) X(ceil, HPTB_CEIL) X(round, HPTB_ROUND) X(trunc, HPTB_TRUNC) X(abs, HPTB_ABS)    \
+  X(neg, HPTB_NEG) X(sign, HPTB_SIGN) X(square, HPTB_SQUARE) X(relu, HPTB_RELU) X(relu6, HPTB_RELU6)    \
+  X(leaky_relu, HPTB_LEAKY_RELU) X(clamp, HPTB_CLAMP) X(bitnot, HPTB_BITNOT)

@@ -118,27 +118,53 @@ struct DynBinaryFn {
       case HPTB_REM: r = OpRem::apply<C>(ca, cb); break;
       case HPTB_DIV: r = OpDiv::apply<C>(ca, cb); break;
       case HPTB_MAXIMUM: r = OpMax::apply<C>(ca, cb); break;
-      default: r = OpMin::apply<C>(ca, cb); break;
+      case HPTB_MINIMUM: r = OpMin::apply<C>(ca, cb); break;
+      case HPTB_POW: r = OpPow::apply<C>(ca, cb); break;      // float outputs only (host-checked)
+      case HPTB_HYPOT: r = OpHypot::apply<C>(ca, cb); break;
+      case HPTB_BITAND: r = OpBitAnd::apply<C>(ca, cb); break;  // bool / integer outputs only
+      case HPTB_BITOR: r = OpBitOr::apply<C>(ca, cb); break;
+      case HPTB_BITXOR: r = OpBitXor::apply<C>(ca, cb); break;
+      case HPTB_SHL: r = OpShl::apply<C>(ca, cb); break;
+      default: r = OpShr::apply<C>(ca, cb); break;
     }
     return from_compute<O>(r);
   }
 };
 
+// scalar parameter of a unary op in the compute type (integers: Rust `as` from f64; bool: != 0)
+template <typename C>
+__device__ __forceinline__ C dyn_param(double v) {
+  if constexpr (is_bool_t<C>::value) return b8{(uint8_t)(v != 0.0)};
+  else if constexpr (std::is_integral<C>::value) return float_to_int_sat<C, double>(v);
+  else return (C)v;
+}
+
 template <typename O>
 struct DynUnaryFn {
   typedef compute_t<O> C;
   static __device__ __forceinline__ O apply(O a, O, const DynExtra& x) {
-    const C c = to_compute<O>(a), al = (C)x.alpha, be = (C)x.beta;
-    C r;
-    switch (x.op) {
+    const C c = to_compute<O>(a), al = dyn_param<C>(x.alpha), be = dyn_param<C>(x.beta);
+    if (x.op >= HPTB_FLOAT_UNARY_COUNT) return from_compute<O>(normal_unary<C>(x.op, c, al, be));
+    if constexpr (std::is_floating_point<C>::value) {
+      C r;
+      switch (x.op) {
 #define XU(NAME, E) \
   case E: r = UnaryOp<E>::apply(c, al, be); break;
-      HPTB_FOR_UNARY_OPS(XU)
+        HPTB_FOR_UNARY_OPS(XU)
 #undef XU
-      default: r = c; break;
+        default: r = c; break;
+      }
+      return from_compute<O>(r);
+    } else {
+      return a;  // FloatUnaryOps never produce an integer output (host-checked)
     }
-    return from_compute<O>(r);
   }
+};
+
+// TensorCmp: the kernel is specialised on the PROMOTED type P (both inputs are cast to it), stores bool
+template <typename P>
+struct DynCmpFn {
+  static __device__ __forceinline__ b8 apply(P a, P b, const DynExtra& x) { return cmp_apply<P>(x.op, a, b); }
 };
 
 template <typename O>
@@ -147,9 +173,10 @@ struct DynCastFn {
 };
 
 // ---- kernel ------------------------------------------------------------------------------------------------
-template <int NIN, int VEC, int UNROLL, int MAXB, typename Fn, typename O>
+// O = the type both inputs are converted to and the operator runs in; S = the stored type (O, or bool for compares)
+template <int NIN, int VEC, int UNROLL, int MAXB, typename Fn, typename O, typename S = O>
 __global__ void __launch_bounds__(kMapThreads)
-map_dyn_kernel(O* __restrict__ out, const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, RowsParams p,
+map_dyn_kernel(S* __restrict__ out, const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, RowsParams p,
                DynExtra x) {
   pdl_prologue();
   const int64_t c0 = (int64_t)blockIdx.x * (kMapThreads * UNROLL) + threadIdx.x;
@@ -232,10 +259,10 @@ map_dyn_kernel(O* __restrict__ out, const unsigned char* __restrict__ a, const u
         for (int k = 1; k < VEC; ++k) vb[u][k] = vb[u][0];
       }
     }
-    Pack<O, VEC> po;
+    Pack<S, VEC> po;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) po.v[k] = Fn::apply(va[u][k], NIN == 2 ? vb[u][k] : va[u][k], x);
-    if (cnt[u] == VEC) store_pack<O, VEC>(out + oo[u], po);
+    if (cnt[u] == VEC) store_pack<S, VEC>(out + oo[u], po);
     else {
 #pragma unroll
       for (int k = 0; k < VEC; ++k)
@@ -253,17 +280,17 @@ constexpr int dyn_vec_width() {
 
 // MAXB = the widest input element the launcher can be handed: 8 for casts; for binary / unary outputs the
 // promotion tables never pair a narrower Output with an 8-byte input (but i32/u32 ⊕ f16 → f16 is a 4-byte input)
-template <int NIN, int MAXB, typename Fn, typename O>
+template <int NIN, int MAXB, typename Fn, typename O, typename S = O>
 hptb_status launch_map_dyn(const MapPlan& plan, cudaStream_t stream) {
   const Collapsed& c = plan.c;
   if (c.numel == 0) return HPTB_OK;
-  O* out = static_cast<O*>(plan.ptr[0]);
+  S* out = static_cast<S*>(plan.ptr[0]);
   const unsigned char* a = static_cast<const unsigned char*>(plan.ptr[1]);
   const unsigned char* b = NIN == 2 ? static_cast<const unsigned char*>(plan.ptr[2]) : a;
   constexpr int VEC = dyn_vec_width<O>();
   DynExtra x;
   memset(&x, 0, sizeof(x));
-  size_t esz[3] = {sizeof(O), 1, 1};
+  size_t esz[3] = {sizeof(S), 1, 1};
   for (int i = 0; i < NIN; ++i) {
     if (!dtype_valid(plan.in_dtype[i])) return fail(HPTB_ERR_INVALID, "elementwise: bad input dtype");
     x.dtype[i] = plan.in_dtype[i];
@@ -316,8 +343,8 @@ hptb_status launch_map_dyn(const MapPlan& plan, cudaStream_t stream) {
   constexpr int UNROLL = 4;
   int64_t blocks = (p.total_chunks + kMapThreads * UNROLL - 1) / (kMapThreads * UNROLL);
   if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "elementwise: tensor too large for one launch");
-  if (vec_ok) HPTB_CUDA_CHECK(launch_kernel(map_dyn_kernel<NIN, VEC, UNROLL, MAXB, Fn, O>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, x));
-  else HPTB_CUDA_CHECK(launch_kernel(map_dyn_kernel<NIN, 1, UNROLL, MAXB, Fn, O>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, x));
+  if (vec_ok) HPTB_CUDA_CHECK(launch_kernel(map_dyn_kernel<NIN, VEC, UNROLL, MAXB, Fn, O, S>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, x));
+  else HPTB_CUDA_CHECK(launch_kernel(map_dyn_kernel<NIN, 1, UNROLL, MAXB, Fn, O, S>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, x));
   return HPTB_OK;
 }
 

@@ -144,6 +144,109 @@ template <typename T> struct ReduceOp<HPTB_SUM_SQUARE, T> : PlainLocal<ReduceOp<
   static __device__ __forceinline__ Out post(Acc a, double) { return from_compute<T>(a); }
   static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
 };
+// |x| in the compute type: wrapping for signed integers, identity for unsigned / bool (impls.rs:77-80,185-196)
+template <typename C> __device__ __forceinline__ C red_abs(C a) {
+  if constexpr (is_bool_t<C>::value) return a;
+  else if constexpr (std::is_integral<C>::value) {
+    if constexpr (std::is_signed<C>::value) {
+      typedef typename std::make_unsigned<C>::type U;
+      return a < 0 ? (C)(U)((U)0 - (U)a) : a;
+    } else return a;
+  } else if constexpr (std::is_same<C, float>::value) return fabsf(a);
+  else return fabs(a);
+}
+template <typename C> __device__ __forceinline__ bool red_isnan(C a) {
+  if constexpr (std::is_floating_point<C>::value) return a != a;
+  else return false;
+}
+// REDUCEL1: Σ|x| in T (common_reduce.rs:147-167)
+template <typename T> struct ReduceOp<HPTB_REDUCEL1, T> : PlainLocal<ReduceOp<HPTB_REDUCEL1, T>, T, compute_t<T>> {
+  typedef T Out;
+  typedef compute_t<T> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return red_zero<Acc>(); }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { return red_abs<Acc>(to_compute<T>(x)); }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return red_add<Acc>(a, b); }
+  static __device__ __forceinline__ Out post(Acc a, double) { return from_compute<T>(a); }
+  static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
+};
+// NANSUM / NANPROD: NaN counts as 0 / 1 (common_reduce.rs:255-324)
+template <typename T> struct ReduceOp<HPTB_NANSUM, T> : PlainLocal<ReduceOp<HPTB_NANSUM, T>, T, compute_t<T>> {
+  typedef T Out;
+  typedef compute_t<T> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return red_zero<Acc>(); }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { const Acc c = to_compute<T>(x); return red_isnan<Acc>(c) ? red_zero<Acc>() : c; }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return red_add<Acc>(a, b); }
+  static __device__ __forceinline__ Out post(Acc a, double) { return from_compute<T>(a); }
+  static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
+};
+template <typename T> struct ReduceOp<HPTB_NANPROD, T> : PlainLocal<ReduceOp<HPTB_NANPROD, T>, T, compute_t<T>> {
+  typedef T Out;
+  typedef compute_t<T> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return red_one<Acc>(); }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { const Acc c = to_compute<T>(x); return red_isnan<Acc>(c) ? red_one<Acc>() : c; }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return red_mul<Acc>(a, b); }
+  static __device__ __forceinline__ Out post(Acc a, double) { return from_compute<T>(a); }
+  static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<T>(o); }
+};
+// ALL / ANY: AND / OR of `x != 0` (NaN is true), bool output (common_reduce.rs:200-242)
+template <typename T> struct ReduceOp<HPTB_ALL, T> : PlainLocal<ReduceOp<HPTB_ALL, T>, T, b8> {
+  typedef b8 Out;
+  typedef b8 Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return b8{1}; }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { return cast<b8>(x); }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return b8{(uint8_t)(a.v & b.v)}; }
+  static __device__ __forceinline__ Out post(Acc a, double) { return a; }
+  static __device__ __forceinline__ Acc from_out(Out o) { return b8{(uint8_t)(o.v != 0)}; }
+};
+template <typename T> struct ReduceOp<HPTB_ANY, T> : PlainLocal<ReduceOp<HPTB_ANY, T>, T, b8> {
+  typedef b8 Out;
+  typedef b8 Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return b8{0}; }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { return cast<b8>(x); }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return b8{(uint8_t)(a.v | b.v)}; }
+  static __device__ __forceinline__ Out post(Acc a, double) { return a; }
+  static __device__ __forceinline__ Acc from_out(Out o) { return b8{(uint8_t)(o.v != 0)}; }
+};
+// REDUCEL2 = sqrt Σ x², REDUCEL3 = (Σ |x|³)^(1/3), in FloatOutBinaryPromote<T,T> (common_reduce.rs:384-450; the
+// exponent 1/3 is rounded to the output dtype first, as the reference's `(1.0 / 3.0).cast()` does)
+template <typename T> struct ReduceOp<HPTB_REDUCEL2, T>
+    : PlainLocal<ReduceOp<HPTB_REDUCEL2, T>, T, compute_t<typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type>> {
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type Out;
+  typedef compute_t<Out> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return (Acc)0; }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) { const Acc c = to_compute<Out>(cast<Out>(x)); return c * c; }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return a + b; }
+  static __device__ __forceinline__ Out post(Acc a, double) {
+    if constexpr (std::is_same<Acc, float>::value) return from_compute<Out>(sqrtf(a));
+    else return from_compute<Out>(sqrt(a));
+  }
+  static __device__ __forceinline__ Acc from_out(Out o) { const Acc c = to_compute<Out>(o); return c * c; }
+};
+template <typename T> struct ReduceOp<HPTB_REDUCEL3, T>
+    : PlainLocal<ReduceOp<HPTB_REDUCEL3, T>, T, compute_t<typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type>> {
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type Out;
+  typedef compute_t<Out> Acc;
+  static constexpr bool kIndexed = false;
+  static __device__ __forceinline__ Acc identity() { return (Acc)0; }
+  static __device__ __forceinline__ Acc pre(T x, int64_t) {
+    const T ax = from_compute<T>(red_abs<compute_t<T>>(to_compute<T>(x)));  // |x| in T (wraps for the integer minimum), then cast
+    const Acc c = to_compute<Out>(cast<Out>(ax));
+    return c * c * c;
+  }
+  static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return a + b; }
+  static __device__ __forceinline__ Out post(Acc a, double) {
+    const Acc third = to_compute<Out>(cast<Out>(1.0 / 3.0));
+    if constexpr (std::is_same<Acc, float>::value) return from_compute<Out>((float)pow((double)a, (double)third));
+    else return from_compute<Out>(pow(a, third));
+  }
+  static __device__ __forceinline__ Acc from_out(Out o) { const Acc c = to_compute<Out>(o); return c * c * c; }
+};
 // MAX / MIN: common_reduce.rs:101-168 (identity NEG_INF / INF; f32::max/min ignore NaN)
 template <typename T> struct ReduceOp<HPTB_MAX, T> : PlainLocal<ReduceOp<HPTB_MAX, T>, T, compute_t<T>> {
   typedef T Out;

@@ -339,11 +339,46 @@ class Tensor:
     def __truediv__(self, rhs): return self._binary("div", rhs)
     def maximum(self, rhs): return self._binary("maximum", rhs)
     def minimum(self, rhs): return self._binary("minimum", rhs)
+    # FloatBinOps (hpt-traits/src/ops/binary.rs:94-188)
+    def pow(self, rhs): return self._binary("pow", rhs)
+    def pow_(self, rhs, out, stream=None): return self._binary("pow", rhs, out, stream)
+    def hypot(self, rhs): return self._binary("hypot", rhs)
+    def hypot_(self, rhs, out, stream=None): return self._binary("hypot", rhs, out, stream)
+    # BitWiseOut / std::ops::{BitAnd, BitOr, BitXor, Shl, Shr, Not} (hpt/src/backends/cuda/std_ops.rs)
+    def __and__(self, rhs): return self._binary("bitand", rhs)
+    def __or__(self, rhs): return self._binary("bitor", rhs)
+    def __xor__(self, rhs): return self._binary("bitxor", rhs)
+    def __lshift__(self, rhs): return self._binary("shl", rhs)
+    def __rshift__(self, rhs): return self._binary("shr", rhs)
+    def __invert__(self): return self._unary("bitnot")
+    def __neg__(self): return self._unary("neg")
+
+    # ---- TensorCmp (hpt/src/backends/cuda/tensor_external/cmp.rs) ------------------------------------------
+    def _compare(self, name, rhs, stream=None):
+        op = _ffi.CMP_OPS[name]
+        if not isinstance(rhs, Tensor):
+            raise HptError(4, "tensor_<cmp> takes a tensor on the right-hand side")
+        bshape = (c_int64 * _ffi.MAX_DIMS)()
+        bn = c_int()
+        check(lib.hptb_broadcast_shape((c_int64 * max(self.ndim, 1))(*self.shape), self.ndim,
+                                       (c_int64 * max(rhs.ndim, 1))(*rhs.shape), rhs.ndim, bshape, byref(bn)))
+        out = Tensor.empty(tuple(bshape[i] for i in range(bn.value)), _ffi.BOOL, self.ctx.device, stream)
+        check(lib.hptb_compare(self.ctx.handle, op, byref(self._c()), byref(rhs._c()), byref(out._c()), _s(stream)))
+        return out
+
+    def tensor_eq(self, rhs): return self._compare("eq", rhs)
+    def tensor_neq(self, rhs): return self._compare("ne", rhs)
+    def tensor_lt(self, rhs): return self._compare("lt", rhs)
+    def tensor_le(self, rhs): return self._compare("le", rhs)
+    def tensor_gt(self, rhs): return self._compare("gt", rhs)
+    def tensor_ge(self, rhs): return self._compare("ge", rhs)
 
     # ---- FloatUnaryOps (hpt/src/backends/cuda/tensor_internal/float_out_unary.rs) ---------------------
     def _unary(self, name, out=None, alpha=0.0, beta=0.0, stream=None):
         op = _ffi.UNARY_OPS[name]
         odt = lib.hptb_unary_out_dtype(op, self.dtype)
+        if odt < 0:
+            raise HptError(2, f"{name} is not supported for {_ffi.DTYPE_NAMES[self.dtype]}")
         if out is None:
             out = Tensor.empty(self.shape, odt, self.ctx.device, stream)
         check(lib.hptb_unary(self.ctx.handle, op, byref(self._c()), byref(out._c()), float(alpha), float(beta), _s(stream)))
@@ -354,6 +389,9 @@ class Tensor:
         return self._unary("selu", out, 1.6732632423543772848170429916717, 1.0507009873554804934193349852946, stream)
 
     def elu(self, alpha, out=None, stream=None): return self._unary("elu", out, alpha, 0.0, stream)
+    # NormalUaryOps with parameters (hpt-traits/src/ops/unary.rs:720-826)
+    def leaky_relu(self, alpha, out=None, stream=None): return self._unary("leaky_relu", out, alpha, 0.0, stream)
+    def clamp(self, min, max, out=None, stream=None): return self._unary("clamp", out, min, max, stream)
     def celu(self, alpha, out=None, stream=None): return self._unary("celu", out, alpha, 0.0, stream)
 
     # ---- reductions (hpt/src/backends/cuda/tensor_internal/{common_reduce,arg_reduce}.rs) ---------------
@@ -396,6 +434,14 @@ class Tensor:
     def argmin(self, axis, keep_dims=False): return self._reduce("argmin", axis, keep_dims)
     def logsumexp(self, axes, keep_dims=False): return self._reduce("logsumexp", axes, keep_dims)
     def sum_square(self, axes, keep_dims=False): return self._reduce("sum_square", axes, keep_dims)
+    def reducel1(self, axes, keep_dims=False): return self._reduce("reducel1", axes, keep_dims)
+    def reducel2(self, axes, keep_dims=False): return self._reduce("reducel2", axes, keep_dims)
+    def reducel3(self, axes, keep_dims=False): return self._reduce("reducel3", axes, keep_dims)
+    def nansum(self, axes, keep_dims=False): return self._reduce("nansum", axes, keep_dims)
+    def nansum_(self, axes, keep_dims, init_out, out): return self._reduce("nansum", axes, keep_dims, init_out, out)
+    def nanprod(self, axes, keep_dims=False): return self._reduce("nanprod", axes, keep_dims)
+    def all(self, axes, keep_dims=False): return self._reduce("all", axes, keep_dims)
+    def any(self, axes, keep_dims=False): return self._reduce("any", axes, keep_dims)
 
     def mean_var(self, axes, stream=None):
         """Extension (Hpt has no `var`): fused single-read population mean and variance."""
@@ -436,6 +482,6 @@ def _make_unary(name):
 
 
 for _n in _ffi.UNARY_OPS:
-    if _n not in ("selu", "elu", "celu"):
+    if _n not in ("selu", "elu", "celu", "leaky_relu", "clamp", "bitnot"):
         setattr(Tensor, _n, _make_unary(_n))
         setattr(Tensor, _n + "_", lambda self, out, _n=_n: self._unary(_n, out))

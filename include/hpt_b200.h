@@ -72,11 +72,23 @@ typedef struct {
  * (hpt-cudakernels/src/binary/binary_template.cuh:107-138) called from binary_fn_precompiled
  * (hpt/src/backends/cuda/utils/binary/binary_normal.rs:371-544).  Output dtype NormalOutPromote<L,R>.
  * DIV is FloatBinOps::div_ (hpt-traits/src/ops/binary.rs:149), output FloatOutBinaryPromote<L,R>.
- * MAX/MIN are NormalOut::_max/_min (hpt-macros/src/normal_out.rs:121-133). */
+ * MAX/MIN are NormalOut::_max/_min (hpt-macros/src/normal_out.rs:121-133).
+ * POW/HYPOT are FloatBinOps::{pow,hypot} (hpt-traits/src/ops/binary.rs:114-183), output FloatOutBinaryPromote<L,R>.
+ * BITAND..SHR are BitWiseOut (hpt-macros/src/lib.rs:384-480): bool and integer dtypes only, both sides cast to
+ * NormalOutPromote<L,R>, shifts wrap the count to the bit width (wrapping_shl/shr, hpt-types/src/scalars/impls.rs:155-162). */
 typedef enum {
   HPTB_ADD = 0, HPTB_SUB = 1, HPTB_MUL = 2, HPTB_REM = 3, HPTB_DIV = 4, HPTB_MAXIMUM = 5, HPTB_MINIMUM = 6,
-  HPTB_BINARY_COUNT = 7
+  HPTB_POW = 7, HPTB_HYPOT = 8,
+  HPTB_BITAND = 9, HPTB_BITOR = 10, HPTB_BITXOR = 11, HPTB_SHL = 12, HPTB_SHR = 13,
+  HPTB_BINARY_COUNT = 14
 } hptb_binary_op;
+
+/* TensorCmp (hpt-traits/src/ops/cmp.rs; device: hpt-cudakernels/src/binary/cmp.cu): both sides are cast to
+ * NormalOutPromote<L,R> and compared there (hpt-macros/src/lib.rs:570-650); the output is bool. */
+typedef enum {
+  HPTB_EQ = 0, HPTB_NE = 1, HPTB_LT = 2, HPTB_LE = 3, HPTB_GT = 4, HPTB_GE = 5,
+  HPTB_CMP_COUNT = 6
+} hptb_cmp_op;
 
 /* FloatUnaryOps (hpt-traits/src/ops/unary.rs:8-608); replaces `<op>_<T>_{contiguous,uncontiguous}`
  * (hpt-cudakernels/src/unary/unary_template.cuh:65-75) called from uary_fn_precompiled
@@ -88,18 +100,30 @@ typedef enum {
   HPTB_SQRT, HPTB_CBRT, HPTB_RECIP, HPTB_ERF,
   HPTB_SIGMOID, HPTB_GELU, HPTB_SELU /* alpha, beta=scale */, HPTB_ELU /* alpha */, HPTB_CELU /* alpha */,
   HPTB_MISH, HPTB_SOFTPLUS, HPTB_SOFTSIGN, HPTB_HARD_SIGMOID, HPTB_HARD_SWISH,
+  /* NormalUaryOps (hpt-traits/src/ops/unary.rs:611-836; scalar semantics hpt-types/src/scalars/{_f32,impls,_bool}.rs
+   * NormalOutUnary2): output dtype = input dtype, every dtype.  LEAKY_RELU takes alpha; CLAMP takes alpha = min,
+   * beta = max (doubles: integer bounds beyond 2^53 are not representable).  BITNOT is BitWiseOut::_not (bool and
+   * integer dtypes only). */
+  HPTB_FLOOR, HPTB_CEIL, HPTB_ROUND, HPTB_TRUNC, HPTB_ABS, HPTB_NEG, HPTB_SIGN, HPTB_SQUARE,
+  HPTB_RELU, HPTB_RELU6, HPTB_LEAKY_RELU, HPTB_CLAMP, HPTB_BITNOT,
   HPTB_UNARY_COUNT
 } hptb_unary_op;
+#define HPTB_FLOAT_UNARY_COUNT HPTB_FLOOR /* ops below this value promote with FloatOutUnaryPromote */
 
 /* Reductions: NormalReduce / FloatReduce / IndexReduce (hpt-traits/src/ops/reduce.rs:6-358); replaces
  * the 8-kernel-per-op families of hpt-cudakernels/src/reduce/declare_macros.cuh:48-326 chosen by
  * hpt/src/backends/cuda/utils/reduce/reduce.rs:62-838.
  * Output dtypes: SUM/MAX/MIN/PROD/SUM_SQUARE = T; MEAN/LOGSUMEXP = FloatOutBinaryPromote<T,T>;
- * ARGMAX/ARGMIN = i64 (exactly one axis). */
+ * ARGMAX/ARGMIN = i64 (exactly one axis).
+ * REDUCEL1 = Σ|x| (T); NANSUM / NANPROD treat NaN as 0 / 1 (T); ALL / ANY = bool (x != 0; NaN is true);
+ * REDUCEL2 = sqrt Σ x², REDUCEL3 = (Σ |x|³)^(1/3), both FloatOutBinaryPromote<T,T>
+ * (hpt/src/backends/cpu/tensor_internal/common_reduce.rs:147-167,200-324,384-450). */
 typedef enum {
   HPTB_SUM = 0, HPTB_MEAN = 1, HPTB_MAX = 2, HPTB_MIN = 3, HPTB_ARGMAX = 4, HPTB_ARGMIN = 5,
   HPTB_LOGSUMEXP = 6, HPTB_SUM_SQUARE = 7, HPTB_PROD = 8,
-  HPTB_REDUCE_COUNT = 9
+  HPTB_REDUCEL1 = 9, HPTB_NANSUM = 10, HPTB_NANPROD = 11, HPTB_ALL = 12, HPTB_ANY = 13,
+  HPTB_REDUCEL2 = 14, HPTB_REDUCEL3 = 15,
+  HPTB_REDUCE_COUNT = 16
 } hptb_reduce_op;
 
 typedef enum {
@@ -188,7 +212,10 @@ hptb_status hptb_collapse(const hptb_tensor* const* operands, int n_operands, co
  * hptb_binary_out_dtype(op, lhs, rhs) and `out->shape` the broadcast shape; any strides. */
 hptb_status hptb_binary(hptb_ctx* ctx, int op, const hptb_tensor* lhs, const hptb_tensor* rhs,
                         hptb_tensor* out, void* stream);
-/* out = op(cast(in)); alpha/beta only for ELU/CELU (alpha) and SELU (alpha, scale). */
+/* out = lhs <op> rhs (hptb_cmp_op) with numpy broadcasting; `out` is bool with the broadcast shape. */
+hptb_status hptb_compare(hptb_ctx* ctx, int op, const hptb_tensor* lhs, const hptb_tensor* rhs,
+                         hptb_tensor* out, void* stream);
+/* out = op(cast(in)); alpha/beta only for ELU/CELU/LEAKY_RELU (alpha), SELU (alpha, scale), CLAMP (min, max). */
 hptb_status hptb_unary(hptb_ctx* ctx, int op, const hptb_tensor* in, hptb_tensor* out,
                        double alpha, double beta, void* stream);
 /* Reduce `in` over `axes` (already normalised, unique).  `out` has the keep_dims=false shape

@@ -14,6 +14,10 @@ What it restates (paths relative to the Hpt repository):
                  hpt-types/src/scalars/_bf16.rs:28-66                  (half types: f32 arithmetic, one rounding)
   broadcasting   hpt-common/src/shape/shape_utils.rs:370-400
   unary ops      hpt-types/src/scalars/_f32.rs:182-330                 (std / libm formulas)
+  normal unary   hpt-types/src/scalars/_f32.rs:70-130, impls.rs:71-131, _bool.rs (NormalOutUnary2: T → T)
+  pow / hypot    hpt-types/src/scalars/_f32.rs:14-20                   (f32::powf / hypot in FloatOutBinaryPromote)
+  bit ops        hpt-macros/src/lib.rs:384-480, impls.rs:133-163       (cast to NormalOutPromote; wrapping shifts)
+  compares       hpt-macros/src/lib.rs:570-650                         (cast to NormalOutPromote, compare, bool)
   reductions     hpt/src/backends/cpu/tensor_internal/common_reduce.rs:32-168, :352-380, :451-480
   argmax/argmin  hpt/src/backends/cpu/kernels/argreduce_kernels.rs:13-21,49-57
   softmax        hpt/src/backends/cpu/kernels/softmax.rs:204-310
@@ -174,8 +178,14 @@ def from_compute(x, d):
 
 
 # ---- binary -----------------------------------------------------------------------------------------
+BIT_OPS = ("bitand", "bitor", "bitxor", "shl", "shr")
+CMP_OPS = ("eq", "ne", "lt", "le", "gt", "ge")
+
+
 def binary_out_dtype(op, a, b):
-    o = float_out_binary(a, b) if op == "div" else normal_out(a, b)
+    if op in BIT_OPS and not (a in INTS + ("bool",) and b in INTS + ("bool",)):
+        return None
+    o = float_out_binary(a, b) if op in ("div", "pow", "hypot") else normal_out(a, b)
     if o == "bool" and op in ("sub", "rem", "div"):
         return None
     return o
@@ -205,7 +215,8 @@ def binary(op, x, xd, y, yd):
     b = to_compute(cast(y, yd, od), od)
     a, b = np.broadcast_arrays(a, b)
     if od == "bool":
-        r = {"add": a | b, "mul": a & b, "maximum": a | b, "minimum": a & b}[op]
+        r = {"add": a | b, "mul": a & b, "maximum": a | b, "minimum": a & b, "bitand": a & b, "bitor": a | b,
+             "bitxor": a ^ b, "shl": a, "shr": a}[op]  # _bool.rs:133-163: shifts leave a bool unchanged
         return r, od
     with np.errstate(all="ignore"):
         if od in INTS:
@@ -221,6 +232,18 @@ def binary(op, x, xd, y, yd):
                 r = np.maximum(a, b)
             elif op == "minimum":
                 r = np.minimum(a, b)
+            elif op == "bitand":
+                r = a & b
+            elif op == "bitor":
+                r = a | b
+            elif op == "bitxor":
+                r = a ^ b
+            elif op in ("shl", "shr"):
+                # wrapping_shl / wrapping_shr of `rhs as u32`: the count is taken modulo the bit width
+                bits = np.dtype(NP[od]).itemsize * 8
+                n = (b.astype(np.int64) if b.dtype != np.uint64 else b).astype(np.uint64) & np.uint64(bits - 1)
+                n = n.astype(NP[od])
+                r = np.left_shift(a, n) if op == "shl" else np.right_shift(a, n)  # >> is arithmetic for signed
             else:
                 raise ValueError(op)
             return r.astype(NP[od]), od
@@ -238,9 +261,100 @@ def binary(op, x, xd, y, yd):
             r = np.fmax(a, b)  # f32::max ignores NaN
         elif op == "minimum":
             r = np.fmin(a, b)
+        elif op in ("pow", "hypot"):
+            # correctly rounded value: evaluated in f64, rounded once (the device is allowed 2 ulp around it)
+            a64, b64 = a.astype(np.float64), b.astype(np.float64)
+            r = np.power(a64, b64) if op == "pow" else np.hypot(a64, b64)
+            if od != "f64":
+                r = r.astype(np.float32)
         else:
             raise ValueError(op)
     return from_compute(r, od), od
+
+
+def compare(op, x, xd, y, yd):
+    """TensorCmp: cast both sides to NormalOutPromote<L,R>, compare there; bool result (NaN is unordered)."""
+    pd = normal_out(xd, yd)
+    a = to_compute(cast(x, xd, pd), pd)
+    b = to_compute(cast(y, yd, pd), pd)
+    a, b = np.broadcast_arrays(a, b)
+    with np.errstate(all="ignore"):
+        r = {"eq": a == b, "ne": a != b, "lt": a < b, "le": a <= b, "gt": a > b, "ge": a >= b}[op]
+    return np.asarray(r, dtype=np.bool_), "bool"
+
+
+NORMAL_UNARY_OPS = ("floor", "ceil", "round", "trunc", "abs", "neg", "sign", "square", "relu", "relu6", "leaky_relu",
+                    "clamp", "bitnot")
+
+
+def normal_unary(op, x, xd, alpha=0.0, beta=0.0):
+    """NormalUaryOps (+ bitnot): T → T, exact.  Floats follow Rust std (round half away from zero, signum(±0) = ±1,
+    relu = f32::max(x, 0) so NaN → 0, clamp keeps NaN); integers wrap; unsigned neg/abs/sign and every bool op
+    except neg/bitnot are the identity."""
+    if op == "bitnot" and xd in FLOATS:
+        raise TypeError("bitnot is integer/bool only")
+    x = np.asarray(x, dtype=NP[xd])
+    if xd == "bool":
+        return (~x if op in ("neg", "bitnot") else x.copy()), xd
+    with np.errstate(all="ignore"):
+        if xd in INTS:
+            t = NP[xd]
+            signed = xd[0] == "i"
+            al, be = _float_to_int(np.float64(alpha), xd), _float_to_int(np.float64(beta), xd)
+            zero = t(0)
+            if op in ("floor", "ceil", "round", "trunc"):
+                r = x.copy()
+            elif op == "square":
+                r = x * x
+            elif op == "abs":
+                r = np.where(x < 0, zero - x, x) if signed else x.copy()
+            elif op == "neg":
+                r = (zero - x) if signed else x.copy()
+            elif op == "sign":
+                r = np.sign(x) if signed else x.copy()
+            elif op == "relu":
+                r = np.maximum(x, zero)
+            elif op == "relu6":
+                r = np.maximum(np.minimum(x, t(6)), zero)
+            elif op == "leaky_relu":
+                r = np.maximum(x, zero) + t(al) * np.minimum(x, zero)
+            elif op == "clamp":
+                r = np.where(x < t(al), t(al), np.where(x > t(be), t(be), x))
+            elif op == "bitnot":
+                r = ~x
+            else:
+                raise ValueError(op)
+            return np.asarray(r).astype(t), xd
+        v = to_compute(x, xd)
+        c = v.dtype.type
+        al, be = c(alpha), c(beta)
+        if op == "floor":
+            r = np.floor(v)
+        elif op == "ceil":
+            r = np.ceil(v)
+        elif op == "round":
+            r = np.where(np.isfinite(v), np.copysign(np.floor(np.abs(v.astype(np.float64)) + 0.5), v), v).astype(v.dtype)
+        elif op == "trunc":
+            r = np.trunc(v)
+        elif op == "abs":
+            r = np.abs(v)
+        elif op == "neg":
+            r = -v
+        elif op == "sign":
+            r = np.where(np.isnan(v), v, np.copysign(c(1), v))
+        elif op == "square":
+            r = v * v
+        elif op == "relu":
+            r = np.fmax(v, c(0))
+        elif op == "relu6":
+            r = np.fmin(np.fmax(v, c(0)), c(6))
+        elif op == "leaky_relu":
+            r = np.fmax(v, c(0)) + al * np.fmin(v, c(0))
+        elif op == "clamp":
+            r = np.where(v < al, al, np.where(v > be, be, v))
+        else:
+            raise ValueError(op)
+    return from_compute(r.astype(v.dtype), xd), xd
 
 
 # ---- unary ---------------------------------------------------------------------------------------------
@@ -314,9 +428,11 @@ def reduce_shape(shape, axes, keep_dims):
 
 
 def reduce_out_dtype(op, d):
-    if op in ("sum", "max", "min", "prod", "sum_square"):
+    if op in ("sum", "max", "min", "prod", "sum_square", "reducel1", "nansum", "nanprod"):
         return d
-    if op in ("mean", "logsumexp"):
+    if op in ("all", "any"):
+        return "bool"
+    if op in ("mean", "logsumexp", "reducel2", "reducel3"):
         return float_out_binary(d, d)
     if op in ("argmax", "argmin"):
         return "i64"
@@ -342,15 +458,29 @@ def reduce(op, x, xd, axes, keep_dims=False):
                 v = np.where(np.isnan(v), fillv, v)
             r = (np.argmax(v, axis=ax) if op == "argmax" else np.argmin(v, axis=ax)).astype(np.int64)
             return r.reshape(oshape), od, True
+        if op in ("all", "any"):
+            # `x != 0` (NaN is true), AND / OR (common_reduce.rs:200-242)
+            t = to_compute(x, xd) != 0
+            r = np.all(t, axis=axes) if op == "all" else np.any(t, axis=axes)
+            return np.asarray(r, dtype=np.bool_).reshape(oshape), od, True
         if xd == "bool":
-            if op in ("sum", "max"):
+            if op in ("sum", "max", "reducel1", "nansum"):
                 r = np.any(x, axis=axes)
-            elif op in ("prod", "min", "sum_square"):
+            elif op in ("prod", "min", "sum_square", "nanprod"):
                 r = np.all(x, axis=axes) if op != "sum_square" else np.any(x, axis=axes)
             else:
                 r = None
             if r is not None:
                 return np.asarray(r).reshape(oshape), od, True
+        if xd in INTS and op in ("reducel1", "nansum", "nanprod"):
+            if op == "reducel1":
+                ax_ = np.where(x < 0, NP[xd](0) - x, x).astype(NP[xd]) if xd[0] == "i" else x
+                r = np.add.reduce(ax_, axis=axes, dtype=NP[xd])
+            elif op == "nansum":
+                r = np.add.reduce(x, axis=axes, dtype=NP[xd])
+            else:
+                r = np.multiply.reduce(x, axis=axes, dtype=NP[xd])
+            return np.asarray(r, dtype=NP[xd]).reshape(oshape), od, True
         if xd in INTS and op in ("sum", "prod", "max", "min", "sum_square"):
             if op == "sum":
                 r = np.add.reduce(x, axis=axes, dtype=NP[xd])
@@ -364,8 +494,11 @@ def reduce(op, x, xd, axes, keep_dims=False):
                 r = np.min(x, axis=axes) if x.size else np.full(oshape, np.iinfo(NP[xd]).max, NP[xd])
             return np.asarray(r, dtype=NP[xd]).reshape(oshape), od, True
         # float-valued results: f64 accumulation
-        if op in ("mean", "logsumexp"):
+        if op in ("mean", "logsumexp", "reducel2"):
             v = to_compute(cast(x, xd, od), od).astype(np.float64)
+        elif op == "reducel3":
+            ax_, _ = normal_unary("abs", x, xd)  # |x| in T (wraps for the integer minimum), then cast
+            v = to_compute(cast(ax_, xd, od), od).astype(np.float64)
         else:
             v = to_compute(x, xd).astype(np.float64)
         n = 1
@@ -377,6 +510,17 @@ def reduce(op, x, xd, axes, keep_dims=False):
             r = v.prod(axis=axes)
         elif op == "sum_square":
             r = (v * v).sum(axis=axes)
+        elif op == "reducel1":
+            r = np.abs(v).sum(axis=axes)
+        elif op == "nansum":
+            r = np.where(np.isnan(v), 0.0, v).sum(axis=axes)
+        elif op == "nanprod":
+            r = np.where(np.isnan(v), 1.0, v).prod(axis=axes)
+        elif op == "reducel2":
+            r = np.sqrt((v * v).sum(axis=axes))
+        elif op == "reducel3":
+            third = np.float64(to_compute(cast(np.array([1.0 / 3.0]), "f64", od), od)[0])  # `(1.0 / 3.0).cast()` to the output dtype
+            r = np.power((v * v * v).sum(axis=axes), third)
         elif op == "mean":
             r = v.sum(axis=axes) / n
         elif op == "logsumexp":
@@ -398,7 +542,13 @@ def reduce_f64(op, x, xd, axes):
     x = np.asarray(x, dtype=NP[xd])
     axes = tuple(process_axes(axes, x.ndim))
     od = reduce_out_dtype(op, xd)
-    v = to_compute(cast(x, xd, od), od).astype(np.float64) if op in ("mean", "logsumexp") else to_compute(x, xd).astype(np.float64)
+    if op in ("mean", "logsumexp", "reducel2"):
+        v = to_compute(cast(x, xd, od), od).astype(np.float64)
+    elif op == "reducel3":
+        ax_, _ = normal_unary("abs", x, xd)
+        v = to_compute(cast(ax_, xd, od), od).astype(np.float64)
+    else:
+        v = to_compute(x, xd).astype(np.float64)
     n = 1
     for a in axes:
         n *= x.shape[a]
@@ -413,6 +563,17 @@ def reduce_f64(op, x, xd, axes):
             return v.prod(axis=axes)
         if op == "logsumexp":
             return np.log(np.exp(v).sum(axis=axes))
+        if op == "reducel1":
+            return np.abs(v).sum(axis=axes)
+        if op == "nansum":
+            return np.where(np.isnan(v), 0.0, v).sum(axis=axes)
+        if op == "nanprod":
+            return np.where(np.isnan(v), 1.0, v).prod(axis=axes)
+        if op == "reducel2":
+            return np.sqrt((v * v).sum(axis=axes))
+        if op == "reducel3":
+            third = np.float64(to_compute(cast(np.array([1.0 / 3.0]), "f64", od), od)[0])
+            return np.power((v * v * v).sum(axis=axes), third)
     raise ValueError(op)
 
 

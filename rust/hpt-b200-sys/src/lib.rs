@@ -102,6 +102,8 @@ extern "C" {
                          plan: *mut hptb_collapse_plan) -> hptb_status;
     pub fn hptb_binary(ctx: *mut hptb_ctx, op: c_int, lhs: *const hptb_tensor, rhs: *const hptb_tensor,
                        out: *mut hptb_tensor, stream: *mut c_void) -> hptb_status;
+    pub fn hptb_compare(ctx: *mut hptb_ctx, op: c_int, lhs: *const hptb_tensor, rhs: *const hptb_tensor,
+                        out: *mut hptb_tensor, stream: *mut c_void) -> hptb_status;
     pub fn hptb_unary(ctx: *mut hptb_ctx, op: c_int, inp: *const hptb_tensor, out: *mut hptb_tensor,
                       alpha: c_double, beta: c_double, stream: *mut c_void) -> hptb_status;
     pub fn hptb_reduce(ctx: *mut hptb_ctx, op: c_int, inp: *const hptb_tensor, axes: *const i32, naxes: c_int,
