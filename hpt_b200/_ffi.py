@@ -114,8 +114,11 @@ SIGNATURES = {
     "hptb_reduce": (c_int, [c_void_p, c_int, _T, POINTER(c_int32), c_int, _T, c_int, c_void_p]),
     "hptb_mean_var": (c_int, [c_void_p, _T, POINTER(c_int32), c_int, _T, _T, c_void_p]),
     "hptb_softmax": (c_int, [c_void_p, _T, c_int, c_int, _T, c_void_p]),
+    "hptb_layernorm": (c_int, [c_void_p, _T, c_int, _T, _T, c_double, _T, c_void_p]),
     "hptb_copy": (c_int, [c_void_p, _T, _T, c_void_p]),
     "hptb_fill": (c_int, [c_void_p, _T, c_void_p, c_void_p]),
+    "hptb_arange": (c_int, [c_void_p, _T, c_void_p, c_void_p, c_void_p]),
+    "hptb_eye": (c_int, [c_void_p, _T, c_int64, c_void_p]),
     "hptb_comm_unique_id": (c_int, [c_void_p]),
     "hptb_comm_init_rank": (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(c_void_p)]),
     "hptb_comm_destroy": (c_int, [c_void_p]),

@@ -947,6 +947,128 @@ reduce_cols_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
   }
 }
 
+// ---- lean cols kernel ------------------------------------------------------------------------------------
+// The common cols case — ONE reduced dim (row stride `rs`), the kept contiguous dim a multiple of the pack width,
+// 32-bit row counters — stripped to what it needs, for the same reason as the lean rows kernel: at ≤ 40 registers
+// six CTAs are resident per SM, and a CTA walks only a short slab of rows (TY·UNROLL·4 ≈ 128), so the hardware
+// scheduler keeps every SM streaming.  TX = 32 lanes × VEC columns (512 contiguous bytes of every row), TY = 8
+// thread rows; shared-memory tree over the thread rows; row slabs are combined by the last CTA of a column tile
+// (S ≤ 64 partials, read back from L2 in fixed order → deterministic).
+struct LeanColsParams {
+  DimWalk kept;          // kept dims other than the contiguous one: stride_a input, stride_b output
+  int64_t rs;            // input stride of the reduced dim
+  int64_t C;             // contiguous kept extent
+  int64_t K;             // prod(kept.shape)
+  double count;
+  uint32_t R;            // reduced extent
+  uint32_t rows_per_split;
+  uint32_t S;
+  uint32_t col_tiles;
+  int32_t use64;
+  int32_t fold_out;
+};
+
+// VEC (value, index) pairs or 16-byte accumulators per thread need 64 registers: 4 CTAs/SM for those
+template <typename Op, int VEC>
+constexpr int lean_cols_min_blocks() {
+  return sizeof(typename Op::Local) > 8 ? 3 : (Op::kIndexed || sizeof(typename Op::Local) * VEC > 16) ? 4 : HPTB_LEAN_MINB;
+}
+
+template <typename Op, typename T, int VEC>
+__global__ void __launch_bounds__(kRedThreads, lean_cols_min_blocks<Op, VEC>())
+reduce_cols_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out, typename Op::Out* __restrict__ out2,
+                        typename Op::Acc* __restrict__ scratch, uint32_t* __restrict__ tickets, LeanColsParams p) {
+  pdl_prologue();
+  typedef typename Op::Acc Acc;
+  typedef typename Op::Local Local;
+  constexpr int UNROLL = HPTB_RED_UNROLL;
+  constexpr int TX = 32, TY = kRedThreads / TX, W = TX * VEC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Acc* sm = reinterpret_cast<Acc*>(smem_raw);  // [TY][W]
+  const uint32_t tid = threadIdx.x, tx = tid & (TX - 1), ty = tid / TX;
+  // blockIdx.x = (split · K + k) · col_tiles + tile: CTAs that run together read adjacent column segments of the same rows
+  uint32_t b = blockIdx.x;
+  const uint32_t tile = b % p.col_tiles;
+  b /= p.col_tiles;
+  const uint32_t k = b % (uint32_t)p.K;
+  const uint32_t split = b / (uint32_t)p.K;
+  const int64_t col = ((int64_t)tile * TX + tx) * VEC;
+  const bool col_ok = col < p.C;
+  int64_t in_off = 0, out_off = 0;
+  if (p.kept.n) walk2(k, p.kept, p.use64, in_off, out_off);
+  const uint32_t r_begin = split * p.rows_per_split;
+  const uint32_t r_end = min(p.R, r_begin + p.rows_per_split);
+  Local acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = Op::local_identity();
+  if (col_ok) {
+    const T* base = in + in_off + col;
+    int32_t it = 0;
+    for (uint32_t r = r_begin + ty; r < r_end; r += TY * UNROLL, it += UNROLL) {
+      Pack<T, VEC> v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (r + (uint32_t)u * TY < r_end) load_pack<T, VEC>(v[u], base + (int64_t)(r + (uint32_t)u * TY) * p.rs);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (r + (uint32_t)u * TY < r_end) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) Op::accumulate(acc[j], v[u].v[j], it + u);
+        }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = Op::finish(acc[j], r_begin + ty, TY, 1, 0);
+  __syncthreads();
+#pragma unroll
+  for (int h = TY >> 1; h > 0; h >>= 1) {
+    if (ty < h) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = Op::combine(sm[ty * W + tx * VEC + j], sm[(ty + h) * W + tx * VEC + j]);
+    }
+    __syncthreads();
+  }
+  if (p.S == 1) {
+    if (ty == 0 && col_ok) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, out_off + col + j, sm[tx * VEC + j], p.count, p.fold_out);
+    }
+    return;
+  }
+  const uint32_t group = k * p.col_tiles + tile;
+  Acc* my = scratch + ((size_t)group * p.S + split) * W;
+  if (ty == 0) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) my[tx * VEC + j] = sm[tx * VEC + j];
+  }
+  if (take_ticket(tickets + group, p.S)) {
+    Acc part[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) part[j] = Op::identity();
+    for (uint32_t sidx = ty; sidx < p.S; sidx += TY) {
+      const Acc* src = scratch + ((size_t)group * p.S + sidx) * W;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) part[j] = Op::combine(part[j], load_cg(src + tx * VEC + j));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = part[j];
+    __syncthreads();
+#pragma unroll
+    for (int h = TY >> 1; h > 0; h >>= 1) {
+      if (ty < h) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = Op::combine(sm[ty * W + tx * VEC + j], sm[(ty + h) * W + tx * VEC + j]);
+      }
+      __syncthreads();
+    }
+    if (ty == 0 && col_ok) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, out_off + col + j, sm[tx * VEC + j], p.count, p.fold_out);
+    }
+  }
+}
+
 // ---- host launcher -------------------------------------------------------------------------------------------
 inline bool red_fits_u32(int64_t v) { return v >= 0 && v < (int64_t(1) << 31); }
 
@@ -1039,6 +1161,55 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
       return true;
     };
     if (!aligned(vec) || p.C < vec) vec = 1;
+    // lean path: one reduced dim, full-width tiles of 32 lanes × VECMAX columns, 32-bit counters
+    if constexpr (VECMAX > 1) {
+      if (vec == VECMAX && nr == 1 && p.C >= 16 * VECMAX && red_fits_u32(R) && red_fits_u32(p.K) && !big &&
+          !tune_knob("HPTB_TUNE_NOLEAN")) {
+        constexpr int LTX = 32, LTY = kRedThreads / LTX;
+        LeanColsParams q;
+        memset(&q, 0, sizeof(q));
+        q.kept = p.kept;
+        q.rs = c.strides[1][red[0]];
+        q.C = p.C;
+        q.K = p.K;
+        q.count = plan.count;
+        q.R = (uint32_t)R;
+        q.fold_out = plan.fold_out;
+        const int64_t ctiles = (p.C + (int64_t)LTX * VECMAX - 1) / ((int64_t)LTX * VECMAX);
+        const int64_t lgroups = p.K * ctiles;
+        // Row slabs: about ONE wave of CTAs at 4 per SM (each CTA pays a shared-memory tree, a partial write and a
+        // ticket, so more, thinner slabs lose: f32 [8192,8192] max(0): 576 CTAs → 43.9 µs, 4096 CTAs → 47.8 µs;
+        // [4096,4096] sum(0): 576 CTAs → 15.4 µs, 1024 → 18.0 µs), but never more than 4096 rows per slab
+        // ([262144,16384] sum(0): 64 slabs → 7.28 TB/s, 5 slabs → 6.9 TB/s); at most 64 partials per column tile.
+        int64_t S = ((int64_t)sms * 4 + lgroups / 2) / lgroups;
+        const int64_t by_rows = (R + 4095) / 4096;
+        if (S < by_rows) S = by_rows;
+        if (S > 64) S = 64;
+        const int64_t max_s = (R + (int64_t)LTY * HPTB_RED_UNROLL - 1) / ((int64_t)LTY * HPTB_RED_UNROLL);  // ≥ one batch per thread row
+        if (S > max_s) S = max_s;
+        if (S < 1) S = 1;
+        if (int64_t t = tune_knob("HPTB_TUNE_S")) S = t > R ? R : t;
+        int64_t rps = (R + S - 1) / S;
+        S = (R + rps - 1) / rps;
+        if (lgroups * S <= 0x7fffffffLL && ctiles <= 0x7fffffffLL) {
+          q.rows_per_split = (uint32_t)rps;
+          q.S = (uint32_t)S;
+          q.col_tiles = (uint32_t)ctiles;
+          q.use64 = 0;
+          Scratch scratch;
+          uint32_t* tickets = nullptr;
+          if (S > 1) {
+            HPTB_TRY(scratch.get(plan.ctx, (size_t)(lgroups * S * LTX * VECMAX) * sizeof(Acc), stream));
+            tickets = ctx_tickets(plan.ctx, stream, (size_t)lgroups);
+            if (!tickets) return fail(HPTB_ERR_OOM, "reduce: ticket buffer allocation failed");
+          }
+          const size_t lsmem = (size_t)kRedThreads * VECMAX * sizeof(Acc);
+          HPTB_CUDA_CHECK(launch_kernel(reduce_cols_lean_kernel<Op, T, VECMAX>, dim3((unsigned)(lgroups * S)), dim3(kRedThreads), lsmem, stream, in, out,
+                                        out2, (Acc*)scratch.ptr, tickets, q));
+          return HPTB_OK;
+        }
+      }
+    }
     int TX = 32;
     while (TX > 1 && (int64_t)(TX / 2) * vec >= p.C) TX >>= 1;
     p.TX = TX;

@@ -336,6 +336,212 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
   return HPTB_OK;
 }
 
+
+// ---- layernorm ---------------------------------------------------------------------------------------------
+// NormalizationOps::layernorm (hpt-traits/src/ops/normalization.rs:12-38; CPU semantics
+// hpt/src/backends/cpu/tensor_internal/normalization.rs:49-200; device: hpt-cudakernels/src/normalization/
+// {layernorm,layernorm_post}.cu): over the last k dims, y = (x − mean) / sqrt(var + eps) with the population
+// variance Σ(x − mean)²/n (two passes over the register-resident row, as the reference computes it), then
+// γ·y + β when given — fused here into the same kernel (the reference launches layernorm_post or a binary op).
+// Output dtype O = FloatOutBinaryPromote<T,T>; statistics in the compute type of O.
+struct LayerNormParams {
+  DimWalk kept;  // stride_a = input, stride_b = output
+  int64_t M, L;
+  double eps;
+  int32_t use64;
+  int32_t nchunks;
+  int32_t has_gamma, has_beta;
+};
+
+template <typename T, int VEC, int G, int NCH>
+__global__ void __launch_bounds__(kSmThreads)
+layernorm_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type* __restrict__ out,
+                   const typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type* __restrict__ gamma,
+                   const typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type* __restrict__ beta,
+                   LayerNormParams p) {
+  pdl_prologue();
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type O;
+  typedef compute_t<O> C;
+  __shared__ C s_buf[kSmThreads / 32];
+  const int tid = threadIdx.x;
+  const int lane = tid & (G - 1);
+  const int64_t row = (int64_t)blockIdx.x * (kSmThreads / G) + tid / G;
+  const bool active = row < p.M;
+  int64_t in_off = 0, out_off = 0;
+  if (active) walk2(row, p.kept, p.use64, in_off, out_off);
+  C x[NCH][VEC];
+  C sum = (C)0;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int e = (i * G + lane) * VEC;
+    if (i < p.nchunks && active && e < (int)p.L) {
+      Pack<T, VEC> v;
+      load_pack<T, VEC>(v, in + in_off + e);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        x[i][k] = to_compute<O>(cast<O>(v.v[k]));
+        sum += x[i][k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) x[i][k] = (C)0;
+    }
+  }
+  sum = group_reduce<AddOp, C, G>(sum, s_buf, (C)0);
+  const C mean = sum / (C)p.L;
+  C sq = (C)0;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int e = (i * G + lane) * VEC;
+    if (i < p.nchunks && e < (int)p.L) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        x[i][k] -= mean;
+        sq += x[i][k] * x[i][k];
+      }
+    }
+  }
+  sq = group_reduce<AddOp, C, G>(sq, s_buf, (C)0);
+  C rstd;
+  if constexpr (std::is_same<C, float>::value) rstd = 1.0f / sqrtf(sq / (C)p.L + (C)p.eps);
+  else rstd = 1.0 / sqrt(sq / (C)p.L + (C)p.eps);
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int e = (i * G + lane) * VEC;
+    if (i < p.nchunks && active && e < (int)p.L) {
+      Pack<O, VEC> g, b, o;
+      if (p.has_gamma) load_pack_cached<O, VEC>(g, gamma + e);
+      if (p.has_beta) load_pack_cached<O, VEC>(b, beta + e);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        // the reference rounds y to O before γ·y + β (two kernels); here the affine step stays in the compute type
+        C y = x[i][k] * rstd;
+        if (p.has_gamma) y *= to_compute<O>(g.v[k]);
+        if (p.has_beta) y += to_compute<O>(b.v[k]);
+        o.v[k] = from_compute<O>(y);
+      }
+      store_pack<O, VEC>(out + out_off + e, o);
+    }
+  }
+}
+
+// any row length: one CTA per row, three streaming passes (Σx, Σ(x−mean)², write); rows come back from L2
+template <typename T>
+__global__ void __launch_bounds__(kSmThreads)
+layernorm_rows_stream(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type* __restrict__ out,
+                      const typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type* __restrict__ gamma,
+                      const typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type* __restrict__ beta,
+                      LayerNormParams p) {
+  pdl_prologue();
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type O;
+  typedef compute_t<O> C;
+  __shared__ C s_buf[kSmThreads / 32];
+  const int tid = threadIdx.x;
+  for (int64_t row = blockIdx.x; row < p.M; row += gridDim.x) {
+    int64_t in_off = 0, out_off = 0;
+    walk2(row, p.kept, p.use64, in_off, out_off);
+    const T* src = in + in_off;
+    O* dst = out + out_off;
+    C sum = (C)0;
+    for (int64_t e = tid; e < p.L; e += kSmThreads) sum += to_compute<O>(cast<O>(load_one(src + e)));
+    sum = group_reduce<AddOp, C, kSmThreads>(sum, s_buf, (C)0);
+    const C mean = sum / (C)p.L;
+    C sq = (C)0;
+    for (int64_t e = tid; e < p.L; e += kSmThreads) {
+      const C d = to_compute<O>(cast<O>(src[e])) - mean;
+      sq += d * d;
+    }
+    sq = group_reduce<AddOp, C, kSmThreads>(sq, s_buf, (C)0);
+    C rstd;
+    if constexpr (std::is_same<C, float>::value) rstd = 1.0f / sqrtf(sq / (C)p.L + (C)p.eps);
+    else rstd = 1.0 / sqrt(sq / (C)p.L + (C)p.eps);
+    for (int64_t e = tid; e < p.L; e += kSmThreads) {
+      C y = (to_compute<O>(cast<O>(src[e])) - mean) * rstd;
+      if (p.has_gamma) y *= to_compute<O>(gamma[e]);
+      if (p.has_beta) y += to_compute<O>(beta[e]);
+      dst[e] = from_compute<O>(y);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+hptb_status launch_layernorm(hptb_ctx* ctx, const Collapsed& c, const void* in_v, void* out_v, const void* gamma_v, const void* beta_v,
+                             double eps, cudaStream_t stream) {
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type O;
+  const T* in = static_cast<const T*>(in_v);
+  O* out = static_cast<O*>(out_v);
+  const O* gamma = static_cast<const O*>(gamma_v);
+  const O* beta = static_cast<const O*>(beta_v);
+  LayerNormParams p;
+  memset(&p, 0, sizeof(p));
+  int ad = -1, kept[kRedMaxDims], nk = 0, nred = 0;
+  for (int d = c.ndim - 1; d >= 0; --d) {
+    if (c.reduced[d]) { ad = d; ++nred; } else kept[nk++] = d;
+  }
+  if (nred > 1 || (ad >= 0 && (c.strides[1][ad] != 1 || c.strides[0][ad] != 1)))
+    return fail(HPTB_ERR_UNSUPPORTED, "layernorm: the normalized dims must be contiguous in the input and the output");
+  bool big = false;
+  p.L = ad < 0 ? 1 : c.shape[ad];
+  p.eps = eps;
+  p.has_gamma = gamma != nullptr;
+  p.has_beta = beta != nullptr;
+  fill_walk(p.kept, c, kept, nk, true, big);
+  int64_t M = 1;
+  for (int i = 0; i < nk; ++i) M *= c.shape[kept[i]];
+  p.M = M;
+  if (M == 0 || p.L == 0) return HPTB_OK;
+  if (!red_fits_u32(M)) big = true;
+  p.use64 = big ? 1 : 0;
+  constexpr int kMinSz = sizeof(T) < sizeof(O) ? sizeof(T) : sizeof(O);
+  constexpr int VECMAX = 16 / kMinSz > 8 ? 8 : 16 / kMinSz;
+  int vec = VECMAX;
+  auto aligned = [&](int v) {
+    if (v == 1) return true;
+    size_t ai = sizeof(T) * v > 16 ? 16 : sizeof(T) * v, ao = sizeof(O) * v > 16 ? 16 : sizeof(O) * v;
+    if (reinterpret_cast<uintptr_t>(in) % ai || reinterpret_cast<uintptr_t>(out) % ao) return false;
+    if ((gamma && reinterpret_cast<uintptr_t>(gamma) % ao) || (beta && reinterpret_cast<uintptr_t>(beta) % ao)) return false;
+    if (p.L % v) return false;
+    for (int i = 0; i < nk; ++i) {
+      if ((uint64_t)(std::llabs(c.strides[1][kept[i]]) * (int64_t)sizeof(T)) % ai) return false;
+      if ((uint64_t)(std::llabs(c.strides[0][kept[i]]) * (int64_t)sizeof(O)) % ao) return false;
+    }
+    return true;
+  };
+  if (!aligned(vec)) vec = 1;
+  const int64_t packs = (p.L + vec - 1) / vec;
+  int G = 0;
+  if (packs <= 32 * 4) G = 32;
+  else if (packs <= (int64_t)kSmThreads * kSmChunks) G = kSmThreads;
+  if (G) {
+    p.nchunks = (int)((packs + G - 1) / G);
+    int64_t blocks = (M + (kSmThreads / G) - 1) / (kSmThreads / G);
+    if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "layernorm: grid too large");
+#define HPTB_LN_LAUNCH2(V, GG, N) \
+  HPTB_CUDA_CHECK(launch_kernel(layernorm_rows_reg<T, V, GG, N>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, gamma, beta, p))
+#define HPTB_LN_LAUNCH(V, GG)                                                 \
+  do {                                                                        \
+    if (GG == 32 || p.nchunks <= 2) HPTB_LN_LAUNCH2(V, GG, (GG == 32 ? 4 : 2)); \
+    else if (p.nchunks <= 4) HPTB_LN_LAUNCH2(V, GG, 4);                       \
+    else HPTB_LN_LAUNCH2(V, GG, kSmChunks);                                   \
+  } while (0)
+    if (vec > 1) {
+      if (G == 32) HPTB_LN_LAUNCH(VECMAX, 32);
+      else HPTB_LN_LAUNCH(VECMAX, kSmThreads);
+    } else {
+      if (G == 32) HPTB_LN_LAUNCH(1, 32);
+      else HPTB_LN_LAUNCH(1, kSmThreads);
+    }
+#undef HPTB_LN_LAUNCH
+#undef HPTB_LN_LAUNCH2
+  } else {
+    int64_t blocks = M < (int64_t)ctx->sm_count * 16 ? M : (int64_t)ctx->sm_count * 16;
+    HPTB_CUDA_CHECK(launch_kernel(layernorm_rows_stream<T>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, gamma, beta, p));
+  }
+  count_launches(1);
+  return HPTB_OK;
+}
+
 }  // namespace
 }  // namespace hptb
 
@@ -366,5 +572,47 @@ extern "C" hptb_status hptb_softmax(hptb_ctx* ctx, const hptb_tensor* in, int ax
     HPTB_FOR_DTYPES(X)
 #undef X
     default: return fail(HPTB_ERR_DTYPE, "softmax: bad dtype");
+  }
+}
+
+extern "C" hptb_status hptb_layernorm(hptb_ctx* ctx, const hptb_tensor* in, int n_normalized_dims, const hptb_tensor* gamma,
+                                      const hptb_tensor* beta, double eps, hptb_tensor* out, void* stream) {
+  if (!ctx) return fail(HPTB_ERR_INVALID, "layernorm: null ctx");
+  HPTB_TRY(validate_tensor(in, "layernorm in"));
+  HPTB_TRY(validate_tensor(out, "layernorm out"));
+  if (n_normalized_dims < 1 || n_normalized_dims > in->ndim)
+    return fail(HPTB_ERR_SHAPE, "layernorm: normalized_shape has %d dims, the input %d", n_normalized_dims, in->ndim);
+  const int odt = kFloatOutBinary[in->dtype][in->dtype];
+  if (out->dtype != odt) return fail(HPTB_ERR_DTYPE, "layernorm: out dtype is %s, expected %s", dtype_name(out->dtype), dtype_name(odt));
+  bool same = in->ndim == out->ndim;
+  for (int i = 0; same && i < in->ndim; ++i) same = in->shape[i] == out->shape[i];
+  if (!same) return fail(HPTB_ERR_SHAPE, "layernorm: out shape differs from the input shape");
+  const int first = in->ndim - n_normalized_dims;
+  const hptb_tensor* gb[2] = {gamma, beta};
+  for (int t = 0; t < 2; ++t) {
+    if (!gb[t]) continue;
+    HPTB_TRY(validate_tensor(gb[t], t ? "layernorm beta" : "layernorm gamma"));
+    if (gb[t]->dtype != odt) return fail(HPTB_ERR_DTYPE, "layernorm: gamma / beta must be %s", dtype_name(odt));
+    bool ok = gb[t]->ndim == n_normalized_dims;
+    int64_t exp = 1;
+    for (int i = n_normalized_dims - 1; ok && i >= 0; --i) {
+      ok = gb[t]->shape[i] == in->shape[first + i] && (gb[t]->shape[i] == 1 || gb[t]->strides[i] == exp);
+      exp *= gb[t]->shape[i];
+    }
+    if (!ok) return fail(HPTB_ERR_SHAPE, "layernorm: gamma / beta must be contiguous tensors of the normalized shape");
+  }
+  uint8_t mask[HPTB_MAX_DIMS] = {0};
+  for (int i = first; i < in->ndim; ++i) mask[i] = 1;
+  int64_t strides[kMaxOperands][HPTB_MAX_DIMS] = {{0}};
+  for (int i = 0; i < in->ndim; ++i) { strides[0][i] = out->strides[i]; strides[1][i] = in->strides[i]; }
+  Collapsed c;
+  collapse(in->ndim, in->shape, 2, strides, mask, &c);
+  DeviceGuard g(ctx->device);
+  switch (in->dtype) {
+#define X(T, N, E) \
+  case E: return launch_layernorm<T>(ctx, c, in->data, out->data, gamma ? gamma->data : nullptr, beta ? beta->data : nullptr, eps, (cudaStream_t)stream);
+    HPTB_FOR_DTYPES(X)
+#undef X
+    default: return fail(HPTB_ERR_DTYPE, "layernorm: bad dtype");
   }
 }

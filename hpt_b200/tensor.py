@@ -140,6 +140,70 @@ class Tensor:
         st = _Storage(ctx, _numel(shape) * _ffi.DTYPE_SIZES[dtype], stream)
         return Tensor(st, st.ptr, dtype, shape, _contig_strides(shape))
 
+    # ---- TensorCreator (hpt-traits/src/ops/creation.rs; CPU semantics normal_creation.rs:34-234) ------------------
+    @staticmethod
+    def _scalar(value, dtype):
+        """one host element of `dtype` (Rust `as` from the Python number)"""
+        if dtype in (_ffi.U16, _ffi.U32, _ffi.U64):
+            return torch.tensor([int(value)], dtype=torch.int64).to(_TORCH_DTYPES[dtype])
+        if dtype in (_ffi.F16, _ffi.BF16, _ffi.F32, _ffi.F64):
+            return torch.tensor([float(value)], dtype=torch.float64).to(_TORCH_DTYPES[dtype])
+        return torch.tensor([value]).to(_TORCH_DTYPES[dtype])
+
+    @staticmethod
+    def full(val, shape, dtype, device=0, stream=None):
+        return Tensor.empty(shape, dtype, device, stream).fill_(val, stream)
+
+    @staticmethod
+    def zeros(shape, dtype, device=0, stream=None): return Tensor.full(0, shape, dtype, device, stream)
+
+    @staticmethod
+    def ones(shape, dtype, device=0, stream=None): return Tensor.full(1, shape, dtype, device, stream)
+
+    def empty_like(self): return Tensor.empty(self.shape, self.dtype, self.ctx.device)
+    def zeros_like(self): return Tensor.zeros(self.shape, self.dtype, self.ctx.device)
+    def ones_like(self): return Tensor.ones(self.shape, self.dtype, self.ctx.device)
+    def full_like(self, val): return Tensor.full(val, self.shape, self.dtype, self.ctx.device)
+
+    @staticmethod
+    def _arange_into(n, start, step, dtype, device, stream):
+        out = Tensor.empty((max(int(n), 0),), dtype, device, stream)
+        a, b = Tensor._scalar(start, dtype), Tensor._scalar(step, dtype)
+        check(lib.hptb_arange(out.ctx.handle, byref(out._c()), c_void_p(a.data_ptr()), c_void_p(b.data_ptr()), _s(stream)))
+        return out
+
+    @staticmethod
+    def arange(start, end, dtype, device=0, stream=None):
+        """`Tensor::<T>::arange(start, end)`: size = end as i64 − start as i64 (empty if ≤ 0), x[i] = start + i."""
+        return Tensor._arange_into(int(end) - int(start), start, 1, dtype, device, stream)
+
+    @staticmethod
+    def arange_step(start, end, step, dtype, device=0, stream=None):
+        """size = floor((end − start) / step) + 1 in f64, as normal_creation.rs:163-185 computes it."""
+        import math
+        s, e, st = float(start), float(end), float(step)
+        n = math.floor((e - s) / st) + 1 if st > 0 else math.floor((s - e) / (-st)) + 1
+        return Tensor._arange_into(n, start, step, dtype, device, stream)
+
+    @staticmethod
+    def linspace(start, end, num, include_end, dtype, device=0, stream=None):
+        """step = (end − start) / (num − 1 | num) in f64, cast to T; x[i] = start + T(i)·step, last = end if included."""
+        n = int(num)
+        step = (float(end) - float(start)) / ((n - 1.0) if include_end else float(n)) if n > (1 if include_end else 0) else 0.0
+        out = Tensor._arange_into(n, start, step, dtype, device, stream)
+        if include_end and n > 0:
+            out[n - 1:n].fill_(end, stream)
+        return out
+
+    @staticmethod
+    def eye(n, m, k, dtype, device=0, stream=None):
+        out = Tensor.empty((int(n), int(m)), dtype, device, stream)
+        check(lib.hptb_eye(out.ctx.handle, byref(out._c()), int(k), _s(stream)))
+        return out
+
+    @staticmethod
+    def identity(n, dtype, device=0, stream=None): return Tensor.eye(n, n, 0, dtype, device, stream)
+
     @staticmethod
     def to_cuda(host, device=0, stream=None, sync=True):
         """`cpu_tensor.to_cuda::<DEVICE>()` (hpt/src/backends/cpu/tensor_impls.rs:295-313).
@@ -297,8 +361,7 @@ class Tensor:
         return out
 
     def fill_(self, value, stream=None):
-        host = torch.tensor([value]).to(_TORCH_DTYPES[self.dtype]) if self.dtype not in (_ffi.U16, _ffi.U32, _ffi.U64) \
-            else torch.tensor([value], dtype=torch.int64).to(_TORCH_DTYPES[self.dtype])
+        host = Tensor._scalar(value, self.dtype)
         check(lib.hptb_fill(self.ctx.handle, byref(self._c()), c_void_p(host.data_ptr()), _s(stream)))
         return self
 
@@ -468,6 +531,18 @@ class Tensor:
         odt = lib.hptb_unary_out_dtype(0, self.dtype)
         out = Tensor.empty(self.shape, odt, self.ctx.device, stream)
         check(lib.hptb_softmax(self.ctx.handle, byref(self._c()), axis, log, byref(out._c()), _s(stream)))
+        return out
+
+    def layernorm(self, normalized_shape, gamma=None, beta=None, eps=1e-5, stream=None):
+        """`x.layernorm(&normalized_shape, Some(&gamma), Some(&beta), eps)` (normalization.rs:30-38)."""
+        ns = tuple(int(v) for v in normalized_shape)
+        if len(ns) < 1 or len(ns) > self.ndim or tuple(self.shape[self.ndim - len(ns):]) != ns:
+            raise HptError(1, f"normalized dims must match last dims of input tensor, shape: {self.shape}, normalized_shape: {ns}")
+        odt = lib.hptb_promote(self.dtype, self.dtype, _ffi.PROMOTE_FLOAT_BINARY)
+        out = Tensor.empty(self.shape, odt, self.ctx.device, stream)
+        g = byref(gamma._c()) if gamma is not None else None
+        b = byref(beta._c()) if beta is not None else None
+        check(lib.hptb_layernorm(self.ctx.handle, byref(self._c()), len(ns), g, b, float(eps), byref(out._c()), _s(stream)))
         return out
 
     def softmax(self, axis): return self._softmax(axis, 0)

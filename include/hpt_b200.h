@@ -233,11 +233,24 @@ hptb_status hptb_mean_var(hptb_ctx* ctx, const hptb_tensor* in, const int32_t* a
 /* softmax / log_softmax along one axis (NormalizationOps, hpt-traits/src/ops/normalization.rs:51-64);
  * replaces `<T>_{softmax,logsoftmax}_{warp,block,block_large}` (hpt-cudakernels/src/normalization/softmax.cu). */
 hptb_status hptb_softmax(hptb_ctx* ctx, const hptb_tensor* in, int axis, int log, hptb_tensor* out, void* stream);
+/* NormalizationOps::layernorm over the LAST n_normalized_dims dims (hpt-traits/src/ops/normalization.rs:12-38;
+ * hpt/src/backends/cuda/tensor_internal/layernorm.rs:47-…, kernels layernorm.cu + layernorm_post.cu):
+ * y = (x − mean) / sqrt(var + eps) · gamma + beta, population variance; gamma / beta (either may be NULL) are
+ * contiguous tensors of the normalized shape; every tensor but `in` has dtype FloatOutBinaryPromote<T,T>. */
+hptb_status hptb_layernorm(hptb_ctx* ctx, const hptb_tensor* in, int n_normalized_dims, const hptb_tensor* gamma,
+                           const hptb_tensor* beta, double eps, hptb_tensor* out, void* stream);
 /* Gather a view into another layout with optional dtype conversion (Rust `as` semantics):
  * replaces strided_copy_<T> (hpt-cudakernels/src/strided_copy.cu) used by contiguous()/to_cpu. */
 hptb_status hptb_copy(hptb_ctx* ctx, const hptb_tensor* in, hptb_tensor* out, void* stream);
 /* out[...] = *scalar (scalar has out's dtype, host memory): replaces set_val_<T> / fill_<T>. */
 hptb_status hptb_fill(hptb_ctx* ctx, hptb_tensor* out, const void* scalar, void* stream);
+/* TensorCreator (hpt-traits/src/ops/creation.rs; replaces the creation kernels of hpt-cudakernels/src/creation.cu and
+ * the NVRTC arange of tensor_internal/normal_creation.rs).  zeros / ones / full are hptb_fill.
+ * hptb_arange: out[i] = start + T(i)·step for a 1-D `out`, every step rounded in T as the reference's
+ * `start._add(i.cast()._mul(step))` (arange, arange_step, linspace; scalars have out's dtype, host memory).
+ * hptb_eye: 2-D `out`, 1 where col == row + k (eye, identity). */
+hptb_status hptb_arange(hptb_ctx* ctx, hptb_tensor* out, const void* start, const void* step, void* stream);
+hptb_status hptb_eye(hptb_ctx* ctx, hptb_tensor* out, int64_t k, void* stream);
 
 /* ---- multi-GPU (new: the reference has no collectives) ---------------------------------- */
 #define HPTB_NCCL_ID_BYTES 128

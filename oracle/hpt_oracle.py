@@ -592,6 +592,23 @@ def softmax(x, xd, axis, log=False):
         return from_compute(r.astype(np.float32), od), od
 
 
+def layernorm(x, xd, n_normalized_dims, gamma=None, beta=None, eps=1e-5):
+    """(f64 reference, output dtype): hpt/src/backends/cpu/tensor_internal/normalization.rs:49-200 — over the last
+    n dims, (x − mean) / sqrt(var + eps) with the population variance, then gamma·y + beta; output
+    FloatOutBinaryPromote<T,T>.  Returned unrounded (f64) for a tolerance check."""
+    od = float_out_binary(xd, xd)
+    v = to_compute(cast(x, xd, od), od).astype(np.float64)
+    axes = tuple(range(v.ndim - n_normalized_dims, v.ndim))
+    mean = v.mean(axis=axes, keepdims=True)
+    var = ((v - mean) ** 2).mean(axis=axes, keepdims=True)
+    y = (v - mean) / np.sqrt(var + eps)
+    if gamma is not None:
+        y = y * np.asarray(gamma, dtype=np.float64)
+    if beta is not None:
+        y = y + np.asarray(beta, dtype=np.float64)
+    return y, od
+
+
 def mean_var(x, xd, axes):
     x = np.asarray(x, dtype=NP[xd])
     axes = tuple(process_axes(axes, x.ndim))

@@ -112,8 +112,12 @@ extern "C" {
                          mean_out: *mut hptb_tensor, var_out: *mut hptb_tensor, stream: *mut c_void) -> hptb_status;
     pub fn hptb_softmax(ctx: *mut hptb_ctx, inp: *const hptb_tensor, axis: c_int, log: c_int,
                         out: *mut hptb_tensor, stream: *mut c_void) -> hptb_status;
+    pub fn hptb_layernorm(ctx: *mut hptb_ctx, inp: *const hptb_tensor, n_normalized_dims: c_int, gamma: *const hptb_tensor,
+                          beta: *const hptb_tensor, eps: c_double, out: *mut hptb_tensor, stream: *mut c_void) -> hptb_status;
     pub fn hptb_copy(ctx: *mut hptb_ctx, inp: *const hptb_tensor, out: *mut hptb_tensor, stream: *mut c_void) -> hptb_status;
     pub fn hptb_fill(ctx: *mut hptb_ctx, out: *mut hptb_tensor, scalar: *const c_void, stream: *mut c_void) -> hptb_status;
+    pub fn hptb_arange(ctx: *mut hptb_ctx, out: *mut hptb_tensor, start: *const c_void, step: *const c_void, stream: *mut c_void) -> hptb_status;
+    pub fn hptb_eye(ctx: *mut hptb_ctx, out: *mut hptb_tensor, k: i64, stream: *mut c_void) -> hptb_status;
     pub fn hptb_comm_unique_id(id128: *mut c_void) -> hptb_status;
     pub fn hptb_comm_init_rank(ctx: *mut hptb_ctx, nranks: c_int, rank: c_int, id128: *const c_void,
                                out: *mut *mut hptb_comm) -> hptb_status;

@@ -167,3 +167,99 @@ def test_mean_var_extension(hb):
         eps = {"f16": 2.0 ** -10, "bf16": 2.0 ** -7, "f32": 2.0 ** -23}[od]
         assert np.all(np.abs(gm - wm) <= 2 * eps * np.abs(wm) + 1e-6)
         assert np.all(np.abs(gv - wv) <= 2 * eps * np.abs(wv) + 1e-6)
+
+
+@pytest.mark.gpu
+def test_layernorm(hb):
+    """NormalizationOps::layernorm vs the oracle (reference test: hpt-tests/src/hpt/cpu/softmax.rs:56-80, shapes
+    [.., normalized] with gamma and beta against torch at 1e-5): register-resident rows, long rows, every dtype,
+    sliced rows, optional gamma / beta."""
+    rng = np.random.default_rng(51)
+    EPS = {"f16": 2.0 ** -10, "bf16": 2.0 ** -7, "f32": 2.0 ** -23, "f64": 2.0 ** -52}
+
+    def check(x, d, ns, use_g, use_b, view=None, eps=1e-5):
+        od = O.float_out_binary(d, d)
+        L = tuple(x.shape[len(x.shape) - ns:])
+        g = rand(rng, L, od) if use_g else None
+        b = rand(rng, L, od) if use_b else None
+        X = hb.Tensor.to_cuda(to_torch(x, d))
+        xv = x
+        if view:
+            X, xv = view(X), view(x)
+        G = hb.Tensor.to_cuda(to_torch(g, od)) if use_g else None
+        B = hb.Tensor.to_cuda(to_torch(b, od)) if use_b else None
+        got_t = X.layernorm(xv.shape[xv.ndim - ns:], G, B, eps)
+        assert got_t.dtype == ENUM[od] and tuple(got_t.shape) == tuple(xv.shape)
+        ref, _ = O.layernorm(xv, d, ns, g, b, eps)
+        got = np.asarray(to_numpy(got_t.to_cpu(), od), np.float64)
+        tol = 4 * EPS[od] * np.maximum(1.0, np.abs(ref)) + (2e-6 if od == "f32" else 0.0)
+        assert (np.abs(got - ref) <= tol).all(), f"layernorm {d} {xv.shape} ns={ns}: max err {np.abs(got - ref).max()}"
+
+    for d in DTYPES:
+        x = rand(rng, (6, 5, 64), d, 0, 20) if d in O.INTS else rand(rng, (6, 5, 64), d)
+        check(x, d, 1, True, True)
+    for shape, ns in (((3, 7, 13), 1), ((33, 1024), 1), ((5, 4096), 1), ((2, 3, 8192), 1), ((3, 20000), 1), ((4, 6, 32, 48), 2),
+                      ((2, 3, 4, 5), 3), ((7, 129), 1)):
+        x = rand(rng, shape, "f32")
+        check(x, "f32", ns, True, True)
+        check(x, "f32", ns, False, True)
+        check(x, "f32", ns, True, False)
+        check(x, "f32", ns, False, False)
+    x = rand(rng, (40, 12, 256), "f32")
+    check(x, "f32", 1, True, True, view=lambda t: t[3:30:2, 1:9])   # strided kept dims, contiguous rows
+    check(rand(rng, (16, 512), "bf16"), "bf16", 1, True, True)
+    with pytest.raises(hb.HptError):
+        hb.Tensor.to_cuda(to_torch(x, "f32")).layernorm((128,))
+
+
+@pytest.mark.gpu
+def test_creation_ops(hb):
+    """TensorCreator (normal_creation.rs:34-234): zeros / ones / full / arange / arange_step / linspace / eye, bit-exact
+    against the reference formula `start + T(i)·step` evaluated with a rounding per step in T."""
+    from hpt_b200 import _ffi
+
+    def host_arange(n, start, step, d):
+        i = O.cast(np.arange(n, dtype=np.uint64), "u64", d)
+        if d == "bool":
+            return np.logical_or(np.bool_(start), np.logical_and(i, np.bool_(step)))
+        st = O.cast(np.array([step], dtype=np.float64 if d in O.FLOATS else np.int64), "f64" if d in O.FLOATS else "i64", d)
+        s0 = O.cast(np.array([start], dtype=np.float64 if d in O.FLOATS else np.int64), "f64" if d in O.FLOATS else "i64", d)
+        prod, _ = O.binary("mul", i, d, st, d)
+        r, _ = O.binary("add", s0, d, prod, d)
+        return r
+
+    for d in DTYPES:
+        e = ENUM[d]
+        z = hb.Tensor.zeros((3, 5), e).to_cpu()
+        o = hb.Tensor.ones((3, 5), e).to_cpu()
+        assert (to_numpy(z, d) == 0).all() and (to_numpy(o, d) == 1).all()
+        if d == "bool":
+            continue
+        lo, hi = (2, 40)
+        got = to_numpy(hb.Tensor.arange(lo, hi, e).to_cpu(), d)
+        assert_exact(got, host_arange(hi - lo, lo, 1, d), d, f"arange {d}")
+        step = 3 if d in O.INTS else 0.37
+        n = int(np.floor((hi - lo) / step)) + 1
+        got = to_numpy(hb.Tensor.arange_step(lo, hi, step, e).to_cpu(), d)
+        assert got.shape == (n,)
+        assert_exact(got, host_arange(n, lo, step, d), d, f"arange_step {d}")
+        f = to_numpy(hb.Tensor.full(7, (4, 9), e).to_cpu(), d)
+        assert (f == 7).all()
+    assert hb.Tensor.arange(5, 5, hb.I64).shape == (0,)
+    for d in ("f32", "f64", "f16", "bf16"):
+        for inc in (True, False):
+            num = 57
+            got = to_numpy(hb.Tensor.linspace(-1.5, 4.0, num, inc, ENUM[d]).to_cpu(), d)
+            step = (4.0 + 1.5) / ((num - 1.0) if inc else num)
+            want = host_arange(num, -1.5, step, d)
+            if inc:
+                want[-1] = O.cast(np.array([4.0]), "f64", d)[0]
+            assert_exact(got, want, d, f"linspace {d} inc={inc}")
+    for d in ("f32", "i64", "bool", "bf16"):
+        for n, m, k in ((5, 7, 0), (6, 4, 1), (3, 3, 2)):
+            got = to_numpy(hb.Tensor.eye(n, m, k, ENUM[d]).to_cpu(), d)
+            want = np.eye(n, m, k)
+            assert (got.astype(np.float64) == want).all(), f"eye {d} {n},{m},{k}"
+    assert (hb.Tensor.identity(4, hb.F32).to_cpu().numpy() == np.eye(4)).all()
+    big = hb.Tensor.arange(0, 1 << 20, hb.F32).to_cpu().numpy()
+    assert (big == np.arange(1 << 20, dtype=np.float32)).all()
