@@ -122,6 +122,7 @@ SIGNATURES = {
     "hptb_comm_unique_id": (c_int, [c_void_p]),
     "hptb_comm_init_rank": (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(c_void_p)]),
     "hptb_comm_destroy": (c_int, [c_void_p]),
+    "hptb_comm_uses_peer_memory": (c_int, [c_void_p]),
     "hptb_shard_bounds": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
     "hptb_shard_plan_reduce": (c_int, [c_int, POINTER(c_int32), c_int, c_int, c_int, POINTER(HptbShardPlan)]),
     "hptb_allreduce": (c_int, [c_void_p, c_int, _T, c_void_p]),

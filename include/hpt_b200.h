@@ -257,6 +257,9 @@ hptb_status hptb_eye(hptb_ctx* ctx, hptb_tensor* out, int64_t k, void* stream);
 hptb_status hptb_comm_unique_id(void* id128);                          /* rank 0, then broadcast out of band */
 hptb_status hptb_comm_init_rank(hptb_ctx* ctx, int nranks, int rank, const void* id128, hptb_comm** out);
 hptb_status hptb_comm_destroy(hptb_comm* comm);
+/* 1 if small partials are exchanged through peer-mapped mailboxes (CUDA IPC over NVLink, one kernel per rank),
+ * 0 if every exchange goes through NCCL (IPC unavailable, or HPTB_NO_P2P=1). */
+int hptb_comm_uses_peer_memory(const hptb_comm* comm);
 /* Outer-axis sharding helpers (pure host code, usable without a GPU).
  * hptb_shard_bounds: rank r of `world` owns rows [offset, offset+len) of an axis of length n — contiguous
  * blocks, the first n % world ranks one row longer.

@@ -122,6 +122,7 @@ extern "C" {
     pub fn hptb_comm_init_rank(ctx: *mut hptb_ctx, nranks: c_int, rank: c_int, id128: *const c_void,
                                out: *mut *mut hptb_comm) -> hptb_status;
     pub fn hptb_comm_destroy(comm: *mut hptb_comm) -> hptb_status;
+    pub fn hptb_comm_uses_peer_memory(comm: *const hptb_comm) -> c_int;
     pub fn hptb_shard_bounds(n: i64, world: c_int, rank: c_int, offset: *mut i64, len: *mut i64) -> hptb_status;
     pub fn hptb_shard_plan_reduce(op: c_int, axes: *const i32, naxes: c_int, shard_axis: c_int, world: c_int,
                                   plan: *mut hptb_shard_plan) -> hptb_status;

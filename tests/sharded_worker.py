@@ -22,6 +22,7 @@ def main():
 
     hb.set_stream(torch.cuda.current_stream().cuda_stream)
     comm = hb.Comm.from_torch_distributed(hb.context(local))
+    p2p = hb.lib.hptb_comm_uses_peer_memory(comm.handle)
     rng = np.random.default_rng(11)  # identical data on every rank
     checked = 0
     for d in ("f32", "f64", "bf16", "f16", "i32", "i64", "u8", "bool"):
@@ -58,7 +59,7 @@ def main():
     dist.barrier()
     comm.destroy()
     dist.destroy_process_group()
-    print(f"rank {rank}: sharded ok ({checked} cases)")
+    print(f"rank {rank}: sharded ok ({checked} cases, peer memory {p2p})")
 
 
 if __name__ == "__main__":
