@@ -64,6 +64,12 @@ def run_rows(hb, torch, dist, world, rank, local, stream, peak):
         add_row("cfg1", "add f32 [4096,4096]+[1,4096]", us, 134234112, 16777216, "rotating 4 buffer sets")
         us = _timeit(torch, stream, [lambda i=i: C[i].sum_([1], False, True, S[i]) for i in range(R)], 200)
         add_row("cfg1", "sum(axis 1) f32 [4096,4096]", us, 67125248, 16777216, "rotating 4 buffer sets")
+        ax1 = (c_int32 * 1)(1)
+        fused = [lambda i=i: _ffi.check(hb.lib.hptb_binary_reduce(A[i].ctx.handle, _ffi.BINARY_OPS["add"], _ffi.REDUCE_OPS["sum"], byref(A[i]._c()),
+                                                                  byref(B[i]._c()), ax1, 1, byref(S[i]._c()), 1, hb.get_stream())) for i in range(R)]
+        us = _timeit(torch, stream, fused, 200)
+        add_row("cfg1", "EXTRA fused (A + B).sum(1) in one pass (hptb_binary_reduce)", us, 67125248 + 16384, 16777216,
+                "bytes = one read of A and B + the [4096] result; the unfused pair above moves 201 MB")
         del A, B, C, S
 
     # ---- config 3: bf16/f16 [64,512,56,56] NCHW viewed NHWC, mean over (0,1,2) ---------------------------------

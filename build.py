@@ -59,6 +59,8 @@ def units():
         u.append((f"dyn_{short}", "dyn_inst.cu", f"-DHPTB_OUT={cty} -DHPTB_OUTNAME={short} -DHPTB_OUT_FLOAT={is_float}"))
     for name in REDUCE_OPS:
         u.append((f"reduce_{name}", "reduce_inst.cu", f"-DHPTB_OPENUM=HPTB_{name.upper()} -DHPTB_OPNAME={name}"))
+    for fn, name in (("OpAdd", "add"), ("OpSub", "sub"), ("OpMul", "mul")):
+        u.append((f"fused_{name}", "fused_inst.cu", f"-DHPTB_OP={fn} -DHPTB_OPNAME={name}"))
     for src in ("softmax.cu", "misc.cu", "meanvar.cu", "sharded.cu"):
         if os.path.exists(os.path.join(CSRC, src)):
             u.append((src[:-3], src, ""))

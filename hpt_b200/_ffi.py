@@ -112,6 +112,7 @@ SIGNATURES = {
     "hptb_compare": (c_int, [c_void_p, c_int, _T, _T, _T, c_void_p]),
     "hptb_unary": (c_int, [c_void_p, c_int, _T, _T, c_double, c_double, c_void_p]),
     "hptb_reduce": (c_int, [c_void_p, c_int, _T, POINTER(c_int32), c_int, _T, c_int, c_void_p]),
+    "hptb_binary_reduce": (c_int, [c_void_p, c_int, c_int, _T, _T, POINTER(c_int32), c_int, _T, c_int, c_void_p]),
     "hptb_mean_var": (c_int, [c_void_p, _T, POINTER(c_int32), c_int, _T, _T, c_void_p]),
     "hptb_softmax": (c_int, [c_void_p, _T, c_int, c_int, _T, c_void_p]),
     "hptb_layernorm": (c_int, [c_void_p, _T, c_int, _T, _T, c_double, _T, c_void_p]),

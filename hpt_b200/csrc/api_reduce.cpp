@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "dtypes_x.h"
+#include "map_plan.h"
 #include "promote.h"
 #include "reduce_plan.h"
 
@@ -30,6 +31,11 @@ HPTB_WEAK hptb::ReduceLauncher hptb_reduce_all(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_any(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_reducel2(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_reducel3(int);
+HPTB_WEAK hptb::FusedLauncher hptb_fused_add(int);
+HPTB_WEAK hptb::FusedLauncher hptb_fused_sub(int);
+HPTB_WEAK hptb::FusedLauncher hptb_fused_mul(int);
+int hptb_binary_out_dtype(int op, int lhs, int rhs);
+hptb_status hptb_binary(hptb_ctx*, int, const hptb_tensor*, const hptb_tensor*, hptb_tensor*, void*);
 }
 
 namespace hptb {
@@ -204,3 +210,78 @@ hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int3
   return st;
 }
 }  // namespace hptb
+
+
+// ---- elementwise → reduce fusion ------------------------------------------------------------------------------------
+extern "C" hptb_status hptb_binary_reduce(hptb_ctx* ctx, int bin_op, int red_op, const hptb_tensor* lhs, const hptb_tensor* rhs,
+                                          const int32_t* axes, int naxes, hptb_tensor* out, int init_out, void* stream) {
+  if (!ctx) return fail(HPTB_ERR_INVALID, "binary_reduce: null ctx");
+  if (!axes && naxes) return fail(HPTB_ERR_INVALID, "binary_reduce: null axes");
+  if (red_op < 0 || red_op >= HPTB_REDUCE_COUNT) return fail(HPTB_ERR_INVALID, "binary_reduce: bad reduce op %d", red_op);
+  HPTB_TRY(validate_tensor(lhs, "binary_reduce lhs"));
+  HPTB_TRY(validate_tensor(rhs, "binary_reduce rhs"));
+  HPTB_TRY(validate_tensor(out, "binary_reduce out"));
+  const int mid = hptb_binary_out_dtype(bin_op, lhs->dtype, rhs->dtype);
+  if (mid < 0)
+    return fail(HPTB_ERR_DTYPE, "binary op %d is not supported for (%s, %s)", bin_op, dtype_name(lhs->dtype), dtype_name(rhs->dtype));
+  const int odt = hptb_reduce_out_dtype(red_op, mid);
+  if (out->dtype != odt) return fail(HPTB_ERR_DTYPE, "binary_reduce: out dtype is %s, expected %s", dtype_name(out->dtype), dtype_name(odt));
+  // the elementwise result (never materialised on the fast path): broadcast shape of the operands
+  hptb_tensor tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  HPTB_TRY(broadcast_shape(lhs->shape, lhs->ndim, rhs->shape, rhs->ndim, tmp.shape, &tmp.ndim));
+  tmp.dtype = mid;
+  int64_t numel_mid = 1;
+  for (int i = tmp.ndim - 1; i >= 0; --i) { tmp.strides[i] = numel_mid; numel_mid *= tmp.shape[i]; }
+  FusedLauncher fn = nullptr;
+  if (lhs->dtype == mid && rhs->dtype == mid) {
+    if (bin_op == HPTB_ADD && hptb_fused_add) fn = hptb_fused_add(mid);
+    else if (bin_op == HPTB_SUB && hptb_fused_sub) fn = hptb_fused_sub(mid);
+    else if (bin_op == HPTB_MUL && hptb_fused_mul) fn = hptb_fused_mul(mid);
+  }
+  if (fn && numel_mid > 0) {
+    // same plan as hptb_reduce on the (virtual) elementwise result, with both inputs' broadcast strides
+    uint8_t mask[HPTB_MAX_DIMS] = {0};
+    bool ok = true;
+    for (int i = 0; i < naxes && ok; ++i) {
+      if (axes[i] < 0 || axes[i] >= tmp.ndim || mask[axes[i]]) ok = false;
+      else mask[axes[i]] = 1;
+    }
+    if (!ok) return fail(HPTB_ERR_AXIS, "binary_reduce: bad axes");
+    int64_t oshape[HPTB_MAX_DIMS];
+    int on = 0;
+    double count = 1.0;
+    for (int i = 0; i < tmp.ndim; ++i) {
+      if (mask[i]) count *= (double)tmp.shape[i];
+      else oshape[on++] = tmp.shape[i];
+    }
+    if (on == 0) { oshape[0] = 1; on = 1; }
+    bool same = out->ndim == on;
+    for (int i = 0; same && i < on; ++i) same = out->shape[i] == oshape[i];
+    if (!same) return fail(HPTB_ERR_SHAPE, "binary_reduce: out shape does not match the reduced broadcast shape");
+    int64_t strides[kMaxOperands][HPTB_MAX_DIMS] = {{0}};
+    int k = 0;
+    for (int i = 0; i < tmp.ndim; ++i) strides[0][i] = mask[i] ? 0 : out->strides[k++];
+    HPTB_TRY(broadcast_strides(*lhs, tmp.shape, tmp.ndim, strides[1]));
+    HPTB_TRY(broadcast_strides(*rhs, tmp.shape, tmp.ndim, strides[2]));
+    FusedPlan plan;
+    collapse(tmp.ndim, tmp.shape, 3, strides, mask, &plan.c);
+    plan.lhs = lhs->data;
+    plan.rhs = rhs->data;
+    plan.out = out->data;
+    plan.count = count;
+    plan.fold_out = init_out ? 0 : 1;
+    plan.red_op = red_op;
+    plan.ctx = ctx;
+    DeviceGuard g(ctx->device);
+    hptb_status st = fn(plan, (cudaStream_t)stream);
+    if (st == HPTB_OK) { count_launches(1); return HPTB_OK; }
+    if (st != HPTB_FALLBACK) return st;
+  }
+  // composition through a temporary: exactly the two calls the fused kernel stands for
+  Scratch scratch;
+  HPTB_TRY(scratch.get(ctx, (size_t)(numel_mid > 0 ? numel_mid : 1) * dtype_size(mid), stream));
+  tmp.data = scratch.ptr;
+  HPTB_TRY(hptb_binary(ctx, bin_op, lhs, rhs, &tmp, stream));
+  return hptb_reduce(ctx, red_op, &tmp, axes, naxes, out, init_out, stream);
+}

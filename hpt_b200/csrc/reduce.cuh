@@ -40,9 +40,6 @@ constexpr int kRedThreads = 256;
 #ifndef HPTB_LEAN_MINB
 #define HPTB_LEAN_MINB 6
 #endif
-#ifndef HPTB_RED_PIPE
-#define HPTB_RED_PIPE 0
-#endif
 constexpr int kRedMaxDims = HPTB_MAX_DIMS;
 
 // ---- op traits ---------------------------------------------------------------------------------------
@@ -571,67 +568,6 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
       runp = base + run_offset(r);
     }
     int32_t it = 0;
-#if HPTB_RED_PIPE
-    // Software pipeline: the loads of batch k+1 are issued BEFORE batch k is consumed, so every thread keeps
-    // UNROLL..2·UNROLL 16-byte loads in flight for the whole loop instead of oscillating between UNROLL and 0
-    // (bytes in flight per SM, not issue slots, bound these kernels: Little's law needs ≈ 45 KB per SM).
-    // Full batches carry no predicates; the ≤ UNROLL-1 leftover chunks of a thread are handled one by one.
-    auto next_src = [&]() -> const T* {
-      const T* src = runp + (int64_t)col * estride;
-      col += (uint32_t)G;
-      if (col >= cpr_eff) {
-        do { col -= cpr_eff; ++r; } while (col >= cpr_eff);
-        runp = base + run_offset(r);
-      }
-      return src;
-    };
-    auto load_batch = [&](Pack<T, VEC> (&v)[UNROLL]) {
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const T* src = next_src();
-        if constexpr (VEC > 1) load_pack<T, VEC>(v[u], src);
-        else v[u].v[0] = load_one(src);
-      }
-    };
-    auto consume = [&](const Pack<T, VEC> (&v)[UNROLL]) {
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) Op::template accumulate_pack<VEC>(acc, v[u], it + u);
-      it += UNROLL;
-    };
-    const uint32_t mine = (uint32_t)g < n_local ? (n_local - (uint32_t)g + (uint32_t)G - 1) / (uint32_t)G : 0u;  // chunks of this thread
-    uint32_t batches = mine / UNROLL;
-    const uint32_t tail = mine - batches * UNROLL;
-    Pack<T, VEC> va[UNROLL], vb[UNROLL];
-    if (batches) load_batch(va);
-    while (batches >= 2) {
-      load_batch(vb);
-      consume(va);
-      --batches;
-      if (batches >= 2) {
-        load_batch(va);
-        consume(vb);
-        --batches;
-      } else {
-        consume(vb);
-        batches = 0;
-      }
-    }
-    if (batches) consume(va);
-    if (tail) {
-      Pack<T, VEC> vt[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL - 1; ++u) {
-        if ((uint32_t)u < tail) {
-          const T* src = next_src();
-          if constexpr (VEC > 1) load_pack<T, VEC>(vt[u], src);
-          else vt[u].v[0] = load_one(src);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL - 1; ++u)
-        if ((uint32_t)u < tail) Op::template accumulate_pack<VEC>(acc, vt[u], it + u);
-    }
-#else
     for (uint32_t lc = (uint32_t)g; lc < n_local; lc += (uint32_t)G * UNROLL, it += UNROLL) {
       Pack<T, VEC> v[UNROLL];
       bool ok[UNROLL];
@@ -655,7 +591,6 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
         Op::template accumulate_pack<VEC>(acc, v[u], it + u);
       }
     }
-#endif
   }
   // thread total; for arg reductions the element index of (iteration it, slot k) is ((c_begin + g) + it·G)·VEC + k
   // (exactly one reduced dim, so chunk number == column)

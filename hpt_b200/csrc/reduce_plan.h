@@ -15,6 +15,19 @@ struct ReducePlan {
 };
 typedef hptb_status (*ReduceLauncher)(const ReducePlan&, cudaStream_t);
 
+// elementwise → reduce fusion (fused_inst.cu)
+struct FusedPlan {
+  Collapsed c;  // operand 0 = out (stride 0 on reduced dims), 1 = lhs, 2 = rhs (broadcast strides)
+  const void* lhs = nullptr;
+  const void* rhs = nullptr;
+  void* out = nullptr;
+  double count = 1.0;
+  int fold_out = 0;
+  int red_op = 0;
+  hptb_ctx* ctx = nullptr;
+};
+typedef hptb_status (*FusedLauncher)(const FusedPlan&, cudaStream_t);
+
 // zero-initialised, self-resetting ticket counters for single-launch split reductions (one buffer per stream)
 uint32_t* ctx_tickets(hptb_ctx* ctx, cudaStream_t stream, size_t n);
 void ctx_tickets_destroy(hptb_ctx* ctx);

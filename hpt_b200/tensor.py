@@ -506,6 +506,33 @@ class Tensor:
     def all(self, axes, keep_dims=False): return self._reduce("all", axes, keep_dims)
     def any(self, axes, keep_dims=False): return self._reduce("any", axes, keep_dims)
 
+    def binary_reduce(self, bin_name, rhs, red_name, axes, keep_dims=False, out=None, stream=None):
+        """Extension: `reduce(self ⊕ rhs, axes)` in one pass (hptb_binary_reduce); same result as `(self ⊕ rhs).red(axes)`."""
+        bop, rop = _ffi.BINARY_OPS[bin_name], _ffi.REDUCE_OPS[red_name]
+        mid = lib.hptb_binary_out_dtype(bop, self.dtype, rhs.dtype)
+        if mid < 0:
+            raise HptError(2, f"{bin_name} is not supported for ({_ffi.DTYPE_NAMES[self.dtype]}, {_ffi.DTYPE_NAMES[rhs.dtype]})")
+        odt = lib.hptb_reduce_out_dtype(rop, mid)
+        bshape = (c_int64 * _ffi.MAX_DIMS)()
+        bn = c_int()
+        check(lib.hptb_broadcast_shape((c_int64 * max(self.ndim, 1))(*self.shape), self.ndim,
+                                       (c_int64 * max(rhs.ndim, 1))(*rhs.shape), rhs.ndim, bshape, byref(bn)))
+        ax_in = _axes_list(axes)
+        ax = (c_int32 * max(len(ax_in), 1))()
+        check(lib.hptb_process_axes((c_int64 * max(len(ax_in), 1))(*ax_in), len(ax_in), bn.value, ax))
+        oshape = (c_int64 * _ffi.MAX_DIMS)()
+        on = c_int()
+        check(lib.hptb_reduce_shape(bshape, bn.value, ax, len(ax_in), 0, oshape, byref(on)))
+        red_shape = tuple(oshape[i] for i in range(on.value))
+        res = out if out is not None else Tensor.empty(red_shape, odt, self.ctx.device, stream)
+        check(lib.hptb_binary_reduce(self.ctx.handle, bop, rop, byref(self._c()), byref(rhs._c()), ax, len(ax_in),
+                                     byref(res._c()), 1, _s(stream)))
+        if keep_dims:
+            check(lib.hptb_reduce_shape(bshape, bn.value, ax, len(ax_in), 1, oshape, byref(on)))
+            ks = tuple(oshape[i] for i in range(on.value))
+            res = Tensor(res.storage, res.ptr, res.dtype, ks, _contig_strides(ks))
+        return res
+
     def mean_var(self, axes, stream=None):
         """Extension (Hpt has no `var`): fused single-read population mean and variance."""
         ax_in = _axes_list(axes)

@@ -226,6 +226,13 @@ hptb_status hptb_unary(hptb_ctx* ctx, int op, const hptb_tensor* in, hptb_tensor
  * freshly allocated output. */
 hptb_status hptb_reduce(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes,
                         hptb_tensor* out, int init_out, void* stream);
+/* Elementwise → reduce fusion (conceptual hook: hpt-codegen/src/fuse/*): out = reduce_<red_op>(
+ * lhs <bin_op> rhs, axes), with exactly the semantics of hptb_binary followed by hptb_reduce but — for same-dtype
+ * add / sub / mul feeding sum / max / min / sum_square over a unit-stride axis — computed in ONE pass that never
+ * writes the elementwise result (config 1: (A + B).sum(1) reads 67 MB instead of moving 201 MB).  Other
+ * combinations run the two kernels through a pooled temporary. */
+hptb_status hptb_binary_reduce(hptb_ctx* ctx, int bin_op, int red_op, const hptb_tensor* lhs, const hptb_tensor* rhs,
+                               const int32_t* axes, int naxes, hptb_tensor* out, int init_out, void* stream);
 /* Fused single-read mean + variance (population, ddof = 0) — an EXTENSION: Hpt has no `var`
  * (SURVEY.md §8a row a7); both outputs have dtype FloatOutBinaryPromote<T,T>. */
 hptb_status hptb_mean_var(hptb_ctx* ctx, const hptb_tensor* in, const int32_t* axes, int naxes,

@@ -108,6 +108,8 @@ extern "C" {
                       alpha: c_double, beta: c_double, stream: *mut c_void) -> hptb_status;
     pub fn hptb_reduce(ctx: *mut hptb_ctx, op: c_int, inp: *const hptb_tensor, axes: *const i32, naxes: c_int,
                        out: *mut hptb_tensor, init_out: c_int, stream: *mut c_void) -> hptb_status;
+    pub fn hptb_binary_reduce(ctx: *mut hptb_ctx, bin_op: c_int, red_op: c_int, lhs: *const hptb_tensor, rhs: *const hptb_tensor,
+                              axes: *const i32, naxes: c_int, out: *mut hptb_tensor, init_out: c_int, stream: *mut c_void) -> hptb_status;
     pub fn hptb_mean_var(ctx: *mut hptb_ctx, inp: *const hptb_tensor, axes: *const i32, naxes: c_int,
                          mean_out: *mut hptb_tensor, var_out: *mut hptb_tensor, stream: *mut c_void) -> hptb_status;
     pub fn hptb_softmax(ctx: *mut hptb_ctx, inp: *const hptb_tensor, axis: c_int, log: c_int,

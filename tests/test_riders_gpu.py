@@ -214,3 +214,51 @@ def test_new_reductions_layouts_and_sizes(hb, op):
     big = rand(rng, (64, 4096), "f32", 0.99, 1.01).astype(np.float32) if op == "nanprod" else rand(rng, (64, 4096), "f32")
     _red_check(hb, op, big, "f32", [1])
     _red_check(hb, op, big, "f32", [0, 1])
+
+
+def test_fused_binary_reduce_equals_the_two_calls(hb):
+    """hptb_binary_reduce (extension, §8f rank 4): one pass, same semantics as binary followed by reduce — integer
+    results bit-exact, float sums within the sum tolerance, max/min exact; fast path (same dtype, unit-stride reduced
+    axis, row-broadcast / same-shape / scalar rhs) and the composed fallback (mixed dtypes, other axes, views)."""
+    rng = np.random.default_rng(47)
+
+    def check(x, xd, y, yd, bop, rop, axes, xv=None):
+        X, Y = hb.Tensor.to_cuda(to_torch(x, xd)), hb.Tensor.to_cuda(to_torch(y, yd))
+        if xv:
+            X, x = xv(X), xv(x)
+        mid, md = O.binary(bop, x, xd, y, yd)
+        want, od, exact = O.reduce(rop, mid, md, axes)
+        got_t = X.binary_reduce(bop, Y, rop, axes)
+        assert got_t.dtype == ENUM[od] and tuple(got_t.shape) == tuple(want.shape)
+        got = to_numpy(got_t.to_cpu(), od)
+        what = f"{bop}->{rop} {xd},{yd} {x.shape} axes={axes}"
+        two = to_numpy(getattr(X._binary(bop, Y), rop)(axes).to_cpu(), od)  # the unfused pair on the device
+        if exact or od in INTB:
+            assert_exact(got, want, od, what)
+            assert_exact(got, two, od, what + " vs unfused")
+            return
+        n = max(2, int(np.prod([mid.shape[a] for a in O.process_axes(axes, mid.ndim)])))
+        ref = O.reduce_f64(rop, mid, md, axes).reshape(want.shape)
+        mag = O.reduce_f64("sum", np.abs(O.to_compute(mid, md).astype(np.float64)) ** (2 if rop == "sum_square" else 1), "f64", axes).reshape(want.shape)
+        tol = 1e-6 * math.log2(n) * np.maximum(np.abs(ref), mag)
+        ok = (np.abs(np.asarray(got, np.float64) - ref) <= tol) | (O.ulp_diff(got, want, od) <= 1)
+        assert ok.all(), what
+
+    a, b = rand(rng, (96, 4096), "f32"), rand(rng, (1, 4096), "f32")
+    for bop in ("add", "sub", "mul"):
+        for rop in ("sum", "max", "min", "sum_square"):
+            check(a, "f32", b, "f32", bop, rop, [1])                       # config 1 shape class: row broadcast
+    check(a, "f32", rand(rng, (96, 4096), "f32"), "f32", "add", "sum", [1])  # same shape
+    check(a, "f32", rand(rng, (1,), "f32"), "f32", "mul", "max", [1])        # scalar rhs
+    check(a, "f32", rand(rng, (96, 1), "f32"), "f32", "add", "sum", [1])     # column broadcast: one rhs element per row
+    for d in ("i32", "i64", "bf16", "f16", "f64", "u8"):
+        x = rand(rng, (33, 512), d, -50, 50) if d in O.INTS else rand(rng, (33, 512), d)
+        y = rand(rng, (1, 512), d, -50, 50) if d in O.INTS else rand(rng, (1, 512), d)
+        check(x, d, y, d, "add", "sum", [1])
+        check(x, d, y, d, "mul", "max", [1])
+    # fallbacks: mixed dtypes, reduce over the outer axis, all axes, a sliced view, mean
+    check(a, "f32", rand(rng, (4096,), "i64", -5, 5), "i64", "add", "sum", [1])
+    check(a, "f32", b, "f32", "add", "sum", [0])
+    check(a, "f32", b, "f32", "add", "sum", [0, 1])
+    check(a, "f32", rand(rng, (1, 1365), "f32"), "f32", "add", "sum", [1], xv=lambda t: t[::2, 1::3])
+    check(a, "f32", b, "f32", "add", "mean", [1])

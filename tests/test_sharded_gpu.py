@@ -11,14 +11,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-def test_sharded_reductions_two_ranks():
+@pytest.mark.parametrize("no_p2p", ["0", "1"])
+def test_sharded_reductions_two_ranks(no_p2p):
+    """no_p2p = 0: tiny partials go through the peer-memory mailbox kernel; 1: everything through NCCL."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, HPTB_NO_P2P=no_p2p)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(29400 + os.getpid() % 500), os.path.join(ROOT, "tests", "sharded_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-4000:] + "\n" + r.stderr[-4000:]
     assert r.stdout.count("sharded ok") == 2, r.stdout[-2000:]
+    if no_p2p == "1":
+        assert "peer memory 0" in r.stdout
 
 
 @pytest.mark.gpu
