@@ -58,7 +58,8 @@ def units():
         is_float = 1 if short in ("f16", "bf16", "f32", "f64") else 0
         u.append((f"dyn_{short}", "dyn_inst.cu", f"-DHPTB_OUT={cty} -DHPTB_OUTNAME={short} -DHPTB_OUT_FLOAT={is_float}"))
     for name in REDUCE_OPS:
-        u.append((f"reduce_{name}", "reduce_inst.cu", f"-DHPTB_OPENUM=HPTB_{name.upper()} -DHPTB_OPNAME={name}"))
+        u.append((f"reduce_{name}", "reduce_inst.cu", f"-DHPTB_OPENUM=HPTB_{name.upper()} -DHPTB_OPNAME={name}"
+                  + (" -DHPTB_LOGSUMEXP_LONG=1" if name == "logsumexp" else "")))
     for fn, name in (("OpAdd", "add"), ("OpSub", "sub"), ("OpMul", "mul")):
         u.append((f"fused_{name}", "fused_inst.cu", f"-DHPTB_OP={fn} -DHPTB_OPNAME={name}"))
     for src in ("softmax.cu", "misc.cu", "meanvar.cu", "sharded.cu"):

@@ -60,7 +60,7 @@ class HptbCollapsePlan(Structure):
 
 class HptbShardPlan(Structure):
     _fields_ = [("crosses", c_int32), ("collective", c_int32), ("pre_exp", c_int32), ("post_ln", c_int32),
-                ("global_count", c_int32)]
+                ("global_count", c_int32), ("post_root", c_int32)]
 
 
 COLLECTIVES = ["none", "allreduce_sum", "allreduce_prod", "allreduce_max", "allreduce_min", "allgather_arg"]

@@ -132,6 +132,7 @@ static hptb_status run_map(hptb_ctx* ctx, MapLauncher fast, MapLauncher dyn, int
   plan.in_dtype[0] = in0->dtype;
   plan.in_dtype[1] = in1 ? in1->dtype : -1;
   plan.op = op;
+  pass_direction(ctx, in0->data, 0, false);  // a forward streaming pass over in0 (snake order, context.h)
   DeviceGuard g(ctx->device);
   hptb_status st = fast ? fast(plan, (cudaStream_t)stream) : HPTB_FALLBACK;
   if (st == HPTB_FALLBACK) {

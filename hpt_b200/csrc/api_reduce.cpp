@@ -22,6 +22,7 @@ HPTB_WEAK hptb::ReduceLauncher hptb_reduce_min(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_argmax(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_argmin(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_logsumexp(int);
+HPTB_WEAK hptb::ReduceLauncher hptb_reduce_logsumexp_long(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_sum_square(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_prod(int);
 HPTB_WEAK hptb::ReduceLauncher hptb_reduce_reducel1(int);
@@ -203,7 +204,12 @@ hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int3
   ReducePlan plan;
   HPTB_TRY(build_reduce_plan(ctx, in, axes, naxes, out, &plan));
   plan.fold_out = init_out ? 0 : 1;
+  if (op == HPTB_LOGSUMEXP && plan.count >= 512.0 && hptb_reduce_logsumexp_long) {  // kLogSumExpLongMin (reduce.cuh)
+    if (ReduceLauncher lf = hptb_reduce_logsumexp_long(in->dtype)) fn = lf;
+  }
   if (count_override > 0) plan.count = count_override;  // sharded mean: divide the local Σ by the GLOBAL count
+  if (count_override == -2.0 && (op == HPTB_REDUCEL2 || op == HPTB_REDUCEL3)) plan.count = -2.0;  // kPartialPowerSum
+  plan.reverse = pass_direction(ctx, in->data, (size_t)numel(*in) * dtype_size(in->dtype), true) ? 1 : 0;
   DeviceGuard g(ctx->device);
   hptb_status st = fn(plan, (cudaStream_t)stream);
   if (st == HPTB_OK) count_launches(1);

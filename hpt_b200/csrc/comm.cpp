@@ -18,6 +18,9 @@
 
 extern "C" hptb_status hptb_reduce(hptb_ctx*, int, const hptb_tensor*, const int32_t*, int, hptb_tensor*, int, void*);
 extern "C" hptb_status hptb_unary(hptb_ctx*, int, const hptb_tensor*, hptb_tensor*, double, double, void*);
+extern "C" hptb_status hptb_binary(hptb_ctx*, int, const hptb_tensor*, const hptb_tensor*, hptb_tensor*, void*);
+extern "C" hptb_status hptb_fill(hptb_ctx*, hptb_tensor*, const void*, void*);
+extern "C" hptb_status hptb_copy(hptb_ctx*, const hptb_tensor*, hptb_tensor*, void*);
 namespace hptb {
 hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, hptb_tensor* out,
                         int init_out, double count_override, void* stream);  // api_reduce.cpp
@@ -267,6 +270,7 @@ hptb_status hptb_shard_plan_reduce(int op, const int32_t* axes, int naxes, int s
     case HPTB_MAX: plan->collective = HPTB_COLL_ALLREDUCE_MAX; break;
     case HPTB_MIN: plan->collective = HPTB_COLL_ALLREDUCE_MIN; break;
     case HPTB_ARGMAX: case HPTB_ARGMIN: plan->collective = HPTB_COLL_ALLGATHER_ARG; break;
+    case HPTB_REDUCEL2: case HPTB_REDUCEL3: plan->collective = HPTB_COLL_ALLREDUCE_SUM; plan->post_root = op == HPTB_REDUCEL2 ? 2 : 3; break;
     default: return fail(HPTB_ERR_UNSUPPORTED, "shard_plan_reduce: op %d across the shard axis is not implemented (reduce locally and combine)", op);
   }
   return HPTB_OK;
@@ -372,6 +376,57 @@ hptb_status hptb_reduce_sharded(hptb_comm* comm, int op, const hptb_tensor* shar
     HPTB_TRY(hptb_unary(comm->ctx, HPTB_EXP, out, out, 0, 0, stream));  // back to Σ exp (naive domain, as the reference)
     HPTB_TRY(hptb_allreduce(comm, HPTB_SUM, out, stream));
     return hptb_unary(comm->ctx, HPTB_LN, out, out, 0, 0, stream);
+  }
+  if (sp.post_root) {
+    // Σ|x|^p is exchanged, then the reference's root: sqrt, or pow with the exponent 1/3 rounded to the OUTPUT dtype
+    // (reduce.cuh ReduceOp<HPTB_REDUCEL3>).  f32/f64 outputs: the local kernel leaves the power sum unrooted in `out`.
+    // f16/bf16 outputs (8- and 16-bit inputs): a power sum does not fit half precision, so the rooted local result
+    // is widened to an f32 scratch, raised to p again, exchanged and rooted there, and rounded to `out` once.
+    const bool half = out->dtype == HPTB_F16 || out->dtype == HPTB_BF16;
+    const int64_t M = numel(*out);
+    Scratch s64, sod, swide, sthird;
+    HPTB_TRY(s64.get(comm->ctx, 8, stream));
+    HPTB_TRY(sod.get(comm->ctx, 8, stream));
+    HPTB_TRY(sthird.get(comm->ctx, 8, stream));
+    hptb_tensor acc = *out;  // where the exchange happens
+    if (half) {
+      HPTB_TRY(swide.get(comm->ctx, (size_t)(M > 0 ? M : 1) * sizeof(float), stream));
+      HPTB_TRY(hptb_reduce(comm->ctx, op, shard, axes, naxes, out, 1, stream));
+      acc.data = swide.ptr;
+      acc.dtype = HPTB_F32;
+      HPTB_TRY(hptb_copy(comm->ctx, out, &acc, stream));
+      hptb_tensor base = acc;
+      Scratch sbase;
+      if (sp.post_root == 3) {  // acc = base³ needs base kept
+        HPTB_TRY(sbase.get(comm->ctx, (size_t)(M > 0 ? M : 1) * sizeof(float), stream));
+        base.data = sbase.ptr;
+        HPTB_TRY(hptb_copy(comm->ctx, &acc, &base, stream));
+        HPTB_TRY(hptb_binary(comm->ctx, HPTB_MUL, &acc, &base, &acc, stream));
+      }
+      HPTB_TRY(hptb_binary(comm->ctx, HPTB_MUL, &acc, &base, &acc, stream));
+    } else {
+      HPTB_TRY(reduce_impl(comm->ctx, op, shard, axes, naxes, out, 1, -2.0, stream));
+    }
+    HPTB_TRY(hptb_allreduce(comm, HPTB_SUM, &acc, stream));
+    if (sp.post_root == 2) {
+      HPTB_TRY(hptb_unary(comm->ctx, HPTB_SQRT, &acc, &acc, 0, 0, stream));
+    } else {
+      const double third = 1.0 / 3.0;
+      hptb_tensor t64;
+      memset(&t64, 0, sizeof(t64));
+      t64.data = s64.ptr; t64.dtype = HPTB_F64; t64.ndim = 1; t64.shape[0] = 1; t64.strides[0] = 1;
+      HPTB_TRY(hptb_fill(comm->ctx, &t64, &third, stream));
+      hptb_tensor tod = t64, tex = t64;
+      tod.data = sod.ptr; tod.dtype = out->dtype;
+      HPTB_TRY(hptb_copy(comm->ctx, &t64, &tod, stream));      // 1/3 rounded to the output dtype
+      tex.data = sthird.ptr; tex.dtype = acc.dtype;
+      HPTB_TRY(hptb_copy(comm->ctx, &tod, &tex, stream));      // … carried in the exchange dtype
+      hptb_tensor ex = acc;
+      ex.data = sthird.ptr;
+      for (int i = 0; i < ex.ndim; ++i) ex.strides[i] = 0;     // broadcast the exponent over the partials
+      HPTB_TRY(hptb_binary(comm->ctx, HPTB_POW, &acc, &ex, &acc, stream));
+    }
+    return half ? hptb_copy(comm->ctx, &acc, out, stream) : HPTB_OK;
   }
   HPTB_TRY(hptb_reduce(comm->ctx, op, shard, axes, naxes, out, 1, stream));
   return hptb_allreduce(comm, op, out, stream);

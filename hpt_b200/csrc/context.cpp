@@ -47,6 +47,17 @@ hptb_status validate_tensor(const hptb_tensor* t, const char* what) {
   return HPTB_OK;
 }
 
+bool pass_direction(hptb_ctx* ctx, const void* in, size_t bytes, bool can_reverse) {
+  static const bool off = [] { const char* e = getenv("HPTB_NO_SNAKE"); return e && e[0] == '1'; }();
+  if (!ctx) return false;
+  const void* prev = ctx->last_pass_in.exchange(in, std::memory_order_relaxed);
+  bool rev = false;
+  // only worth it when the tensor does not fit L2 anyway (a forward re-read of a resident tensor already hits)
+  if (!off && can_reverse && prev == in && bytes >= (size_t)96 << 20) rev = !ctx->last_pass_rev.load(std::memory_order_relaxed);
+  ctx->last_pass_rev.store(rev ? 1 : 0, std::memory_order_relaxed);
+  return rev;
+}
+
 DeviceGuard::DeviceGuard(int dev) {
   if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
   if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;

@@ -89,6 +89,7 @@ extern "C" hptb_status hptb_mean_var(hptb_ctx* ctx, const hptb_tensor* in, const
   bool same = mean_out->ndim == var_out->ndim;
   for (int i = 0; same && i < mean_out->ndim; ++i) same = mean_out->shape[i] == var_out->shape[i];
   if (!same) return fail(HPTB_ERR_SHAPE, "mean_var: mean_out and var_out shapes differ");
+  pass_direction(ctx, in->data, 0, false);  // a forward streaming pass (snake order, context.h)
   bool same_layout = true;
   for (int i = 0; i < mean_out->ndim; ++i)
     if (mean_out->shape[i] != 1 && mean_out->strides[i] != var_out->strides[i]) same_layout = false;

@@ -209,6 +209,8 @@ template <typename T> struct ReduceOp<HPTB_ANY, T> : PlainLocal<ReduceOp<HPTB_AN
   static __device__ __forceinline__ Out post(Acc a, double) { return a; }
   static __device__ __forceinline__ Acc from_out(Out o) { return b8{(uint8_t)(o.v != 0)}; }
 };
+// `count` value that asks REDUCEL2 / REDUCEL3 for the bare power sum (hptb_reduce_sharded exchanges Σ|x|^p, comm.cpp)
+constexpr double kPartialPowerSum = -2.0;
 // REDUCEL2 = sqrt Σ x², REDUCEL3 = (Σ |x|³)^(1/3), in FloatOutBinaryPromote<T,T> (common_reduce.rs:384-450; the
 // exponent 1/3 is rounded to the output dtype first, as the reference's `(1.0 / 3.0).cast()` does)
 template <typename T> struct ReduceOp<HPTB_REDUCEL2, T>
@@ -219,7 +221,8 @@ template <typename T> struct ReduceOp<HPTB_REDUCEL2, T>
   static __device__ __forceinline__ Acc identity() { return (Acc)0; }
   static __device__ __forceinline__ Acc pre(T x, int64_t) { const Acc c = to_compute<Out>(cast<Out>(x)); return c * c; }
   static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return a + b; }
-  static __device__ __forceinline__ Out post(Acc a, double) {
+  static __device__ __forceinline__ Out post(Acc a, double n) {
+    if (n == kPartialPowerSum) return from_compute<Out>(a);  // sharded: Σ x² leaves unrooted, the root follows the exchange
     if constexpr (std::is_same<Acc, float>::value) return from_compute<Out>(sqrtf(a));
     else return from_compute<Out>(sqrt(a));
   }
@@ -237,7 +240,8 @@ template <typename T> struct ReduceOp<HPTB_REDUCEL3, T>
     return c * c * c;
   }
   static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return a + b; }
-  static __device__ __forceinline__ Out post(Acc a, double) {
+  static __device__ __forceinline__ Out post(Acc a, double n) {
+    if (n == kPartialPowerSum) return from_compute<Out>(a);
     const Acc third = to_compute<Out>(cast<Out>(1.0 / 3.0));
     if constexpr (std::is_same<Acc, float>::value) return from_compute<Out>((float)pow((double)a, (double)third));
     else return from_compute<Out>(pow(a, third));
@@ -279,16 +283,29 @@ template <typename T> struct ReduceOp<HPTB_MEAN, T>
   static __device__ __forceinline__ Acc from_out(Out o) { return to_compute<Out>(o); }
 };
 // LOGSUMEXP: common_reduce.rs:451-480 — ln Σ exp(x), no max shift (as the reference; overflows to +inf alike)
-template <typename T> struct ReduceOp<HPTB_LOGSUMEXP, T>
-    : PlainLocal<ReduceOp<HPTB_LOGSUMEXP, T>, T, compute_t<typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type>> {
+// LONG (reductions of ≥ kLogSumExpLongMin elements, picked in api_reduce.cpp): exp is the bare ex2(x·log2e), 2
+// instructions instead of 11.  Dropping the product's rounding error adds ≤ |x|·2^-24 relative error per term
+// (|x| < 89 before overflow), i.e. ≤ 5e-6 ABSOLUTE on the logarithm — far inside the 1e-6·log2(n) sum bound.
+constexpr int64_t kLogSumExpLongMin = 512;
+template <typename T, bool LONG> struct LogSumExpOp
+    : PlainLocal<LogSumExpOp<T, LONG>, T, compute_t<typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type>> {
   typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, dtype_of<T>::value, 1)>::type Out;
   typedef compute_t<Out> Acc;
   static constexpr bool kIndexed = false;
   static __device__ __forceinline__ Acc identity() { return (Acc)0; }
   static __device__ __forceinline__ Acc pre(T x, int64_t) {
     Acc c = to_compute<Out>(cast<Out>(x));
-    if constexpr (std::is_same<Acc, float>::value) return fast_expf_ovf(c);  // ≤ 2 ulp, 9 instructions (scalar.cuh)
-    else return exp(c);
+    if constexpr (std::is_same<Acc, float>::value) {
+      if constexpr (LONG) {
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(c * 1.4426950408889634f));  // −inf → 0, overflow → +inf, NaN → NaN
+        return e;
+      } else {
+        return fast_expf_ovf(c);  // ≤ 2 ulp, 9 instructions (scalar.cuh)
+      }
+    } else {
+      return exp(c);
+    }
   }
   static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return a + b; }
   static __device__ __forceinline__ Out post(Acc a, double) {
@@ -301,6 +318,7 @@ template <typename T> struct ReduceOp<HPTB_LOGSUMEXP, T>
     else return exp(c);
   }
 };
+template <typename T> struct ReduceOp<HPTB_LOGSUMEXP, T> : LogSumExpOp<T, false> {};
 // ARGMAX / ARGMIN: cpu/kernels/argreduce_kernels.rs:13-21,49-57 — strict compare from NEG_INF / INF with
 // index 0 as the start, so ties resolve to the lowest index, NaN never wins and an all-NaN (or all-identity)
 // row yields 0.  A (value, index) pair with "better value, else lower index" is the associative form.
@@ -675,6 +693,7 @@ struct LeanRowsParams {
   uint32_t chunks;     // chunks per output (= cpr unless MULTI)
   int32_t logG;        // log2 of the threads per output (8 = a whole CTA)
   int32_t fold_out;
+  int32_t reverse;     // walk the outputs from the last CTA's to the first (snake order, context.h pass_direction)
 };
 
 // resident CTAs per SM the register allocation must allow: 6 (≤ 40 registers) for plain 4-byte accumulators — 8
@@ -701,7 +720,8 @@ reduce_rows_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__
   const uint32_t tid = threadIdx.x;
   const uint32_t G = 1u << p.logG;
   const uint32_t g = tid & (G - 1);
-  const int64_t m = (((int64_t)blockIdx.x * kRedThreads) >> p.logG) + (tid >> p.logG);
+  const uint32_t bx = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int64_t m = (((int64_t)bx * kRedThreads) >> p.logG) + (tid >> p.logG);
   const bool active = m < p.M;
   Local acc[VEC];
 #pragma unroll
@@ -1279,6 +1299,7 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
         q.chunks = (uint32_t)p.chunks;
         q.logG = logG;
         q.fold_out = plan.fold_out;
+        q.reverse = plan.reverse;
         if (multi)
           HPTB_CUDA_CHECK(launch_kernel(reduce_rows_lean_kernel<Op, T, VECMAX, true>, dim3((unsigned)lean_blocks), dim3(kRedThreads), 0, stream, in, out, out2, q));
         else

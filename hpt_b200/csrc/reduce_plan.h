@@ -11,6 +11,7 @@ struct ReducePlan {
   void* out2 = nullptr;  // second output of the fused mean/var extension (same layout as out)
   double count = 1.0;
   int fold_out = 0;
+  int reverse = 0;  // snake order: kernels that can, walk their outputs backwards (context.h pass_direction)
   hptb_ctx* ctx = nullptr;
 };
 typedef hptb_status (*ReduceLauncher)(const ReducePlan&, cudaStream_t);

@@ -559,6 +559,7 @@ extern "C" hptb_status hptb_softmax(hptb_ctx* ctx, const hptb_tensor* in, int ax
   bool same = in->ndim == out->ndim;
   for (int i = 0; same && i < in->ndim; ++i) same = in->shape[i] == out->shape[i];
   if (!same) return fail(HPTB_ERR_SHAPE, "softmax: out shape differs from the input shape");
+  pass_direction(ctx, in->data, 0, false);  // a forward streaming pass (snake order, context.h)
   uint8_t mask[HPTB_MAX_DIMS] = {0};
   mask[axis] = 1;
   int64_t strides[kMaxOperands][HPTB_MAX_DIMS] = {{0}};

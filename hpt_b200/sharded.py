@@ -26,7 +26,8 @@ def shard_plan(op, axes, shard_axis, world):
     p = _ffi.HptbShardPlan()
     check(lib.hptb_shard_plan_reduce(_ffi.REDUCE_OPS[op], ax, len(axes), int(shard_axis), int(world), byref(p)))
     return {"crosses": bool(p.crosses), "collective": _ffi.COLLECTIVES[p.collective], "pre_exp": bool(p.pre_exp),
-            "post_ln": bool(p.post_ln), "global_count": bool(p.global_count)}
+            "post_ln": bool(p.post_ln), "global_count": bool(p.global_count),
+            "post_root": int(p.post_root)}
 
 
 class Comm:
@@ -145,5 +146,12 @@ class ShardedTensor:
     def prod(self, axes): return self._reduce("prod", axes)
     def logsumexp(self, axes): return self._reduce("logsumexp", axes)
     def sum_square(self, axes): return self._reduce("sum_square", axes)
+    def reducel1(self, axes): return self._reduce("reducel1", axes)
+    def reducel2(self, axes): return self._reduce("reducel2", axes)
+    def reducel3(self, axes): return self._reduce("reducel3", axes)
+    def nansum(self, axes): return self._reduce("nansum", axes)
+    def nanprod(self, axes): return self._reduce("nanprod", axes)
+    def all(self, axes): return self._reduce("all", axes)
+    def any(self, axes): return self._reduce("any", axes)
     def argmax(self, axis): return self._reduce("argmax", axis)
     def argmin(self, axis): return self._reduce("argmin", axis)

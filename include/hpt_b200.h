@@ -286,6 +286,7 @@ typedef struct hptb_shard_plan {
   int32_t pre_exp;      /* 1: exp() the local result before the collective (logsumexp) */
   int32_t post_ln;      /* 1: ln() after the collective (logsumexp) */
   int32_t global_count; /* 1: the local op divides by the GLOBAL element count (mean) */
+  int32_t post_root;    /* p = 2 or 3: the local op leaves Σ|x|^p unrooted, the p-th root follows the collective (reducel2/3) */
 } hptb_shard_plan;
 hptb_status hptb_shard_bounds(int64_t n, int world, int rank, int64_t* offset, int64_t* len);
 hptb_status hptb_shard_plan_reduce(int op, const int32_t* axes, int naxes, int shard_axis, int world,

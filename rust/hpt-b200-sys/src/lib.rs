@@ -65,7 +65,7 @@ pub struct hptb_collapse_plan {
 #[repr(C)] pub struct hptb_ctx { _private: [u8; 0] }
 #[repr(C)] pub struct hptb_comm { _private: [u8; 0] }
 #[repr(C)] #[derive(Clone, Copy, Debug, Default)]
-pub struct hptb_shard_plan { pub crosses: i32, pub collective: i32, pub pre_exp: i32, pub post_ln: i32, pub global_count: i32 }
+pub struct hptb_shard_plan { pub crosses: i32, pub collective: i32, pub pre_exp: i32, pub post_ln: i32, pub global_count: i32, pub post_root: i32 }
 
 extern "C" {
     pub fn hptb_version() -> c_int;

@@ -31,7 +31,8 @@ def main():
             if d in ("f32", "f64"):
                 x.flat[::7] = x.flat[3]  # ties
             X = hb.ShardedTensor.scatter_from_host(to_torch(x, d), comm, sax, device=local)
-            for op in ("sum", "mean", "max", "min", "prod", "logsumexp", "sum_square", "argmax", "argmin"):
+            for op in ("sum", "mean", "max", "min", "prod", "logsumexp", "sum_square", "reducel1", "reducel2", "reducel3", "nansum",
+                       "all", "any", "argmax", "argmin"):
                 if op == "prod" and d in ("f16", "bf16"):
                     continue  # products of hundreds of half-precision values over/underflow: nothing to compare
                 axes_list = [[sax]] if op.startswith("arg") else [[sax], list(range(len(shape)))]

@@ -24,6 +24,8 @@ CASES = [  # (op, dtype, shape, axes, shard_axis)
     ("max", "f32", (10, 3), [0], 0), ("min", "i64", (7, 3), [0, 1], 0), ("prod", "i32", (6, 4), [0], 0),
     ("sum_square", "f32", (10, 4), [0], 0), ("argmax", "f32", (9, 6), [0], 0), ("argmin", "i32", (12, 5), [0], 0),
     ("argmax", "f32", (9, 6), [1], 0), ("sum", "f32", (5, 12), [1], 1), ("argmin", "f32", (5, 12), [1], 1),
+    ("reducel2", "f32", (10, 7), [0], 0), ("reducel3", "f64", (9, 5), [0, 1], 0), ("reducel2", "i32", (8, 6), [0], 0),
+    ("reducel1", "f32", (10, 7), [0, 1], 0),
 ]
 
 
@@ -80,6 +82,8 @@ def _worker(rank, world, port, q):
                 part = O.reduce_f64("sum", local, d, axes) / n
             elif plan["pre_exp"]:
                 part = np.exp(O.reduce_f64("logsumexp", local, d, axes))
+            elif plan["post_root"]:
+                part = O.reduce_f64(op, local, d, axes) ** plan["post_root"]  # the unrooted power sum
             elif d in O.INTS or op in ("max", "min"):
                 part, _, _ = O.reduce(op, local, d, axes)
             else:
@@ -90,6 +94,8 @@ def _worker(rank, world, port, q):
             got = t.numpy()
             if plan["post_ln"]:
                 got = np.log(got)
+            if plan["post_root"]:
+                got = got ** (1.0 / plan["post_root"])
             if exact:
                 np.testing.assert_array_equal(got.astype(want.dtype), want)
             else:

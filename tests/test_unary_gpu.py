@@ -127,3 +127,27 @@ def test_large_tail_is_written(hb):
     got = to_numpy(V.sin().to_cpu(), "f32")
     want = O.unary("sin", x[: 3000 * 4000].reshape(3000, 4000).T, "f32")[0]
     assert_ulp(got, want, "f32", 2)
+
+
+@pytest.mark.parametrize("op", ["sin", "cos"])
+def test_sin_cos_bit_pattern_sweep(hb, op):
+    """ops.cuh evaluates f32 sin/cos with its own Cody–Waite + minimax path up to |x| = 105615 and f64 above:
+    sweep every 509th f32 bit pattern of both signs (8.4 M values: every binade, the 105615 switch, subnormals,
+    inf, NaN) plus the floats nearest to k·π/2, in the flat, rows and transposing-tile kernels."""
+    bits = np.arange(0, 2 ** 32, 509, dtype=np.uint64).astype(np.uint32)
+    x = bits.view(np.float32)
+    k = np.arange(1, 70000, dtype=np.float64)
+    near = (k[:, None] * (np.pi / 2) + np.array([0.0, 1e-4, -1e-4])[None, :]).astype(np.float32).ravel()
+    edge = np.array([0.0, -0.0, 105615.0, -105615.0, np.nextafter(np.float32(105615.0), np.float32(np.inf)), 1e30, -3e38,
+                     np.inf, -np.inf, np.nan], np.float32)
+    x = np.concatenate([x, near, -near, edge])
+    x = np.concatenate([x, np.zeros((-x.size) % 4096, np.float32)]).reshape(-1, 4096)
+    with np.errstate(invalid="ignore"):
+        want, od = O.unary(op, x, "f32")
+    X = hb.Tensor.to_cuda(to_torch(x, "f32"))
+    for name, got in (("flat", getattr(X, op)()), ("rows", getattr(X[:, 4:4092], op)()), ("tile", getattr(X.t(), op)())):
+        g = to_numpy(got.to_cpu(), od)
+        w = want if name == "flat" else want[:, 4:4092] if name == "rows" else want.T
+        assert_ulp(g, w, od, 2, f"{op} sweep {name}")
+        if name == "flat" and op == "sin":  # sin(−0) = −0
+            assert np.signbit(g.ravel()[np.flatnonzero(np.signbit(x.ravel()) & (x.ravel() == 0))]).all()
