@@ -1048,6 +1048,29 @@ inline void fill_walk(DimWalk& w, const Collapsed& c, const int* dims, int n, bo
   }
 }
 
+// An empty reduced extent (some reduced dim has length 0): every output is the op's value on no elements — the
+// identity through post() (sum 0, prod 1, max NEG_INF, all true, argmax 0, mean 0/0 = NaN), as the reference's
+// init value left untouched by an empty loop (cpu/tensor_internal/common_reduce.rs:32-168).
+struct EmptyRedParams {
+  int64_t M;
+  int32_t nk, fold_out;
+  int64_t shape[kRedMaxDims], stride[kRedMaxDims];  // kept dims, innermost first
+  double count;
+};
+template <typename Op>
+__global__ void reduce_empty_kernel(typename Op::Out* __restrict__ out, typename Op::Out* __restrict__ out2, EmptyRedParams p) {
+  pdl_prologue();
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < p.M; m += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rest = m, off = 0;
+    for (int i = 0; i < p.nk; ++i) {
+      const int64_t q = rest / p.shape[i];
+      off += (rest - q * p.shape[i]) * p.stride[i];
+      rest = q;
+    }
+    red_store<Op>(out, out2, off, Op::identity(), p.count, p.fold_out);
+  }
+}
+
 // resident CTAs per SM of one kernel instantiation (registers / shared memory decide), asked once
 template <typename K>
 inline int ctas_per_sm(K kernel, size_t smem) {
@@ -1083,6 +1106,18 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   for (int i = 0; i < nk; ++i) M *= c.shape[kept[i]];
   for (int i = 0; i < nr; ++i) R *= c.shape[red[i]];
   if (M == 0) return HPTB_OK;  // no outputs
+  if (R == 0) {
+    EmptyRedParams e;
+    memset(&e, 0, sizeof(e));
+    e.M = M;
+    e.nk = nk;
+    e.fold_out = plan.fold_out;
+    e.count = plan.count;
+    for (int i = 0; i < nk; ++i) { e.shape[i] = c.shape[kept[i]]; e.stride[i] = c.strides[0][kept[i]]; }
+    const int64_t blocks = (M + 255) / 256;
+    HPTB_CUDA_CHECK(launch_kernel(reduce_empty_kernel<Op>, dim3((unsigned)(blocks > 4096 ? 4096 : blocks)), dim3(256), 0, stream, out, out2, e));
+    return HPTB_OK;
+  }
 
   // ---- cols: the unit-stride dim is kept (and is the output's unit-stride dim) ---------------------------
   int cdim = -1;

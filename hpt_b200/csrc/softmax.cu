@@ -234,10 +234,17 @@ softmax_cols(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_o
   walk2(col, p.kept, p.use64, in_off, out_off);
   const T* src = in + in_off;
   O* dst = out + out_off;
+  // blocks of 256 elements, combined pairwise-style: a plain running Σ over a long column (70000 rows) would carry
+  // ~sqrt(L)/2 ulp of accumulated rounding, at the edge of the 1e-6·log2(n) sum bound
   MS<C> a{Limits<C>::lowest(), (C)0};
-  for (int64_t e = 0; e < p.L; ++e) {
-    const C x = to_compute<O>(cast<O>(load_one(src + e * p.sa_in)));
-    ms_push<C>(a, x);
+  for (int64_t e0 = 0; e0 < p.L; e0 += 256) {
+    MS<C> blk{Limits<C>::lowest(), (C)0};
+    const int64_t e1 = e0 + 256 < p.L ? e0 + 256 : p.L;
+    for (int64_t e = e0; e < e1; ++e) {
+      const C x = to_compute<O>(cast<O>(load_one(src + e * p.sa_in)));
+      ms_push<C>(blk, x);
+    }
+    a = ms_combine<C>(a, blk);
   }
   const C ssum = a.s, lg = sm_log<C>(a.s);
   for (int64_t e = 0; e < p.L; ++e) {

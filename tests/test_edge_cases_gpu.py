@@ -1,0 +1,202 @@
+"""GPU parity on the edges of the domain: empty and ragged shapes, 8-D views, broadcast (stride-0) and negative
+strides as kernel INPUTS, misaligned base pointers, in-place aliasing, 64-bit extents and indices, extreme
+integers.  Everything is compared with the oracle, exact unless the op is a float transcendental / sum."""
+import numpy as np
+import pytest
+import torch
+
+from test_binary_gpu import _run as run_binary
+from test_reduce_gpu import _check as check_reduce
+from test_softmax_misc_gpu import _softmax_check
+from test_unary_gpu import _check as check_unary
+from util import ENUM, O, assert_exact, rand, to_numpy, to_torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hpt_b200
+    return hpt_b200
+
+
+def test_empty_tensors(hb):
+    for shape in [(0,), (0, 5), (5, 0), (3, 0, 7)]:
+        E = hb.Tensor.empty(shape, ENUM["f32"])
+        assert E.sin().shape == shape and (E * E).shape == shape and E.contiguous().shape == shape
+        assert E.astype(ENUM["i32"]).shape == shape
+    # reducing an empty axis yields the identity (Hpt: init value; numpy agrees for sum/prod/all/any)
+    x = np.zeros((4, 0), np.float32)
+    X = hb.Tensor.to_cuda(torch.from_numpy(x))
+    assert (X.sum([1]).to_cpu().numpy() == 0).all()
+    assert (X.prod([1]).to_cpu().numpy() == 1).all()
+    assert (X.max([1]).to_cpu().numpy() == -np.inf).all() and (X.min([1]).to_cpu().numpy() == np.inf).all()
+    assert (X.any([1]).to_cpu().numpy() == False).all() and (X.all([1]).to_cpu().numpy() == True).all()  # noqa: E712
+    assert (X.argmax(1).to_cpu().numpy() == 0).all()
+    assert X.sum([0]).shape == (0,)
+    xi = np.zeros((0, 3), np.int32)
+    Xi = hb.Tensor.to_cuda(torch.from_numpy(xi))
+    assert (Xi.max([0]).to_cpu().numpy() == np.iinfo(np.int32).min).all()
+    assert (Xi.min([0]).to_cpu().numpy() == np.iinfo(np.int32).max).all()
+    assert X.softmax(1).shape == (4, 0)
+
+
+def test_eight_dims_and_permutations(hb):
+    rng = np.random.default_rng(40)
+    shape = (2, 3, 2, 5, 2, 3, 2, 4)
+    x, y = rand(rng, shape, "f32"), rand(rng, shape, "i32", -50, 50)
+    perm = [7, 0, 6, 1, 5, 2, 4, 3]
+    pv = lambda t: t.permute(perm) if hasattr(t, "storage") else np.transpose(t, perm)
+    run_binary(hb, "add", x, "f32", y, "i32", pv, pv)
+    run_binary(hb, "mul", x, "f32", np.ascontiguousarray(np.transpose(y, perm)), "i32", pv, None)
+    check_unary(hb, "exp", x, "f32", view=pv)
+    for axes in ([0], [7], [0, 7], [1, 3, 5], [0, 1, 2, 3, 4, 5, 6, 7], [2, 4, 6, 7]):
+        check_reduce(hb, "sum", x, "f32", axes, view=pv)
+        check_reduce(hb, "max", y, "i32", axes, view=pv)
+    check_reduce(hb, "argmin", x, "f32", [4], view=pv)
+    _softmax_check(hb, x, "f32", 3, False, pv)
+
+
+def test_broadcast_and_negative_strides_as_inputs(hb):
+    rng = np.random.default_rng(41)
+    col = rand(rng, (37, 1), "f32")
+    ex = lambda t: t.expand((37, 129)) if hasattr(t, "storage") else np.broadcast_to(t, (37, 129))
+    check_unary(hb, "sin", col, "f32", view=ex)
+    for axes in ([0], [1], [0, 1]):
+        check_reduce(hb, "sum", col, "f32", axes, view=ex)
+        check_reduce(hb, "argmax", col, "f32", axes[:1], view=ex)  # every row is one long tie → index 0
+    x = rand(rng, (65, 130), "f32")
+    flip = lambda t: t[::-1, ::-1]
+    check_unary(hb, "exp", x, "f32", view=flip)
+    run_binary(hb, "sub", x, "f32", x, "f32", flip, None)
+    for op in ("sum", "max", "argmax", "logsumexp"):
+        check_reduce(hb, op, x, "f32", [1], view=flip)
+        check_reduce(hb, op, x, "f32", [0], view=flip)
+    _softmax_check(hb, x, "f32", 1, False, flip)
+    _softmax_check(hb, x, "f32", 0, True, flip)
+
+
+def test_misaligned_base_pointers_and_ragged_tails(hb):
+    """Views that start 1–3 elements into an allocation are not 16-byte aligned: the vector kernels must fall back
+    (or peel) without touching the neighbours."""
+    rng = np.random.default_rng(42)
+    for d in ("f32", "bf16", "i8", "f64"):
+        base = rand(rng, (5000,), d)
+        for off in (1, 2, 3):
+            for n in (1, 7, 1023, 4096, 4099):
+                v = lambda t, off=off, n=n: t[off:off + n]
+                run_binary(hb, "add", base, d, base, d, v, v)
+                check_reduce(hb, "sum", base, d, [0], view=v)
+                check_reduce(hb, "argmax", base, d, [0], view=v)
+        m = rand(rng, (33, 1030), d)
+        for v in (lambda t: t[:, 1:1028], lambda t: t[1:, 3:], lambda t: t[:, 2::3]):
+            check_reduce(hb, "max", m, d, [1], view=v)
+            check_reduce(hb, "sum", m, d, [0], view=v)
+            if d in ("f32", "bf16"):
+                check_unary(hb, "sqrt", np.abs(m), d, view=v)
+                _softmax_check(hb, m, d, 1, False, v)
+    # neighbours untouched: write through an out view in the middle of a poisoned buffer
+    buf = hb.Tensor.full(7.0, (1000,), ENUM["f32"])
+    X = hb.Tensor.to_cuda(torch.arange(100, dtype=torch.float32))
+    X.add_(X, buf[3:103])
+    got = buf.to_cpu().numpy()
+    assert (got[:3] == 7).all() and (got[103:] == 7).all() and (got[3:103] == 2 * np.arange(100)).all()
+
+
+def test_inplace_aliasing(hb):
+    """`out` may alias an input (the reference's `_` ops reuse the lhs storage, binary_normal.rs:546-564)."""
+    rng = np.random.default_rng(43)
+    x, y = rand(rng, (257, 129), "f32"), rand(rng, (257, 129), "f32")
+    X, Y = hb.Tensor.to_cuda(torch.from_numpy(x)), hb.Tensor.to_cuda(torch.from_numpy(y))
+    X.add_(Y, X)
+    assert (X.to_cpu().numpy() == x + y).all()
+    X.mul_(X, X)
+    assert (X.to_cpu().numpy() == (x + y) * (x + y)).all()
+    Y.exp(out=Y)
+    want, _ = O.unary("exp", y, "f32")
+    assert O.ulp_diff(Y.to_cpu().numpy(), want, "f32").max() <= 2
+
+
+def test_extreme_integers_are_exact(hb):
+    rng = np.random.default_rng(44)
+    for d in ("i64", "u64"):
+        info = np.iinfo(O.NP[d])
+        x = rng.integers(info.max - 1000, info.max, size=(64, 300), dtype=O.NP[d], endpoint=True)  # all above 2^53
+        x[3, 7] = info.max
+        x[5, :] = info.min
+        for op in ("max", "min", "argmax", "argmin", "sum", "prod"):
+            check_reduce(hb, op, x, d, [1])
+            check_reduce(hb, op, x, d, [0])
+        y = rng.integers(info.min, info.max, size=(64, 300), dtype=O.NP[d], endpoint=True)
+        for op in ("add", "sub", "mul", "maximum", "minimum", "rem"):
+            run_binary(hb, op, x, d, y, d)
+    # float → int casts saturate, NaN → 0 (Rust `as`)
+    f = np.array([np.nan, np.inf, -np.inf, 3e38, -3e38, 1e10, -1e10, 255.5, -0.5, 2147483648.0], np.float32)
+    F = hb.Tensor.to_cuda(torch.from_numpy(f))
+    for d in ("i8", "u8", "i32", "u32", "i64", "u64", "bool"):
+        want = O.cast(f, "f32", d)
+        assert_exact(to_numpy(F.astype(ENUM[d]).to_cpu(), d), want, d, f"f32 → {d}")
+
+
+def test_index_beyond_int32(hb):
+    """One row of 2^31 + 4099 int8 elements: chunk counters, element offsets and the argmax index need 64 bits
+    (the reference's kernels are i32-indexed)."""
+    n = 2 ** 31 + 4099
+    free, _ = torch.cuda.mem_get_info()
+    if free < 8 * 2 ** 30:
+        pytest.skip("needs 2 GiB for the tensor")
+    x = torch.zeros(n, dtype=torch.int8, device="cuda")
+    x[n - 5] = 7
+    x[n - 3] = 7      # tie: the lower index wins
+    x[12345] = -9
+    X = hb.Tensor.from_device_ptr(x.data_ptr(), ENUM["i8"], (n,), keepalive=x)
+    assert int(X.argmax(0).to_cpu().numpy()[0]) == n - 5
+    assert int(X.argmin(0).to_cpu().numpy()[0]) == 12345
+    assert int(X.max([0]).to_cpu().numpy()[0]) == 7
+    assert int(X.sum([0]).to_cpu().numpy()[0]) == np.int8((7 + 7 - 9) & 0xFF)
+    M = hb.Tensor.from_device_ptr(x.data_ptr(), ENUM["i8"], (2, n // 2), keepalive=x)  # 2-D: rows of 2^30 elements
+    got = M.argmax(1).to_cpu().numpy()
+    assert got[0] == 0 and got[1] == (n - 5) - n // 2
+    Y = X.astype(ENUM["u8"])  # elementwise over > 2^31 elements
+    assert int(Y.max([0]).to_cpu().numpy()[0]) == 247  # −9 as u8
+    del X, M, Y, x
+    torch.cuda.empty_cache()
+
+
+def _softmax_check_long(hb, x, axis, log):
+    """Rows beyond the register-resident limit (8192 f32) stream through an online (max, Σ) pass: every output then
+    also carries the rounding of an f32 sum of L terms (each thread adds L/256 terms in sequence, then a tree), which
+    BASELINE.json bounds by 1e-6·log2(n) relative.  Bar: the elementwise 4 + |x − max| ulp of _softmax_check plus
+    min(L/2048, 1e-6·log2(L)/2^-23) ulp for Σ; log_softmax: the same amount as an absolute error of ln Σ."""
+    X = hb.Tensor.to_cuda(to_torch(x, "f32"))
+    got = (X.log_softmax(axis) if log else X.softmax(axis)).to_cpu().numpy()
+    want, od = O.softmax(x, "f32", axis, log)
+    L = x.shape[axis]
+    extra = min(np.ceil(L / 2048), 1e-6 * np.log2(L) / 2.0 ** -23)
+    xc = x.astype(np.float64)
+    shift = np.abs(xc - xc.max(axis=axis, keepdims=True))
+    if log:
+        err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+        ok = err <= 2.0 ** -23 * ((4 + extra) + 4 * (np.abs(xc).max(axis=axis, keepdims=True) + 1.0))
+    else:
+        ok = O.ulp_diff(got, want, "f32") <= 4 + np.ceil(shift) + extra
+    assert ok.all(), f"softmax log={log} shape={x.shape} axis={axis}: {np.count_nonzero(~ok)} outside the bar"
+    if not log:
+        assert np.abs(got.astype(np.float64).sum(axis=axis) - 1.0).max() <= 1e-6 * np.log2(L)
+
+
+def test_softmax_row_lengths_around_the_register_limit(hb):
+    rng = np.random.default_rng(45)
+    for n in (1, 2, 31, 33, 255, 257, 8191, 8192):
+        x = rand(rng, (3, n), "f32") * 4
+        _softmax_check(hb, x, "f32", 1, False)
+        _softmax_check(hb, x, "f32", 1, True)
+    for n in (8193, 8200, 16384, 65536 + 3, 300001):
+        x = rand(rng, (3, n), "f32") * 4
+        _softmax_check_long(hb, x, 1, False)
+        _softmax_check_long(hb, x, 1, True)
+    h = rand(rng, (5, 8000), "bf16")
+    _softmax_check(hb, h, "bf16", 1, False)
+    x = rand(rng, (70000, 3), "f32")  # strided axis: one thread walks a column
+    _softmax_check_long(hb, x, 0, False)
+    _softmax_check_long(hb, x, 0, True)
