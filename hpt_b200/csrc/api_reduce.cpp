@@ -8,6 +8,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include <algorithm>
 #include "dtypes_x.h"
 #include "map_plan.h"
 #include "promote.h"
@@ -201,6 +202,47 @@ hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int3
     return fail(HPTB_ERR_DTYPE, "reduce: out dtype is %s, expected %s", dtype_name(out->dtype), dtype_name(odt));
   ReduceLauncher fn = reduce_launcher(op, in->dtype);
   if (!fn) return fail(HPTB_ERR_DTYPE, "reduce: no kernel for op %d on %s", op, dtype_name(in->dtype));
+  // Transposing reduction: the input's fastest KEPT dim is not the output's fastest dim (x.permute(2,0,1).sum(2):
+  // the lanes that read a full line would each write to a different line, and no kernel class is coalesced on both
+  // sides — 0.13 of peak through the general kernel).  The output is the small side, so reduce into a scratch
+  // laid out in the INPUT's dim order (coalesced cols / rows kernels apply) and gather it into `out` afterwards.
+  if (init_out && count_override != -2.0 && in->ndim > 0 && out->ndim >= 2) {
+    uint8_t mask[HPTB_MAX_DIMS] = {0};
+    bool ok = true;
+    for (int i = 0; i < naxes; ++i) {
+      if (axes[i] < 0 || axes[i] >= in->ndim) { ok = false; break; }
+      mask[axes[i]] = 1;
+    }
+    int src_dim[HPTB_MAX_DIMS], nk = 0;
+    double red = 1.0;
+    for (int i = 0; ok && i < in->ndim; ++i) {
+      if (mask[i]) red *= (double)in->shape[i];
+      else src_dim[nk++] = i;
+    }
+    if (ok && nk == out->ndim && red >= 8.0) {
+      int fin = -1, fout = -1;  // fastest kept dim on the input side / on the output side (extent > 1)
+      for (int j = 0; j < nk; ++j) {
+        if (out->shape[j] <= 1) continue;
+        if (fin < 0 || std::llabs(in->strides[src_dim[j]]) < std::llabs(in->strides[src_dim[fin]])) fin = j;
+        if (fout < 0 || std::llabs(out->strides[j]) < std::llabs(out->strides[fout])) fout = j;
+      }
+      if (fin >= 0 && fin != fout && std::llabs(in->strides[src_dim[fin]]) == 1 && out->shape[fin] >= 32 && numel(*out) > 0) {
+        hptb_tensor tmp = *out;
+        int order[HPTB_MAX_DIMS];  // out dims from the slowest to the fastest input stride
+        for (int j = 0; j < nk; ++j) order[j] = j;
+        std::sort(order, order + nk, [&](int a, int b) {
+          return std::llabs(in->strides[src_dim[a]]) > std::llabs(in->strides[src_dim[b]]);
+        });
+        int64_t st = 1;
+        for (int j = nk - 1; j >= 0; --j) { tmp.strides[order[j]] = st; st *= out->shape[order[j]]; }
+        Scratch sc;
+        HPTB_TRY(sc.get(ctx, (size_t)numel(*out) * dtype_size(out->dtype), stream));
+        tmp.data = sc.ptr;
+        HPTB_TRY(reduce_impl(ctx, op, in, axes, naxes, &tmp, 1, count_override, stream));
+        return hptb_copy(ctx, &tmp, out, stream);
+      }
+    }
+  }
   ReducePlan plan;
   HPTB_TRY(build_reduce_plan(ctx, in, axes, naxes, out, &plan));
   plan.fold_out = init_out ? 0 : 1;

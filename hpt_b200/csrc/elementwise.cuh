@@ -32,6 +32,7 @@ constexpr int kMapThreads = 256;
 #define HPTB_MAP_UNROLL_SCALE 1
 #endif
 constexpr int kMaxOuter = HPTB_MAX_DIMS - 1;
+constexpr int kScalarUnroll = 8;  // elements per thread of the scalar (VEC = 1) rows kernel
 
 struct RowsParams {
   int64_t inner;         // elements in the inner dim
@@ -192,7 +193,8 @@ template <int NIN, int VEC, int UNROLL, typename F, typename O, typename A, type
 __global__ void __launch_bounds__(kMapThreads)
 map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, Rows32Params p, F f) {
   pdl_prologue();
-  static_assert(VEC > 1, "the specialised rows kernel is vector-only; scalar layouts take the runtime-typed kernel");
+  // VEC == 1: one element per lane and chunk, any inner stride per operand (stepped slices, rows that do not start
+  // on a 16-byte boundary) — consecutive lanes still touch consecutive elements, so a warp's access is one run
   const uint32_t c0 = blockIdx.x * (uint32_t)(kMapThreads * UNROLL) + threadIdx.x;
   Pack<A, VEC> pa[UNROLL];
   Pack<B, VEC> pb[UNROLL];
@@ -534,6 +536,54 @@ inline bool tune_flag(const char* name) {
   return e && e[0] == '1';
 }
 
+// rows launch: the innermost collapsed dim is walked by consecutive lanes (VEC elements each), the other dims by one
+// magic-number division per chunk; 32-bit element offsets (larger tensors take the runtime-typed kernel, which is
+// 64-bit).  VEC == 1 accepts any inner stride per operand.
+template <int NIN, int VEC, int UNROLL, typename F, typename O, typename A, typename B>
+hptb_status launch_rows(const Collapsed& c, O* out, const A* a, const B* b, F f, cudaStream_t stream) {
+  const int nd = c.ndim;
+  if (nd < 1) return HPTB_FALLBACK;
+  Rows32Params p;
+  memset(&p, 0, sizeof(p));
+  const int64_t inner = c.shape[nd - 1];
+  if (inner % VEC) return HPTB_FALLBACK;
+  p.nouter = nd - 1;
+  int64_t rows = 1;
+  for (int o = 0; o <= NIN; ++o) {
+    if (std::llabs(c.strides[o][nd - 1]) > 0x7fffffffLL) return HPTB_FALLBACK;
+    p.inner_stride[o] = (int32_t)c.strides[o][nd - 1];
+    int64_t span = (inner - 1) * std::llabs(c.strides[o][nd - 1]);  // largest |offset| this operand can reach
+    for (int i = 0; i < p.nouter; ++i) {
+      const int d = nd - 2 - i;
+      span += (c.shape[d] - 1) * std::llabs(c.strides[o][d]);
+      if (std::llabs(c.strides[o][d]) > 0x7fffffffLL) return HPTB_FALLBACK;
+      p.outer_stride[o][i] = (int32_t)c.strides[o][d];
+      if (o > 0 && c.strides[o][d] == 0) p.reuse[o] = 1;
+    }
+    if (span > 0x7fffffffLL - 64) return HPTB_FALLBACK;
+  }
+  for (int i = 0; i < p.nouter; ++i) {
+    const int d = nd - 2 - i;
+    rows *= c.shape[d];
+    p.outer_shape[i] = (uint32_t)c.shape[d];
+    p.outer_div[i] = FastDiv((uint32_t)c.shape[d]);
+  }
+  if (p.nouter == 0) {  // a single dim: one row (the kernel always folds an outermost dim)
+    p.nouter = 1;
+    p.outer_shape[0] = 1;
+    p.outer_div[0] = FastDiv(1u);
+  }
+  const int64_t cpr = inner / VEC;
+  const int64_t total = rows * cpr;
+  if (total >= (int64_t(1) << 31)) return HPTB_FALLBACK;
+  p.cpr = (uint32_t)cpr;
+  p.cpr_div = FastDiv((uint32_t)cpr);
+  p.total_chunks = (uint32_t)total;
+  int64_t blocks = (total + kMapThreads * UNROLL - 1) / (kMapThreads * UNROLL);
+  HPTB_CUDA_CHECK(launch_kernel(map_rows_kernel<NIN, VEC, UNROLL, F, O, A, B>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, f));
+  return HPTB_OK;
+}
+
 template <int NIN, typename F, typename O, typename A, typename B>
 hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
   const Collapsed& c = plan.c;
@@ -551,10 +601,13 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
     for (int o = 0; o <= NIN; ++o) {
       if (nd && c.strides[o][nd - 1] == 0) continue;
       size_t align = esz[o] * VEC > 16 ? 16 : esz[o] * VEC;
-      if (reinterpret_cast<uintptr_t>(plan.ptr[o]) % align) return HPTB_FALLBACK;
+      bool misaligned = reinterpret_cast<uintptr_t>(plan.ptr[o]) % align;
       for (int d = 0; d + 1 < nd; ++d)
-        if ((uint64_t)(std::llabs(c.strides[o][d]) * (int64_t)esz[o]) % align) return HPTB_FALLBACK;
+        if ((uint64_t)(std::llabs(c.strides[o][d]) * (int64_t)esz[o]) % align) misaligned = true;
+      // rows that do not start on a pack boundary (a[5:8000, 3:8100]): one element per lane, still one run per warp
+      if (misaligned) return nd ? launch_rows<NIN, 1, kScalarUnroll, F, O, A, B>(c, out, a, b, f, stream) : HPTB_FALLBACK;
     }
+    if (nd >= 2 && c.shape[nd - 1] % VEC) return launch_rows<NIN, 1, kScalarUnroll, F, O, A, B>(c, out, a, b, f, stream);  // ragged rows
     if (nd <= 1) {  // flat: one contiguous run per operand (or a broadcast scalar)
       FlatParams p;
       p.n = nd ? c.shape[0] : 1;
@@ -567,40 +620,7 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
       HPTB_CUDA_CHECK(launch_kernel(map_flat_kernel<NIN, VEC, UNROLL, F, O, A, B>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, f));
       return HPTB_OK;
     }
-    // rows: 32-bit element offsets (larger tensors with outer dims take the runtime-typed kernel, which is 64-bit)
-    Rows32Params p;
-    memset(&p, 0, sizeof(p));
-    const int64_t inner = c.shape[nd - 1];
-    if (inner % VEC) return HPTB_FALLBACK;
-    p.nouter = nd - 1;
-    int64_t rows = 1;
-    for (int o = 0; o <= NIN; ++o) {
-      p.inner_stride[o] = (int32_t)c.strides[o][nd - 1];
-      int64_t span = (inner - 1) * std::llabs(c.strides[o][nd - 1]);  // largest |offset| this operand can reach
-      for (int i = 0; i < p.nouter; ++i) {
-        const int d = nd - 2 - i;
-        span += (c.shape[d] - 1) * std::llabs(c.strides[o][d]);
-        if (std::llabs(c.strides[o][d]) > 0x7fffffffLL) return HPTB_FALLBACK;
-        p.outer_stride[o][i] = (int32_t)c.strides[o][d];
-        if (o > 0 && c.strides[o][d] == 0) p.reuse[o] = 1;
-      }
-      if (span > 0x7fffffffLL - 64) return HPTB_FALLBACK;
-    }
-    for (int i = 0; i < p.nouter; ++i) {
-      const int d = nd - 2 - i;
-      rows *= c.shape[d];
-      p.outer_shape[i] = (uint32_t)c.shape[d];
-      p.outer_div[i] = FastDiv((uint32_t)c.shape[d]);
-    }
-    const int64_t cpr = inner / VEC;
-    const int64_t total = rows * cpr;
-    if (total >= (int64_t(1) << 31)) return HPTB_FALLBACK;
-    p.cpr = (uint32_t)cpr;
-    p.cpr_div = FastDiv((uint32_t)cpr);
-    p.total_chunks = (uint32_t)total;
-    int64_t blocks = (total + kMapThreads * UNROLL - 1) / (kMapThreads * UNROLL);
-    HPTB_CUDA_CHECK(launch_kernel(map_rows_kernel<NIN, VEC, UNROLL, F, O, A, B>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, f));
-    return HPTB_OK;
+    return launch_rows<NIN, VEC, UNROLL, F, O, A, B>(c, out, a, b, f, stream);
   }
 
   // strided: choose tile dims
@@ -619,7 +639,16 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
     for (int d = 0; d < nd; ++d)
       if (d != da && c.strides[o][d] == 1) { db = d; break; }
   }
-  if (db < 0) {  // no permuted unit-stride dim: take the innermost remaining dim (largest extent wins ties)
+  if (db < 0) {
+    // No operand has its unit stride on another dim: nothing to transpose, the inner dim is merely stepped
+    // (a[:, ::2]) or reversed.  Lanes along the output's fastest dim with scalar accesses are as coalesced as such a
+    // layout allows (the tile kernel would run 64-element tiles here: f32 a[:, ::2].exp() 1146 µs).
+    if (da == nd - 1) {
+      hptb_status st = launch_rows<NIN, 1, kScalarUnroll, F, O, A, B>(c, out, a, b, f, stream);
+      if (st != HPTB_FALLBACK) return st;
+    }
+  }
+  if (db < 0) {  // take the innermost remaining dim (largest extent wins ties)
     for (int d = nd - 1; d >= 0; --d)
       if (d != da) { db = d; break; }
   }
