@@ -16,6 +16,7 @@
 //                        write pass (two reads, one write).
 //   softmax_cols         axis is strided and another dim is contiguous: one thread per output column,
 //                        lanes along the contiguous dim (coalesced), online pass + write pass.
+#include <algorithm>
 #include "context.h"
 #include "dtypes_x.h"
 #include "layout.h"
@@ -266,6 +267,69 @@ softmax_cols(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_o
   }
 }
 
+// Long unit-stride rows (more than 8 packs per thread): one CTA per row, 16-byte loads with four in flight per
+// thread, an online (max, Σ) sweep and a write sweep whose reads come back from L2 (a row is ≤ a few MB).  The scalar
+// softmax_rows_stream below stays for strided axes: f32 [256,131072] softmax(1) 551 µs through it.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kSmThreads)
+softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
+                        SoftmaxParams p) {
+  pdl_prologue();
+  typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type O;
+  typedef compute_t<O> C;
+  constexpr int UN = 4;
+  __shared__ C s_m[kSmThreads / 32], s_s[kSmThreads / 32];
+  const int tid = threadIdx.x;
+  const int64_t packs = p.L / VEC;  // the host picks this kernel only when L is a multiple of VEC
+  for (int64_t row = blockIdx.x; row < p.M; row += gridDim.x) {
+    int64_t in_off = 0, out_off = 0;
+    walk2(row, p.kept, p.use64, in_off, out_off);
+    const T* src = in + in_off;
+    O* dst = out + out_off;
+    MS<C> a{Limits<C>::lowest(), (C)0};
+    for (int64_t c = tid; c < packs; c += (int64_t)kSmThreads * UN) {
+      Pack<T, VEC> v[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+        if (c + (int64_t)u * kSmThreads < packs) load_pack<T, VEC>(v[u], src + (c + (int64_t)u * kSmThreads) * VEC);
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+        if (c + (int64_t)u * kSmThreads < packs) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) ms_push_fast<C>(a, to_compute<O>(cast<O>(v[u].v[k])));
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      MS<C> b{shfl_xor<C>(a.m, off), shfl_xor<C>(a.s, off)};
+      a = (tid & off) == 0 ? ms_combine<C>(a, b) : ms_combine<C>(b, a);
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { s_m[tid >> 5] = a.m; s_s[tid >> 5] = a.s; }
+    __syncthreads();
+    MS<C> r{Limits<C>::lowest(), (C)0};
+    for (int w = 0; w < kSmThreads / 32; ++w) r = ms_combine<C>(r, MS<C>{s_m[w], s_s[w]});
+    const C inv = (C)1 / r.s, lg = sm_log<C>(r.s);
+    for (int64_t c = tid; c < packs; c += (int64_t)kSmThreads * UN) {
+      Pack<T, VEC> v[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+        if (c + (int64_t)u * kSmThreads < packs) load_pack_cached<T, VEC>(v[u], src + (c + (int64_t)u * kSmThreads) * VEC);
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+        if (c + (int64_t)u * kSmThreads < packs) {
+          Pack<O, VEC> o;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const C sh = to_compute<O>(cast<O>(v[u].v[k])) - r.m;
+            o.v[k] = from_compute<O>(p.log ? sh - lg : sm_exp_fast(sh) * inv);
+          }
+          store_pack<O, VEC>(dst + (c + (int64_t)u * kSmThreads) * VEC, o);
+        }
+    }
+  }
+}
+
 // Strided axis, contiguous kept dim (softmax over axis 0 of a row-major matrix): a CTA owns TX·VEC adjacent columns,
 // lanes run along them with 16-byte loads (a warp reads 32/TX full rows of TX·VEC·sizeof(T) bytes per instruction),
 // the TY = 256/TX thread rows stride down the axis keeping one online (max, Σ) pair per column, a shared-memory
@@ -419,6 +483,24 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
       HPTB_CUDA_CHECK(cudaGetLastError());
       count_launches(1);
       return HPTB_OK;
+    }
+  }
+  if constexpr (VECMAX > 1) {
+    // long unit-stride rows with pack-aligned starts: the vectorised streaming kernel
+    if (p.sa_in == 1 && p.sa_out == 1 && p.L % VECMAX == 0) {
+      size_t ai = sizeof(T) * VECMAX > 16 ? 16 : sizeof(T) * VECMAX, ao = sizeof(O) * VECMAX > 16 ? 16 : sizeof(O) * VECMAX;
+      bool ok = !(reinterpret_cast<uintptr_t>(in) % ai) && !(reinterpret_cast<uintptr_t>(out) % ao);
+      for (int i = 0; ok && i < nk; ++i) {
+        if ((uint64_t)(std::llabs(c.strides[1][kept[i]]) * (int64_t)sizeof(T)) % ai) ok = false;
+        if ((uint64_t)(std::llabs(c.strides[0][kept[i]]) * (int64_t)sizeof(O)) % ao) ok = false;
+      }
+      if (ok) {
+        int64_t blocks = M < (int64_t)ctx->sm_count * 16 ? M : (int64_t)ctx->sm_count * 16;
+        HPTB_CUDA_CHECK(launch_kernel(softmax_rows_stream_vec<T, VECMAX>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p));
+        HPTB_CUDA_CHECK(cudaGetLastError());
+        count_launches(1);
+        return HPTB_OK;
+      }
     }
   }
   const bool cols_ok = nk > 0 && c.strides[1][kept[0]] == 1 && c.strides[0][kept[0]] == 1 && !(p.sa_in == 1 && p.sa_out == 1) &&
@@ -688,6 +770,25 @@ extern "C" hptb_status hptb_softmax(hptb_ctx* ctx, const hptb_tensor* in, int ax
   for (int i = 0; same && i < in->ndim; ++i) same = in->shape[i] == out->shape[i];
   if (!same) return fail(HPTB_ERR_SHAPE, "softmax: out shape differs from the input shape");
   pass_direction(ctx, in->data, 0, false);  // a forward streaming pass (snake order, context.h)
+  // The axis is the input's unit-stride dim but the output runs along another dim (x.t().softmax(0) into a fresh
+  // contiguous tensor): every row kernel would scatter 4-byte writes over separate lines (f32 [8192,4096]ᵀ: 319 µs).
+  // Normalise into a scratch laid out in the INPUT's dim order (register-resident row kernel), then let the
+  // transposing copy kernel move it: two coalesced passes (≈ 95 µs) instead of one scattered one.
+  if (in->strides[axis] == 1 && out->strides[axis] != 1 && in->shape[axis] >= 32 && numel(*in) >= (1 << 16)) {
+    hptb_tensor tmp = *out;
+    int order[HPTB_MAX_DIMS];
+    for (int i = 0; i < in->ndim; ++i) order[i] = i;
+    std::sort(order, order + in->ndim, [&](int a, int b) { return std::llabs(in->strides[a]) > std::llabs(in->strides[b]); });
+    int64_t st = 1;
+    for (int j = in->ndim - 1; j >= 0; --j) { tmp.strides[order[j]] = st; st *= in->shape[order[j]]; }
+    if (tmp.strides[axis] == 1) {
+      Scratch sc;
+      HPTB_TRY(sc.get(ctx, (size_t)numel(*out) * dtype_size(out->dtype), stream));
+      tmp.data = sc.ptr;
+      HPTB_TRY(hptb_softmax(ctx, in, axis, log, &tmp, stream));
+      return hptb_copy(ctx, &tmp, out, stream);
+    }
+  }
   uint8_t mask[HPTB_MAX_DIMS] = {0};
   mask[axis] = 1;
   int64_t strides[kMaxOperands][HPTB_MAX_DIMS] = {{0}};
