@@ -43,6 +43,7 @@ struct SoftmaxParams {
   DimWalk outer;    // cols_tiled: the kept dims other than the contiguous one
   int64_t C;        // cols_tiled: extent of the contiguous kept dim
   int64_t ctiles;   // cols_tiled: column tiles per outer index
+  int64_t rps;      // cols_tiled: axis positions per split (gridDim.y splits)
 };
 
 template <typename C> __device__ __forceinline__ C sm_exp(C x) {
@@ -335,16 +336,22 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
 // the TY = 256/TX thread rows stride down the axis keeping one online (max, Σ) pair per column, a shared-memory
 // tree merges the thread rows, then a second sweep writes.  2 reads + 1 write; the column-per-thread kernel this
 // replaces for wide tensors ran 4096 serial steps on 32 CTAs (f32 [4096,8192] axis 0: 4050 µs).
-template <typename T, int VEC, int TX>
+// PHASE 0: the whole job in one launch.  When the column tiles alone cannot fill the GPU the axis is split over
+// gridDim.y CTAs and the job becomes two launches: PHASE 1 leaves one (max, Σ) pair per (split, column) in `part`,
+// PHASE 2 merges a column's pairs (in split order: deterministic) and writes its own slab of rows.
+template <typename T, int VEC, int TX, int PHASE>
 __global__ void __launch_bounds__(kSmThreads)
 softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
-                   SoftmaxParams p) {
+                   compute_t<typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type>* __restrict__ part, SoftmaxParams p) {
   pdl_prologue();
   typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type O;
   typedef compute_t<O> C;
   constexpr int TY = kSmThreads / TX, W = TX * VEC, UN = 4;
-  __shared__ C s_m[TY][W], s_s[TY][W];
+  __shared__ C s_m[PHASE == 2 ? 1 : TY][W], s_s[PHASE == 2 ? 1 : TY][W];
   const int lane = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int64_t e_begin = (int64_t)blockIdx.y * p.rps;
+  const int64_t e_end = e_begin + p.rps < p.L ? e_begin + p.rps : p.L;
+  const int64_t ncols = (int64_t)gridDim.x * W;  // row length of the `part` arrays (padded to whole tiles)
   const int64_t outer = (int64_t)blockIdx.x / p.ctiles, tile = (int64_t)blockIdx.x - outer * p.ctiles;
   const int64_t col0 = tile * W + (int64_t)lane * VEC;
   int64_t in_off = 0, out_off = 0;
@@ -355,32 +362,56 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
   MS<C> a[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) a[k] = MS<C>{Limits<C>::lowest(), (C)0};
-  if (active) {
-    for (int64_t e = ty; e < p.L; e += (int64_t)TY * UN) {
-      Pack<T, VEC> v[UN];
+  if constexpr (PHASE != 2) {
+    if (active) {
+      for (int64_t e = e_begin + ty; e < e_end; e += (int64_t)TY * UN) {
+        Pack<T, VEC> v[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u)
-        if (e + (int64_t)u * TY < p.L) load_pack<T, VEC>(v[u], src + (e + (int64_t)u * TY) * p.sa_in);
+        for (int u = 0; u < UN; ++u)
+          if (e + (int64_t)u * TY < e_end) load_pack<T, VEC>(v[u], src + (e + (int64_t)u * TY) * p.sa_in);
 #pragma unroll
-      for (int u = 0; u < UN; ++u)
-        if (e + (int64_t)u * TY < p.L) {
+        for (int u = 0; u < UN; ++u)
+          if (e + (int64_t)u * TY < e_end) {
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) ms_push_fast<C>(a[k], to_compute<O>(cast<O>(v[u].v[k])));
-        }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) { s_m[ty][lane * VEC + k] = a[k].m; s_s[ty][lane * VEC + k] = a[k].s; }
-  __syncthreads();
-#pragma unroll 1
-  for (int off = TY / 2; off > 0; off >>= 1) {
-    if (ty < off) {
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        a[k] = ms_combine<C>(a[k], MS<C>{s_m[ty + off][lane * VEC + k], s_s[ty + off][lane * VEC + k]});
-        s_m[ty][lane * VEC + k] = a[k].m;
-        s_s[ty][lane * VEC + k] = a[k].s;
+            for (int k = 0; k < VEC; ++k) ms_push_fast<C>(a[k], to_compute<O>(cast<O>(v[u].v[k])));
+          }
       }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { s_m[ty][lane * VEC + k] = a[k].m; s_s[ty][lane * VEC + k] = a[k].s; }
+    __syncthreads();
+#pragma unroll 1
+    for (int off = TY / 2; off > 0; off >>= 1) {
+      if (ty < off) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          a[k] = ms_combine<C>(a[k], MS<C>{s_m[ty + off][lane * VEC + k], s_s[ty + off][lane * VEC + k]});
+          s_m[ty][lane * VEC + k] = a[k].m;
+          s_s[ty][lane * VEC + k] = a[k].s;
+        }
+      }
+      __syncthreads();
+    }
+    if constexpr (PHASE == 1) {  // one pair per (split, column)
+      if (ty == 0) {
+        C* pm = part + ((int64_t)blockIdx.y * 2) * ncols + (int64_t)blockIdx.x * W + lane * VEC;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { pm[k] = a[k].m; pm[ncols + k] = a[k].s; }
+      }
+      return;
+    }
+  } else {
+    // merge the column's per-split pairs in split order; every thread row needs them, thread row 0 fetches
+    if (ty == 0) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) a[k] = MS<C>{Limits<C>::lowest(), (C)0};
+      for (int sp = 0; sp < (int)gridDim.y; ++sp) {
+        const C* pm = part + ((int64_t)sp * 2) * ncols + (int64_t)blockIdx.x * W + lane * VEC;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) a[k] = ms_combine<C>(a[k], MS<C>{pm[k], pm[ncols + k]});
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { s_m[0][lane * VEC + k] = a[k].m; s_s[0][lane * VEC + k] = a[k].s; }
     }
     __syncthreads();
   }
@@ -392,14 +423,14 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
     inv[k] = (C)1 / s_s[0][lane * VEC + k];  // one division per column; the per-element multiply adds ≤ 0.5 ulp
     lg[k] = sm_log<C>(s_s[0][lane * VEC + k]);
   }
-  for (int64_t e = ty; e < p.L; e += (int64_t)TY * UN) {
+  for (int64_t e = e_begin + ty; e < e_end; e += (int64_t)TY * UN) {
     Pack<T, VEC> v[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u)
-      if (e + (int64_t)u * TY < p.L) load_pack<T, VEC>(v[u], src + (e + (int64_t)u * TY) * p.sa_in);
+      if (e + (int64_t)u * TY < e_end) load_pack<T, VEC>(v[u], src + (e + (int64_t)u * TY) * p.sa_in);
 #pragma unroll
     for (int u = 0; u < UN; ++u)
-      if (e + (int64_t)u * TY < p.L) {
+      if (e + (int64_t)u * TY < e_end) {
         Pack<O, VEC> o;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
@@ -530,9 +561,33 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
     p.ctiles = (p.C + (int64_t)tx * vec - 1) / ((int64_t)tx * vec);
     const int64_t blocks = outer_n * p.ctiles;
     if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "softmax: grid too large");
-    if (vec > 1 && tx == 32) HPTB_CUDA_CHECK(launch_kernel(softmax_cols_tiled<T, VECMAX, 32>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p));
-    else if (vec > 1) HPTB_CUDA_CHECK(launch_kernel(softmax_cols_tiled<T, VECMAX, 8>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p));
-    else HPTB_CUDA_CHECK(launch_kernel(softmax_cols_tiled<T, 1, 32>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p));
+    // splits of the axis: up to ≈ 8 CTAs per SM in total, each thread row keeping ≥ 2 batches of loads
+    const int ty = kSmThreads / tx;
+    int64_t S = ((int64_t)ctx->sm_count * 8 + blocks - 1) / blocks;
+    const int64_t max_s = p.L / ((int64_t)ty * 4 * 2);
+    if (S > max_s) S = max_s;
+    if (S > 64) S = 64;
+    if (S < 1) S = 1;
+    p.rps = (p.L + S - 1) / S;
+    S = (p.L + p.rps - 1) / p.rps;
+    typedef compute_t<O> CT;
+    Scratch part;
+    CT* pp = nullptr;
+    if (S > 1) {
+      HPTB_TRY(part.get(ctx, (size_t)S * 2 * (size_t)blocks * tx * vec * sizeof(CT), stream));
+      pp = static_cast<CT*>(part.ptr);
+    }
+#define HPTB_SMC(V, X, PH) HPTB_CUDA_CHECK(launch_kernel(softmax_cols_tiled<T, V, X, PH>, dim3((unsigned)blocks, (unsigned)(PH == 0 ? 1 : S)), dim3(kSmThreads), 0, stream, in, out, pp, p))
+#define HPTB_SMC_ALL(PH)                                  \
+  do {                                                    \
+    if (vec > 1 && tx == 32) HPTB_SMC(VECMAX, 32, PH);    \
+    else if (vec > 1) HPTB_SMC(VECMAX, 8, PH);            \
+    else HPTB_SMC(1, 32, PH);                             \
+  } while (0)
+    if (S == 1) HPTB_SMC_ALL(0);
+    else { HPTB_SMC_ALL(1); HPTB_SMC_ALL(2); count_launches(1); }
+#undef HPTB_SMC_ALL
+#undef HPTB_SMC
   } else if (cols_ok) {
     int64_t blocks = (M + kSmThreads - 1) / kSmThreads;
     if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "softmax: grid too large");
