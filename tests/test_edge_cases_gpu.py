@@ -163,16 +163,21 @@ def test_index_beyond_int32(hb):
     torch.cuda.empty_cache()
 
 
-def _softmax_check_long(hb, x, axis, log):
-    """Rows beyond the register-resident limit (8192 f32) stream through an online (max, Σ) pass: every output then
-    also carries the rounding of an f32 sum of L terms (each thread adds L/256 terms in sequence, then a tree), which
-    BASELINE.json bounds by 1e-6·log2(n) relative.  Bar: the elementwise 4 + |x − max| ulp of _softmax_check plus
-    min(L/2048, 1e-6·log2(L)/2^-23) ulp for Σ; log_softmax: the same amount as an absolute error of ln Σ."""
+def _softmax_check_long(hb, x, axis, log, view=None):
+    """The ONLINE kernels (rows beyond the register-resident limit of 8192 f32, and every strided axis) keep a running
+    (max, Σ) pair: whenever the running max moves, Σ is rescaled by an exp() that is itself good to ≈ 3 ulp, a thread
+    sees ≈ log2 of its share of L new maxima and the thread rows / splits merge the same way, so Σ — and with it every
+    output — carries ≈ 3·(1 + log2 L) ulp on top of the plain f32 summation error (L/2048 ulp for L/256 sequential
+    adds per thread).  BASELINE.json bounds sums by 1e-6·log2(n) relative, which caps the allowance.  Bar: the
+    elementwise 4 + |x − max| ulp of _softmax_check plus that allowance; log_softmax: the same as an absolute error
+    of ln Σ."""
     X = hb.Tensor.to_cuda(to_torch(x, "f32"))
+    if view:
+        X, x = view(X), view(x)
     got = (X.log_softmax(axis) if log else X.softmax(axis)).to_cpu().numpy()
     want, od = O.softmax(x, "f32", axis, log)
     L = x.shape[axis]
-    extra = min(np.ceil(L / 2048), 1e-6 * np.log2(L) / 2.0 ** -23)
+    extra = min(np.ceil(L / 2048) + 3 * (1 + np.ceil(np.log2(L))), 1e-6 * np.log2(max(L, 2)) / 2.0 ** -23)
     xc = x.astype(np.float64)
     shift = np.abs(xc - xc.max(axis=axis, keepdims=True))
     if log:
@@ -200,3 +205,59 @@ def test_softmax_row_lengths_around_the_register_limit(hb):
     x = rand(rng, (70000, 3), "f32")  # strided axis: one thread walks a column
     _softmax_check_long(hb, x, 0, False)
     _softmax_check_long(hb, x, 0, True)
+
+
+def test_stepped_reversed_and_ragged_rows_scalar_path(hb):
+    """map_rows_kernel<VEC = 1>: stepped / reversed inner dims and rows off the pack boundary, every element size,
+    unary and binary (operands with DIFFERENT inner strides), large enough for several CTAs."""
+    rng = np.random.default_rng(46)
+    for d in ("f32", "bf16", "f64", "i8", "i64"):
+        x = rand(rng, (300, 1030), d, -50, 50) if d in O.INTS else rand(rng, (300, 1030), d)
+        y = rand(rng, (300, 1030), d, -50, 50) if d in O.INTS else rand(rng, (300, 1030), d)
+        for v in (lambda t: t[:, ::2], lambda t: t[:, ::-1], lambda t: t[:, 1::3], lambda t: t[7:, 5:1028], lambda t: t[::-2, 3:1000:7]):
+            run_binary(hb, "add", x, d, y, d, v, v)
+            run_binary(hb, "mul", x, d, np.ascontiguousarray(v(y)), d, v, None)   # stepped ⊕ contiguous
+            if d in ("f32", "bf16", "f64"):
+                check_unary(hb, "exp", x, d, view=v)
+    z = rand(rng, (2_000_000,), "f32")  # one stepped dim, > 2^20 elements: the 1-D form of a[:, ::2]
+    check_unary(hb, "sin", z, "f32", view=lambda t: t[::2])
+    check_unary(hb, "sin", z, "f32", view=lambda t: t[::-1])
+    run_binary(hb, "sub", z, "f32", z, "f32", lambda t: t[::2], lambda t: t[1::2])
+
+
+@pytest.mark.parametrize("op", ["sum", "max", "argmax", "mean", "logsumexp", "prod"])
+def test_transposing_reductions_two_step(hb, op):
+    """The output's fastest dim is not the input's fastest kept dim (api_reduce.cpp reduces into an input-ordered
+    scratch and gathers): permuted 3-D and 4-D views, every op class, i64 exactness."""
+    rng = np.random.default_rng(47)
+    x = rand(rng, (40, 24, 64), "f32") * (0.05 if op == "prod" else 1.0) + (1.0 if op == "prod" else 0.0)
+    p201 = lambda t: t.permute([2, 0, 1]) if hasattr(t, "storage") else np.transpose(t, (2, 0, 1))
+    p120 = lambda t: t.permute([1, 2, 0]) if hasattr(t, "storage") else np.transpose(t, (1, 2, 0))
+    check_reduce(hb, op, x, "f32", [2], view=p201)   # kept (orig 2, orig 0): out fastest = orig 0, in fastest = orig 2
+    check_reduce(hb, op, x, "f32", [0], view=p120)   # reduce orig 1; kept (orig 2, orig 0) again
+    if op not in ("argmax",):
+        w = rand(rng, (12, 9, 10, 48), "f32") * (0.05 if op == "prod" else 1.0) + (1.0 if op == "prod" else 0.0)
+        p3012 = lambda t: t.permute([3, 0, 1, 2]) if hasattr(t, "storage") else np.transpose(t, (3, 0, 1, 2))
+        check_reduce(hb, op, w, "f32", [1, 3], view=p3012)
+    if op in ("sum", "max", "argmax"):
+        xi = rand(rng, (40, 24, 64), "i64", -1000, 1000)
+        check_reduce(hb, op, xi, "i64", [2], view=p201)
+
+
+def test_softmax_strided_axis_tiled_and_two_step(hb):
+    """softmax_cols_tiled (one launch and the split-axis two-phase form, packs and scalars, 32 and 8 lanes) and the
+    two-step path for an axis that is contiguous in the input but not in the output."""
+    rng = np.random.default_rng(48)
+    for shape in [(5000, 40), (5000, 37), (300, 4096), (64, 8), (9000, 256), (33, 7, 130)]:
+        for log in (False, True):
+            _softmax_check_long(hb, rand(rng, shape, "f32") * 3, 0, log)
+            _softmax_check(hb, rand(rng, shape, "bf16"), "bf16", 0, log)  # one bf16 ulp dwarfs the Σ allowance
+    x3 = rand(rng, (33, 700, 130), "f32")
+    _softmax_check_long(hb, x3, 1, False)        # middle axis: outer dims on both sides of the column tiles
+    t = rand(rng, (64, 1100), "f32") * 3
+    tv = lambda a: a.t() if hasattr(a, "storage") else a.T
+    _softmax_check(hb, t, "f32", 0, False, tv)   # axis contiguous in the input, output contiguous the other way:
+    _softmax_check(hb, t, "f32", 0, True, tv)    # the register-resident row kernel + a transposing copy
+    t3 = rand(rng, (40, 50, 64), "f32")
+    pv = lambda a: a.permute([2, 0, 1]) if hasattr(a, "storage") else np.transpose(a, (2, 0, 1))
+    _softmax_check(hb, t3, "f32", 0, False, pv)
