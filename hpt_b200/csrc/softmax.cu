@@ -271,15 +271,17 @@ softmax_cols(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_o
 // Long unit-stride rows (more than 8 packs per thread): one CTA per row, 16-byte loads with four in flight per
 // thread, an online (max, Σ) sweep and a write sweep whose reads come back from L2 (a row is ≤ a few MB).  The scalar
 // softmax_rows_stream below stays for strided axes: f32 [256,131072] softmax(1) 551 µs through it.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(kSmThreads)
+// NT = 1024 threads for rows of ≥ 8192 packs: a grid of a few hundred rows otherwise leaves each SM with one or two
+// 256-thread CTAs (f32 [256,131072]: 118 µs with 256 threads per row)
+template <typename T, int VEC, int NT>
+__global__ void __launch_bounds__(NT)
 softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
                         SoftmaxParams p) {
   pdl_prologue();
   typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type O;
   typedef compute_t<O> C;
   constexpr int UN = 4;
-  __shared__ C s_m[kSmThreads / 32], s_s[kSmThreads / 32];
+  __shared__ C s_m[NT / 32], s_s[NT / 32];
   const int tid = threadIdx.x;
   const int64_t packs = p.L / VEC;  // the host picks this kernel only when L is a multiple of VEC
   for (int64_t row = blockIdx.x; row < p.M; row += gridDim.x) {
@@ -288,14 +290,14 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
     const T* src = in + in_off;
     O* dst = out + out_off;
     MS<C> a{Limits<C>::lowest(), (C)0};
-    for (int64_t c = tid; c < packs; c += (int64_t)kSmThreads * UN) {
+    for (int64_t c = tid; c < packs; c += (int64_t)NT * UN) {
       Pack<T, VEC> v[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u)
-        if (c + (int64_t)u * kSmThreads < packs) load_pack<T, VEC>(v[u], src + (c + (int64_t)u * kSmThreads) * VEC);
+        if (c + (int64_t)u * NT < packs) load_pack<T, VEC>(v[u], src + (c + (int64_t)u * NT) * VEC);
 #pragma unroll
       for (int u = 0; u < UN; ++u)
-        if (c + (int64_t)u * kSmThreads < packs) {
+        if (c + (int64_t)u * NT < packs) {
 #pragma unroll
           for (int k = 0; k < VEC; ++k) ms_push_fast<C>(a, to_compute<O>(cast<O>(v[u].v[k])));
         }
@@ -309,23 +311,23 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
     if ((tid & 31) == 0) { s_m[tid >> 5] = a.m; s_s[tid >> 5] = a.s; }
     __syncthreads();
     MS<C> r{Limits<C>::lowest(), (C)0};
-    for (int w = 0; w < kSmThreads / 32; ++w) r = ms_combine<C>(r, MS<C>{s_m[w], s_s[w]});
+    for (int w = 0; w < NT / 32; ++w) r = ms_combine<C>(r, MS<C>{s_m[w], s_s[w]});
     const C inv = (C)1 / r.s, lg = sm_log<C>(r.s);
-    for (int64_t c = tid; c < packs; c += (int64_t)kSmThreads * UN) {
+    for (int64_t c = tid; c < packs; c += (int64_t)NT * UN) {
       Pack<T, VEC> v[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u)
-        if (c + (int64_t)u * kSmThreads < packs) load_pack_cached<T, VEC>(v[u], src + (c + (int64_t)u * kSmThreads) * VEC);
+        if (c + (int64_t)u * NT < packs) load_pack_cached<T, VEC>(v[u], src + (c + (int64_t)u * NT) * VEC);
 #pragma unroll
       for (int u = 0; u < UN; ++u)
-        if (c + (int64_t)u * kSmThreads < packs) {
+        if (c + (int64_t)u * NT < packs) {
           Pack<O, VEC> o;
 #pragma unroll
           for (int k = 0; k < VEC; ++k) {
             const C sh = to_compute<O>(cast<O>(v[u].v[k])) - r.m;
             o.v[k] = from_compute<O>(p.log ? sh - lg : sm_exp_fast(sh) * inv);
           }
-          store_pack<O, VEC>(dst + (c + (int64_t)u * kSmThreads) * VEC, o);
+          store_pack<O, VEC>(dst + (c + (int64_t)u * NT) * VEC, o);
         }
     }
   }
@@ -527,7 +529,10 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
       }
       if (ok) {
         int64_t blocks = M < (int64_t)ctx->sm_count * 16 ? M : (int64_t)ctx->sm_count * 16;
-        HPTB_CUDA_CHECK(launch_kernel(softmax_rows_stream_vec<T, VECMAX>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p));
+        if (p.L / VECMAX >= 8192 && M < (int64_t)ctx->sm_count * 8)
+          HPTB_CUDA_CHECK(launch_kernel(softmax_rows_stream_vec<T, VECMAX, 1024>, dim3((unsigned)blocks), dim3(1024), 0, stream, in, out, p));
+        else
+          HPTB_CUDA_CHECK(launch_kernel(softmax_rows_stream_vec<T, VECMAX, kSmThreads>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p));
         HPTB_CUDA_CHECK(cudaGetLastError());
         count_launches(1);
         return HPTB_OK;
