@@ -261,3 +261,33 @@ def test_softmax_strided_axis_tiled_and_two_step(hb):
     t3 = rand(rng, (40, 50, 64), "f32")
     pv = lambda a: a.permute([2, 0, 1]) if hasattr(a, "storage") else np.transpose(a, (2, 0, 1))
     _softmax_check(hb, t3, "f32", 0, False, pv)
+
+
+def test_misaligned_rows_head_body_tail(hb):
+    """api_reduce.cpp peels rows that start off the 16-byte boundary into head + aligned body + tail and folds the
+    three partial results into `out` (init_out = 0): every foldable op, exact-accumulator dtypes, 2-D and 3-D."""
+    rng = np.random.default_rng(49)
+    for d in ("f32", "f64", "i8", "i32", "i64", "bool"):
+        m = rand(rng, (300, 1030), d, -3, 3) if d in O.INTS else rand(rng, (300, 1030), d)
+        for v in (lambda t: t[:, 1:1028], lambda t: t[2:, 3:], lambda t: t[:, 5:1029]):
+            for op in ("sum", "max", "min", "sum_square", "reducel1", "nansum", "all", "any"):
+                if d == "bool" and op in ("sum_square", "reducel1"):
+                    continue
+                mm = np.abs(m) if (op == "nansum" and d in ("f32", "f64")) else m  # the checker's nansum bound is relative to |Σ|
+                check_reduce(hb, op, mm, d, [1], view=v)
+                check_reduce(hb, op, mm, d, [0, 1], view=v)
+        c = rand(rng, (12, 40, 517), d, -3, 3) if d in O.INTS else rand(rng, (12, 40, 517), d)
+        check_reduce(hb, "sum", c, d, [2], view=lambda t: t[:, :, 3:515])   # row stride 517: NOT pack-aligned → scalar path
+        c = rand(rng, (12, 40, 528), d, -3, 3) if d in O.INTS else rand(rng, (12, 40, 528), d)  # 528 = 33·16: every dtype peels
+        for op in ("sum", "max", "min", "sum_square", "all", "any"):
+            if d == "bool" and op == "sum_square":
+                continue
+            check_reduce(hb, op, c, d, [2], view=lambda t: t[:, :, 3:515])
+            check_reduce(hb, op, c, d, [0, 2], view=lambda t: t[:, 1:, 1:519])
+            check_reduce(hb, op, c, d, [0, 1, 2], view=lambda t: t[:, :, 5:])
+    x = rand(rng, (300, 1030), "f32") * 0.01 + 1.0
+    check_reduce(hb, "prod", x, "f32", [1], view=lambda t: t[:, 1:200])
+    xn = np.abs(rand(rng, (300, 1030), "f32"))
+    xn[::7, ::5] = np.nan
+    check_reduce(hb, "nansum", xn, "f32", [1], view=lambda t: t[:, 3:1029])
+    check_reduce(hb, "nanprod", xn * 0.01 + 1.0, "f32", [1], view=lambda t: t[:, 3:300])
