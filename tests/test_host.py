@@ -193,3 +193,16 @@ def test_errors_without_gpu():
     t = make_tensor(0, ENUM["f32"], (2, 2), (2, 1))
     assert lib.hptb_binary(None, 0, byref(t), byref(t), byref(t), None) == 4
     assert b"null ctx" in lib.hptb_last_error()
+
+
+def test_rust_sys_crate_declares_every_abi_entry():
+    """rust/hpt-b200-sys is delivered as source (no cargo in the image): keep its extern block in step with the header."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "hpt_b200.h")).read()
+    rust = open(os.path.join(root, "rust", "hpt-b200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"\b(hptb_[a-z0-9_]+)\s*\(", header)) - {"hptb_status"}
+    bound = set(re.findall(r"pub fn (hptb_[a-z0-9_]+)", rust))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    # struct images that cross the boundary by value or pointer
+    assert "pub post_root: i32" in rust and "post_root" in header
