@@ -223,14 +223,20 @@ map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restric
       if (NIN == 2) o2 += (int32_t)r * p.outer_stride[2][last];
       oo[u] = o0;
       if (p.inner_stride[1] == 0) {
-        const A s = load_one(a + o1);
+        // a column operand ([N,1]): every chunk of a row re-reads the same element — let it live in L1 (the no-allocate
+        // load crossed to L2 per chunk: f32 a + column [8192,1] 104.7 µs against 80.0 µs for a + row)
+        Pack<A, 1> s1;
+        load_pack_cached<A, 1>(s1, a + o1);
+        const A s = s1.v[0];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) pa[u].v[k] = s;
       } else if (p.reuse[1]) load_pack_cached<A, VEC>(pa[u], a + o1);
       else load_pack<A, VEC>(pa[u], a + o1);
       if constexpr (NIN == 2) {
         if (p.inner_stride[2] == 0) {
-          const B s = load_one(b + o2);
+          Pack<B, 1> s1;
+          load_pack_cached<B, 1>(s1, b + o2);
+          const B s = s1.v[0];
 #pragma unroll
           for (int k = 0; k < VEC; ++k) pb[u].v[k] = s;
         } else if (p.reuse[2]) load_pack_cached<B, VEC>(pb[u], b + o2);
