@@ -58,6 +58,14 @@ class HptbCollapsePlan(Structure):
                 ("shape", c_int64 * MAX_DIMS), ("strides", (c_int64 * MAX_DIMS) * 4), ("reduced", c_uint8 * MAX_DIMS)]
 
 
+class HptbReduceRoute(Structure):
+    _fields_ = [("kind", c_int32), ("reserved", c_int32), ("head", c_int64), ("body", c_int64), ("tail", c_int64),
+                ("scratch_strides", c_int64 * MAX_DIMS)]
+
+
+ROUTES = ["direct", "peel", "two_step"]
+
+
 class HptbShardPlan(Structure):
     _fields_ = [("crosses", c_int32), ("collective", c_int32), ("pre_exp", c_int32), ("post_ln", c_int32),
                 ("global_count", c_int32), ("post_root", c_int32)]
@@ -108,6 +116,7 @@ SIGNATURES = {
     "hptb_process_axes": (c_int, [POINTER(c_int64), c_int, c_int, POINTER(c_int32)]),
     "hptb_reduce_shape": (c_int, [POINTER(c_int64), c_int, POINTER(c_int32), c_int, c_int, POINTER(c_int64), POINTER(c_int)]),
     "hptb_collapse": (c_int, [POINTER(_T), c_int, POINTER(c_uint8), POINTER(HptbCollapsePlan)]),
+    "hptb_reduce_route": (c_int, [c_int, _T, POINTER(c_int32), c_int, _T, c_int, POINTER(HptbReduceRoute)]),
     "hptb_binary": (c_int, [c_void_p, c_int, _T, _T, _T, c_void_p]),
     "hptb_compare": (c_int, [c_void_p, c_int, _T, _T, _T, c_void_p]),
     "hptb_unary": (c_int, [c_void_p, c_int, _T, _T, c_double, c_double, c_void_p]),

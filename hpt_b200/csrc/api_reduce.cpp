@@ -161,6 +161,84 @@ hptb_status build_reduce_plan(hptb_ctx* ctx, const hptb_tensor* in, const int32_
 }  // namespace hptb
 
 namespace hptb {
+// Host-side routing of one reduction (pure: looks at shapes, strides, dtypes and the alignment of in->data only).
+//
+// PEEL — rows that start off the 16-byte boundary (a[5:8000, 3:8100].sum(1)): every row has the same misalignment when
+// the other strides are multiples of a pack, so a row is head (< one pack) + aligned body + tail.  The body takes the
+// vector kernels; head and tail are folded into `out` by two tiny launches (init_out = 0).  Only where `out` holds
+// the accumulator exactly (f32 / f64 / integers) and the op folds associatively.  (Scalar loads through the general
+// kernel: 26 issued instructions per element, 82.7 µs for that f32 window against 40.4 µs peeled; torch 52.7 µs.)
+//
+// TWO_STEP — transposing reduction: the input's fastest KEPT dim is not the output's fastest dim
+// (x.permute(2,0,1).sum(2)): the lanes that read a full line would each write to a different line, and no kernel
+// class is coalesced on both sides (0.13 of peak through the general kernel).  The output is the small side, so
+// reduce into a scratch laid out in the INPUT's dim order (coalesced cols / rows kernels apply) and gather it
+// into `out` afterwards (319 → 49 µs).
+void plan_reduce_route(int op, const hptb_tensor* in, const int32_t* axes, int naxes, const hptb_tensor* out, int init_out,
+                       double count_override, hptb_reduce_route_t* route) {
+  memset(route, 0, sizeof(*route));
+  route->kind = HPTB_ROUTE_DIRECT;
+  if (init_out && naxes >= 1 && in->ndim >= 1 && in->data && count_override < 0 && count_override != -2.0) {
+    const int last = in->ndim - 1;
+    const size_t esz = dtype_size(in->dtype);
+    const int64_t pack = esz <= 8 ? (int64_t)(16 / esz) : 1;
+    const bool op_ok = op == HPTB_SUM || op == HPTB_MAX || op == HPTB_MIN || op == HPTB_PROD || op == HPTB_SUM_SQUARE ||
+                       op == HPTB_REDUCEL1 || op == HPTB_NANSUM || op == HPTB_NANPROD || op == HPTB_ALL || op == HPTB_ANY;
+    const bool dt_ok = in->dtype != HPTB_F16 && in->dtype != HPTB_BF16;
+    bool has_last = false;
+    for (int i = 0; i < naxes; ++i) has_last |= axes[i] == last;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(in->data);
+    if (op_ok && dt_ok && has_last && pack >= 2 && in->strides[last] == 1 && in->shape[last] >= 64 && numel(*in) >= (1 << 16) &&
+        addr % esz == 0 && addr % 16 != 0) {
+      bool rows_ok = true;
+      for (int d = 0; d < last; ++d)
+        if (in->shape[d] > 1 && (uint64_t)(std::llabs(in->strides[d]) * (int64_t)esz) % 16) rows_ok = false;
+      if (rows_ok) {
+        const int64_t L = in->shape[last];
+        route->kind = HPTB_ROUTE_PEEL;
+        route->head = pack - (int64_t)((addr % 16) / esz);
+        route->body = ((L - route->head) / pack) * pack;
+        route->tail = L - route->head - route->body;
+        return;
+      }
+    }
+  }
+  if (init_out && count_override != -2.0 && in->ndim > 0 && out->ndim >= 2) {
+    uint8_t mask[HPTB_MAX_DIMS] = {0};
+    bool ok = true;
+    for (int i = 0; i < naxes; ++i) {
+      if (axes[i] < 0 || axes[i] >= in->ndim) { ok = false; break; }
+      mask[axes[i]] = 1;
+    }
+    int src_dim[HPTB_MAX_DIMS], nk = 0;
+    double red = 1.0;
+    for (int i = 0; ok && i < in->ndim; ++i) {
+      if (mask[i]) red *= (double)in->shape[i];
+      else src_dim[nk++] = i;
+    }
+    if (ok && nk == out->ndim && red >= 8.0) {
+      int fin = -1, fout = -1;  // fastest kept dim on the input side / on the output side (extent > 1)
+      for (int j = 0; j < nk; ++j) {
+        if (out->shape[j] <= 1) continue;
+        if (fin < 0 || std::llabs(in->strides[src_dim[j]]) < std::llabs(in->strides[src_dim[fin]])) fin = j;
+        if (fout < 0 || std::llabs(out->strides[j]) < std::llabs(out->strides[fout])) fout = j;
+      }
+      if (fin >= 0 && fin != fout && std::llabs(in->strides[src_dim[fin]]) == 1 && out->shape[fin] >= 32 && numel(*out) > 0) {
+        int order[HPTB_MAX_DIMS];  // out dims from the slowest to the fastest input stride
+        for (int j = 0; j < nk; ++j) order[j] = j;
+        std::sort(order, order + nk, [&](int a, int b) {
+          return std::llabs(in->strides[src_dim[a]]) > std::llabs(in->strides[src_dim[b]]);
+        });
+        int64_t st = 1;
+        for (int j = nk - 1; j >= 0; --j) { route->scratch_strides[order[j]] = st; st *= out->shape[order[j]]; }
+        route->kind = HPTB_ROUTE_TWO_STEP;
+      }
+    }
+  }
+}
+}  // namespace hptb
+
+namespace hptb {
 hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, hptb_tensor* out,
                         int init_out, double count_override, void* stream);
 }
@@ -185,6 +263,15 @@ hptb_status hptb_reduce(hptb_ctx* ctx, int op, const hptb_tensor* in, const int3
   return reduce_impl(ctx, op, in, axes, naxes, out, init_out, -1.0, stream);
 }
 
+hptb_status hptb_reduce_route(int op, const hptb_tensor* in, const int32_t* axes, int naxes, const hptb_tensor* out,
+                              int init_out, hptb_reduce_route_t* route) {
+  if (!in || !out || !route || (!axes && naxes)) return fail(HPTB_ERR_INVALID, "reduce_route: null argument");
+  HPTB_TRY(validate_tensor(in, "reduce_route in"));
+  HPTB_TRY(validate_tensor(out, "reduce_route out"));
+  plan_reduce_route(op, in, axes, naxes, out, init_out, -1.0, route);
+  return HPTB_OK;
+}
+
 }  // extern "C"
 
 namespace hptb {
@@ -202,87 +289,34 @@ hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int3
     return fail(HPTB_ERR_DTYPE, "reduce: out dtype is %s, expected %s", dtype_name(out->dtype), dtype_name(odt));
   ReduceLauncher fn = reduce_launcher(op, in->dtype);
   if (!fn) return fail(HPTB_ERR_DTYPE, "reduce: no kernel for op %d on %s", op, dtype_name(in->dtype));
-  // Rows that start off the 16-byte boundary (a[5:8000, 3:8100].sum(1)): every row has the same misalignment when the
-  // other strides are multiples of a pack, so the row is head (< one pack) + aligned body + tail.  The body takes the
-  // vector kernels; head and tail are folded into `out` by two tiny launches (init_out = 0).  Only where `out` holds
-  // the accumulator exactly (f32 / f64 / integers) and the op folds associatively.  (Scalar loads through the general
-  // kernel: 26 issued instructions per element, 82.7 µs for that f32 window; torch 52.7 µs.)
-  if (init_out && naxes >= 1 && in->ndim >= 1 && in->data && count_override < 0 && count_override != -2.0) {
+  // host-side routing (plan_reduce_route above): peel misaligned rows, or reduce into an input-ordered scratch
+  hptb_reduce_route_t route;
+  plan_reduce_route(op, in, axes, naxes, out, init_out, count_override, &route);
+  if (route.kind == HPTB_ROUTE_PEEL) {
     const int last = in->ndim - 1;
-    const size_t esz = dtype_size(in->dtype);
-    const int64_t pack = esz <= 8 ? (int64_t)(16 / esz) : 1;
-    const bool op_ok = op == HPTB_SUM || op == HPTB_MAX || op == HPTB_MIN || op == HPTB_PROD || op == HPTB_SUM_SQUARE ||
-                       op == HPTB_REDUCEL1 || op == HPTB_NANSUM || op == HPTB_NANPROD || op == HPTB_ALL || op == HPTB_ANY;
-    const bool dt_ok = in->dtype != HPTB_F16 && in->dtype != HPTB_BF16;
-    bool has_last = false;
-    for (int i = 0; i < naxes; ++i) has_last |= axes[i] == last;
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(in->data);
-    if (op_ok && dt_ok && has_last && pack >= 2 && in->strides[last] == 1 && in->shape[last] >= 64 && numel(*in) >= (1 << 16) &&
-        addr % esz == 0 && addr % 16 != 0) {
-      bool rows_ok = true;
-      for (int d = 0; d < last; ++d)
-        if (in->shape[d] > 1 && (uint64_t)(std::llabs(in->strides[d]) * (int64_t)esz) % 16) rows_ok = false;
-      if (rows_ok) {
-        const int64_t L = in->shape[last];
-        const int64_t head = pack - (int64_t)((addr % 16) / esz);
-        const int64_t body = ((L - head) / pack) * pack;
-        const int64_t tail = L - head - body;
-        hptb_tensor part = *in;
-        part.data = static_cast<char*>(in->data) + head * (int64_t)esz;
-        part.shape[last] = body;
-        HPTB_TRY(reduce_impl(ctx, op, &part, axes, naxes, out, 1, count_override, stream));
-        part.data = in->data;
-        part.shape[last] = head;
-        HPTB_TRY(reduce_impl(ctx, op, &part, axes, naxes, out, 0, count_override, stream));
-        if (tail > 0) {
-          part.data = static_cast<char*>(in->data) + (head + body) * (int64_t)esz;
-          part.shape[last] = tail;
-          HPTB_TRY(reduce_impl(ctx, op, &part, axes, naxes, out, 0, count_override, stream));
-        }
-        return HPTB_OK;
-      }
+    const int64_t esz = (int64_t)dtype_size(in->dtype);
+    hptb_tensor part = *in;
+    part.data = static_cast<char*>(in->data) + route.head * esz;
+    part.shape[last] = route.body;
+    HPTB_TRY(reduce_impl(ctx, op, &part, axes, naxes, out, 1, count_override, stream));
+    part.data = in->data;
+    part.shape[last] = route.head;
+    HPTB_TRY(reduce_impl(ctx, op, &part, axes, naxes, out, 0, count_override, stream));
+    if (route.tail > 0) {
+      part.data = static_cast<char*>(in->data) + (route.head + route.body) * esz;
+      part.shape[last] = route.tail;
+      HPTB_TRY(reduce_impl(ctx, op, &part, axes, naxes, out, 0, count_override, stream));
     }
+    return HPTB_OK;
   }
-  // Transposing reduction: the input's fastest KEPT dim is not the output's fastest dim (x.permute(2,0,1).sum(2):
-  // the lanes that read a full line would each write to a different line, and no kernel class is coalesced on both
-  // sides — 0.13 of peak through the general kernel).  The output is the small side, so reduce into a scratch
-  // laid out in the INPUT's dim order (coalesced cols / rows kernels apply) and gather it into `out` afterwards.
-  if (init_out && count_override != -2.0 && in->ndim > 0 && out->ndim >= 2) {
-    uint8_t mask[HPTB_MAX_DIMS] = {0};
-    bool ok = true;
-    for (int i = 0; i < naxes; ++i) {
-      if (axes[i] < 0 || axes[i] >= in->ndim) { ok = false; break; }
-      mask[axes[i]] = 1;
-    }
-    int src_dim[HPTB_MAX_DIMS], nk = 0;
-    double red = 1.0;
-    for (int i = 0; ok && i < in->ndim; ++i) {
-      if (mask[i]) red *= (double)in->shape[i];
-      else src_dim[nk++] = i;
-    }
-    if (ok && nk == out->ndim && red >= 8.0) {
-      int fin = -1, fout = -1;  // fastest kept dim on the input side / on the output side (extent > 1)
-      for (int j = 0; j < nk; ++j) {
-        if (out->shape[j] <= 1) continue;
-        if (fin < 0 || std::llabs(in->strides[src_dim[j]]) < std::llabs(in->strides[src_dim[fin]])) fin = j;
-        if (fout < 0 || std::llabs(out->strides[j]) < std::llabs(out->strides[fout])) fout = j;
-      }
-      if (fin >= 0 && fin != fout && std::llabs(in->strides[src_dim[fin]]) == 1 && out->shape[fin] >= 32 && numel(*out) > 0) {
-        hptb_tensor tmp = *out;
-        int order[HPTB_MAX_DIMS];  // out dims from the slowest to the fastest input stride
-        for (int j = 0; j < nk; ++j) order[j] = j;
-        std::sort(order, order + nk, [&](int a, int b) {
-          return std::llabs(in->strides[src_dim[a]]) > std::llabs(in->strides[src_dim[b]]);
-        });
-        int64_t st = 1;
-        for (int j = nk - 1; j >= 0; --j) { tmp.strides[order[j]] = st; st *= out->shape[order[j]]; }
-        Scratch sc;
-        HPTB_TRY(sc.get(ctx, (size_t)numel(*out) * dtype_size(out->dtype), stream));
-        tmp.data = sc.ptr;
-        HPTB_TRY(reduce_impl(ctx, op, in, axes, naxes, &tmp, 1, count_override, stream));
-        return hptb_copy(ctx, &tmp, out, stream);
-      }
-    }
+  if (route.kind == HPTB_ROUTE_TWO_STEP) {
+    hptb_tensor tmp = *out;
+    for (int j = 0; j < out->ndim; ++j) tmp.strides[j] = route.scratch_strides[j];
+    Scratch sc;
+    HPTB_TRY(sc.get(ctx, (size_t)numel(*out) * dtype_size(out->dtype), stream));
+    tmp.data = sc.ptr;
+    HPTB_TRY(reduce_impl(ctx, op, in, axes, naxes, &tmp, 1, count_override, stream));
+    return hptb_copy(ctx, &tmp, out, stream);
   }
   ReducePlan plan;
   HPTB_TRY(build_reduce_plan(ctx, in, axes, naxes, out, &plan));

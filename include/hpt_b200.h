@@ -206,6 +206,20 @@ typedef struct {
 } hptb_collapse_plan;
 hptb_status hptb_collapse(const hptb_tensor* const* operands, int n_operands, const uint8_t* reduce_mask,
                           hptb_collapse_plan* plan);
+/* Host-side routing of a reduction (pure; no launch): how hptb_reduce will run it.  New functionality — the
+ * reference's planner (reduce.rs:641-838) has neither case.  DIRECT: one kernel.  PEEL: rows start off the 16-byte
+ * boundary with a common misalignment → head / aligned body / tail along the last axis, folded into `out`.
+ * TWO_STEP: the output's fastest dim is not the input's fastest kept dim → reduce into a scratch with
+ * `scratch_strides` (input dim order), then gather into `out`. */
+typedef enum hptb_route_kind { HPTB_ROUTE_DIRECT = 0, HPTB_ROUTE_PEEL = 1, HPTB_ROUTE_TWO_STEP = 2 } hptb_route_kind;
+typedef struct hptb_reduce_route_t {
+  int32_t kind;      /* hptb_route_kind */
+  int32_t reserved;
+  int64_t head, body, tail;                 /* PEEL: extents along the last axis */
+  int64_t scratch_strides[HPTB_MAX_DIMS];   /* TWO_STEP: element strides of the scratch, per `out` dim */
+} hptb_reduce_route_t;
+hptb_status hptb_reduce_route(int op, const hptb_tensor* in, const int32_t* axes, int naxes, const hptb_tensor* out,
+                              int init_out, hptb_reduce_route_t* route);
 
 /* ---- compute entry points ------------------------------------------------------------------------------- */
 /* out = op(cast(lhs), cast(rhs)) with numpy broadcasting.  `out->dtype` must equal

@@ -62,6 +62,17 @@ pub struct hptb_collapse_plan {
     pub reduced: [u8; HPTB_MAX_DIMS],
 }
 
+/// hptb_route_kind: 0 direct, 1 peel (head / aligned body / tail along the last axis), 2 two-step (input-ordered scratch)
+#[repr(C)] #[derive(Clone, Copy, Debug, Default)]
+pub struct hptb_reduce_route_t {
+    pub kind: i32,
+    pub reserved: i32,
+    pub head: i64,
+    pub body: i64,
+    pub tail: i64,
+    pub scratch_strides: [i64; HPTB_MAX_DIMS],
+}
+
 #[repr(C)] pub struct hptb_ctx { _private: [u8; 0] }
 #[repr(C)] pub struct hptb_comm { _private: [u8; 0] }
 #[repr(C)] #[derive(Clone, Copy, Debug, Default)]
@@ -100,6 +111,8 @@ extern "C" {
                              out_shape: *mut i64, out_ndim: *mut c_int) -> hptb_status;
     pub fn hptb_collapse(operands: *const *const hptb_tensor, n_operands: c_int, reduce_mask: *const u8,
                          plan: *mut hptb_collapse_plan) -> hptb_status;
+    pub fn hptb_reduce_route(op: c_int, input: *const hptb_tensor, axes: *const i32, naxes: c_int, out: *const hptb_tensor,
+                             init_out: c_int, route: *mut hptb_reduce_route_t) -> hptb_status;
     pub fn hptb_binary(ctx: *mut hptb_ctx, op: c_int, lhs: *const hptb_tensor, rhs: *const hptb_tensor,
                        out: *mut hptb_tensor, stream: *mut c_void) -> hptb_status;
     pub fn hptb_compare(ctx: *mut hptb_ctx, op: c_int, lhs: *const hptb_tensor, rhs: *const hptb_tensor,

@@ -206,3 +206,43 @@ def test_rust_sys_crate_declares_every_abi_entry():
     assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
     # struct images that cross the boundary by value or pointer
     assert "pub post_root: i32" in rust and "post_root" in header
+
+
+def test_reduce_route_is_pure_host_logic():
+    """hptb_reduce_route: how hptb_reduce will run a reduction — decided from shapes, strides, dtypes and the alignment of
+    the input pointer alone (api_reduce.cpp plan_reduce_route), so it is testable without a GPU."""
+    from hpt_b200._ffi import REDUCE_OPS, ROUTES, HptbReduceRoute
+
+    def route(op, dtype, shape, strides, axes, out_shape, out_strides, ptr=0x10000, init_out=1):
+        t_in = make_tensor(ptr, ENUM[dtype], shape, strides)
+        odt = lib.hptb_reduce_out_dtype(REDUCE_OPS[op], ENUM[dtype])
+        t_out = make_tensor(0x900000, odt, out_shape, out_strides)
+        r = HptbReduceRoute()
+        ax = (ctypes.c_int32 * len(axes))(*axes)
+        check(lib.hptb_reduce_route(REDUCE_OPS[op], byref(t_in), ax, len(axes), byref(t_out), init_out, byref(r)))
+        return ROUTES[r.kind], (r.head, r.body, r.tail), [r.scratch_strides[i] for i in range(len(out_shape))]
+
+    # aligned rows: direct
+    assert route("sum", "f32", (7995, 8097), (8192, 1), [1], (7995,), (1,))[0] == "direct"
+    # a[5:8000, 3:8100]: base 12 bytes past a 16-byte boundary, row stride 8192 elements → head 1, body 8096, tail 0
+    kind, hbt, _ = route("sum", "f32", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 3 * 4)
+    assert (kind, hbt) == ("peel", (1, 8096, 0))
+    kind, hbt, _ = route("max", "i8", (300, 1030), (1040, 1), [1], (300,), (1,), ptr=0x10000 + 5)
+    assert (kind, hbt) == ("peel", (11, 1008, 11))
+    # rows whose stride is not a multiple of a pack have no common misalignment; half types and non-folding ops do not peel
+    assert route("sum", "f32", (7995, 8097), (8191, 1), [1], (7995,), (1,), ptr=0x10000 + 12)[0] == "direct"
+    assert route("sum", "bf16", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 6)[0] == "direct"
+    assert route("mean", "f32", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 12)[0] == "direct"
+    assert route("argmax", "f32", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 12)[0] == "direct"
+    assert route("sum", "f32", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 12, init_out=0)[0] == "direct"
+    # x[256,512,512].permute(2,0,1).sum(2): view shape (512,256,512), strides (1,262144,512); out (512,256) contiguous.
+    # kept dims: view 0 (input stride 1) and view 1 (input stride 262144) → scratch strides (1, 512): input order
+    kind, _, ss = route("sum", "f32", (512, 256, 512), (1, 262144, 512), [2], (512, 256), (256, 1))
+    assert (kind, ss) == ("two_step", [1, 512])
+    # the same reduction into an output that already has the input's order needs no second step
+    assert route("sum", "f32", (512, 256, 512), (1, 262144, 512), [2], (512, 256), (1, 512))[0] == "direct"
+    # config 2 (transposed view, axis 0) and config 3 (NHWC view) are single-kept-dim reductions: direct
+    assert route("max", "f32", (8192, 8192), (1, 8192), [0], (8192,), (1,))[0] == "direct"
+    assert route("mean", "bf16", (64, 56, 56, 512), (1605632, 56, 1, 3136), [0, 1, 2], (512,), (1,))[0] == "direct"
+    # short reduced extents are not worth a second launch
+    assert route("sum", "f32", (512, 256, 4), (1, 2048, 512), [2], (512, 256), (256, 1))[0] == "direct"
