@@ -1,4 +1,4 @@
-"""bench_rows.py — the other BASELINE.json configurations, reported under "rows" by `bench.py --rows`.
+"""bench_rows.py — the other BASELINE.json configurations (1–4), reported under "rows" by `bench.py` (every run).
 
 Every row: device-resident inputs, CUDA-event timing on the launch stream, ≥3 warm-ups, median-free mean over
 `reps` launches; working sets that fit the 126 MB L2 (configs 1 and 4) rotate over 4 independent buffer sets so
@@ -103,55 +103,25 @@ def run_rows(hb, torch, dist, world, rank, local, stream, peak):
         add_row("cfg4", "add f32 [32,128,4096] + i64 [4096] → f64", us, 201359360, 16777216, "normal_promote f32⊕i64→f64")
         del X, Y, Z
 
-    # ---- config 5: f32 [262144,16384] sharded over the outer axis, full sum / mean, sum(0) -------------------------
-    def rows_cfg5():
-        rows_total, cols = 262144, 16384
-        rows_local = rows_total // world
-        big = torch.empty((rows_local, cols), device=dev, dtype=torch.float32)
-        for r0 in range(0, rows_local, 16384):  # generate in slabs to bound the temporary
-            big[r0:r0 + 16384].normal_(generator=g)
-        Xs = T.from_device_ptr(big.data_ptr(), F32, (rows_local, cols), device=local, keepalive=big)
-        comm = None
-        if world > 1:
-            idbuf = (ctypes.c_char * 128)()
-            if rank == 0:
-                _ffi.check(hb.lib.hptb_comm_unique_id(idbuf))
-            obj = [bytes(idbuf)]
-            dist.broadcast_object_list(obj, src=0)
-            comm = c_void_p()
-            _ffi.check(hb.lib.hptb_comm_init_rank(Xs.ctx.handle, world, rank, ctypes.c_char_p(obj[0]), byref(comm)))
+    # ---- config 2: f32 [8192,8192] transposed view: sin, exp, max(0), argmax(0) (input 268 MB > L2) -----------------------
+    def rows_cfg2():
+        X = dev_randn((8192, 8192))
+        V = X.t()
+        Y = T.empty((8192, 8192), F32, local)
+        Mx, Ai = T.empty((8192,), F32, local), T.empty((8192,), I64, local)
 
-        def sharded(op, axes, out):
-            ax = (c_int32 * len(axes))(*axes)
-            if comm is None:
-                _ffi.check(hb.lib.hptb_reduce(Xs.ctx.handle, _ffi.REDUCE_OPS[op], byref(Xs._c()), ax, len(axes), byref(out._c()), 1, hb.get_stream()))
-            else:
-                _ffi.check(hb.lib.hptb_reduce_sharded(comm, _ffi.REDUCE_OPS[op], byref(Xs._c()), ax, len(axes), 0, rank * rows_local,
-                                                       rows_total, byref(out._c()), hb.get_stream()))
-        o1 = T.empty((1,), F32, local)
-        oc = T.empty((cols,), F32, local)
-        nbytes = rows_local * cols * 4  # per rank; add_row multiplies by world
-        for op, axes, out, label in (("sum", [0, 1], o1, "sum() all axes"), ("mean", [0, 1], o1, "mean() all axes"), ("sum", [0], oc, "sum(axis 0) → [16384]")):
-            us = _timeit(torch, stream, [lambda: sharded(op, axes, out)], 20)
-            add_row("cfg5", f"{label} f32 [262144,16384] sharded over {world} GPU(s)", us, nbytes + 4, rows_local * cols,
-                    ("strong scaling: total size fixed; partials exchanged through " +
-                     ("peer-mapped mailboxes (one kernel per rank, NVLink stores)" if hb.lib.hptb_comm_uses_peer_memory(comm) else "ncclAllReduce"))
-                    if world > 1 else "single GPU, no exchange")
-        # parity of the sharded sum against an f64 accumulation of the same data (computed with torch on the device)
-        sharded("sum", [0, 1], o1)
-        torch.cuda.synchronize()
-        got = float(o1.to_cpu().item())
-        ref = big.sum(dtype=torch.float64)
-        mag = big.abs().sum(dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ref)
-            dist.all_reduce(mag)
-        rel = abs(got - ref.item()) / mag.item()
-        rows.append({"config": "cfg5", "op": "parity: |sum − f64 sum| / Σ|x|", "value": rel, "bound_1e-6_log2n": 1e-6 * 32, "ok": rel <= 1e-6 * 32})
-        if comm is not None:
-            hb.lib.hptb_comm_destroy(comm)
+        def unary_into(op):
+            _ffi.check(hb.lib.hptb_unary(X.ctx.handle, _ffi.UNARY_OPS[op], byref(V._c()), byref(Y._c()), 0.0, 0.0, hb.get_stream()))
+        for op in ("sin", "exp"):
+            us = _timeit(torch, stream, [lambda op=op: unary_into(op)], 100)
+            add_row("cfg2", f"{op} f32 [8192,8192] transposed view → contiguous", us, 536870912, 67108864, "input and output 268 MB each > L2")
+        us = _timeit(torch, stream, [lambda: V._reduce("max", [0], out=Mx)], 100)
+        add_row("cfg2", "max(axis 0) f32 [8192,8192] transposed view", us, 268468224, 67108864, "")
+        us = _timeit(torch, stream, [lambda: V._reduce("argmax", [0], out=Ai)], 100)
+        add_row("cfg2", "argmax(axis 0) f32 [8192,8192] transposed view", us, 268500992, 67108864, "")
+        del X, V, Y
 
-    for cfg, fn in (("cfg1", rows_cfg1), ("cfg3", rows_cfg3), ("cfg4", rows_cfg4), ("cfg5", rows_cfg5)):
+    for cfg, fn in (("cfg1", rows_cfg1), ("cfg2", rows_cfg2), ("cfg3", rows_cfg3), ("cfg4", rows_cfg4)):
         if want(cfg):
             fn()
     return rows

@@ -334,6 +334,63 @@ hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int3
 }
 }  // namespace hptb
 
+// ---- sharded reductions: the two halves comm.cpp composes (xchg.cuh) ------------------------------------------------
+namespace hptb {
+static ReduceLauncher sharded_launcher(int op, int in_dtype, double count) {
+  ReduceLauncher fn = reduce_launcher(op, in_dtype);
+  if (fn && op == HPTB_LOGSUMEXP && count >= 512.0 && hptb_reduce_logsumexp_long)
+    if (ReduceLauncher lf = hptb_reduce_logsumexp_long(in_dtype)) fn = lf;
+  return fn;
+}
+
+// Local pass.  `lay` is `out`'s shape with ROW-MAJOR strides; lay->data is the real output when that is how `out` is laid
+// out (the kernel may then exchange in its epilogue and write the result: *fused = true), else NULL.  Otherwise the bare
+// accumulators land in `raw` at the same row-major offsets.  `count` is the GLOBAL element count per output.
+hptb_status reduce_for_exchange(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, const hptb_tensor* lay,
+                                double count, const XchgParams* x, void* raw, bool* fused, size_t* acc_bytes, void* stream) {
+  ReduceLauncher fn = sharded_launcher(op, in->dtype, count);
+  if (!fn) return fail(HPTB_ERR_DTYPE, "reduce_sharded: no kernel for op %d on %s", op, dtype_name(in->dtype));
+  ReducePlan plan;
+  HPTB_TRY(build_reduce_plan(ctx, in, axes, naxes, lay, &plan));
+  plan.count = count;
+  plan.fold_out = 0;
+  plan.xchg = x;
+  plan.raw_out = raw;
+  plan.fused = fused;
+  plan.acc_bytes = acc_bytes;
+  plan.reverse = pass_direction(ctx, in->data, (size_t)numel(*in) * dtype_size(in->dtype), true) ? 1 : 0;
+  DeviceGuard g(ctx->device);
+  hptb_status st = fn(plan, (cudaStream_t)stream);
+  if (st == HPTB_OK) count_launches(1);
+  return st;
+}
+
+// Exchange (gathered == 0: through the peer mailboxes of `x`) or take the NCCL-gathered accumulators ([gathered][M]),
+// combine in rank order, apply the op's post step and write `out` (any strides).
+hptb_status reduce_combine(hptb_ctx* ctx, int op, int in_dtype, double count, const void* partials, int gathered, const XchgParams* x,
+                           const hptb_tensor* out, void* stream) {
+  ReduceLauncher fn = sharded_launcher(op, in_dtype, count);
+  if (!fn) return fail(HPTB_ERR_DTYPE, "reduce_sharded: no kernel for op %d on %s", op, dtype_name(in_dtype));
+  ReducePlan plan;
+  plan.mode = kPlanCombine;
+  plan.ctx = ctx;
+  plan.in = partials;
+  plan.out = out->data;
+  plan.count = count;
+  plan.xchg = x;
+  plan.gathered = gathered;
+  plan.comb_M = numel(*out);
+  plan.comb_nk = out->ndim;
+  for (int i = 0; i < out->ndim; ++i) {
+    plan.comb_shape[i] = out->shape[out->ndim - 1 - i];
+    plan.comb_stride[i] = out->strides[out->ndim - 1 - i];
+  }
+  DeviceGuard g(ctx->device);
+  hptb_status st = fn(plan, (cudaStream_t)stream);
+  if (st == HPTB_OK) count_launches(1);
+  return st;
+}
+}  // namespace hptb
 
 // ---- elementwise → reduce fusion ------------------------------------------------------------------------------------
 extern "C" hptb_status hptb_binary_reduce(hptb_ctx* ctx, int bin_op, int red_op, const hptb_tensor* lhs, const hptb_tensor* rhs,

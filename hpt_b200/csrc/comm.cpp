@@ -4,7 +4,8 @@
 // `cudarc` is built without its nccl feature, Cargo.toml:75-87; the device is a const generic,
 // hpt/src/tensor.rs:32).  A tensor sharded along its outermost axis is k per-GPU tensors; elementwise
 // ops and reductions over other axes need no exchange, reductions that cross the shard axis exchange
-// one small partial per rank (4 B – 64 KB for BASELINE config 5) with ncclAllReduce over NVLink.
+// one accumulator per output and rank (4 B – 64 KB for BASELINE config 5): through peer-mapped mailboxes written
+// by the reduce kernel itself (xchg.cuh), or — without peer memory — with ncclAllGather over NVLink.
 //
 // NCCL is resolved at run time with dlopen (the process usually already holds torch's bundled
 // libnccl.so.2; the same soname resolves to it), so libhpt_b200.so has no link-time NCCL dependency
@@ -15,18 +16,16 @@
 #include <vector>
 
 #include "context.h"
+#include "xchg.cuh"
 
 extern "C" hptb_status hptb_reduce(hptb_ctx*, int, const hptb_tensor*, const int32_t*, int, hptb_tensor*, int, void*);
-extern "C" hptb_status hptb_unary(hptb_ctx*, int, const hptb_tensor*, hptb_tensor*, double, double, void*);
-extern "C" hptb_status hptb_binary(hptb_ctx*, int, const hptb_tensor*, const hptb_tensor*, hptb_tensor*, void*);
-extern "C" hptb_status hptb_fill(hptb_ctx*, hptb_tensor*, const void*, void*);
-extern "C" hptb_status hptb_copy(hptb_ctx*, const hptb_tensor*, hptb_tensor*, void*);
 namespace hptb {
-hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, hptb_tensor* out,
-                        int init_out, double count_override, void* stream);  // api_reduce.cpp
-hptb_status arg_combine(int dtype, bool is_max, const void* vals, const int64_t* idx, int k, int64_t M, int64_t* out,
-                        cudaStream_t s);                                      // sharded.cu
-hptb_status add_offset_i64(int64_t* p, int64_t off, int64_t n, cudaStream_t s);
+// api_reduce.cpp
+hptb_status reduce_for_exchange(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, const hptb_tensor* lay,
+                                double count, const XchgParams* x, void* raw, bool* fused, size_t* acc_bytes, void* stream);
+hptb_status reduce_combine(hptb_ctx* ctx, int op, int in_dtype, double count, const void* partials, int gathered, const XchgParams* x,
+                           const hptb_tensor* out, void* stream);
+hptb_status add_offset_pairs(void* pairs, int64_t off, int64_t n, cudaStream_t s);  // sharded.cu
 size_t p2p_mailbox_bytes(int nranks, size_t slot_bytes);
 hptb_status p2p_allreduce(int dtype, int op, void* inout, int64_t n, void* const* boxes, int nranks, int rank, size_t slot_bytes,
                           uint32_t seq, cudaStream_t s);
@@ -116,80 +115,91 @@ struct hptb_comm {
   hptb_ctx* ctx = nullptr;
   hptb::ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
-  // peer-memory mailboxes for small partials (sharded.cu): box[r] = rank r's mailbox as mapped in this process
+  // Peer-mapped mailboxes (CUDA IPC over NVLink): box[r] = rank r's mailbox as mapped in this process.  Two regions:
+  // [0, ll_bytes) the flag-in-data exchange of reduction accumulators (xchg.cuh), then the slots + flags of the plain
+  // small-message allreduce (sharded.cu p2p_allreduce_kernel).
   bool p2p = false;
   void* box[16] = {nullptr};
+  void* box_ar[16] = {nullptr};  // box[r] + ll_bytes
+  size_t ll_slot_bytes = 0, ll_bytes = 0;
   size_t slot_bytes = 0;
-  uint32_t seq = 0;
+  uint32_t seq = 0;     // allreduce call number
+  uint32_t ll_seq = 0;  // sharded-reduction call number
 };
 
 namespace hptb {
 namespace {
-constexpr size_t kSlotBytes = 256 * 1024;  // per-rank payload capacity (config 5's sum(0) partial is 64 KB)
+constexpr size_t kSlotBytes = 256 * 1024;        // allreduce region: per-rank payload capacity
+constexpr size_t kLLSlotBytes = 2 * 1024 * 1024; // exchange region: 65536 outputs of the widest (16-byte) accumulator per call
+constexpr size_t kLLEntryMax = 32;               // bytes per output of the widest accumulator (4 words × {word, call number})
 
 // Map every rank's mailbox into this process: cudaMalloc + CUDA IPC handles exchanged with ncclAllGather.  Any
-// failure (no peer access, IPC unavailable in the container, HPTB_NO_P2P=1) leaves p2p off and NCCL carries the data.
-void setup_p2p(hptb_comm* c) {
-  const char* off = getenv("HPTB_NO_P2P");
-  if ((off && off[0] == '1') || c->nranks < 2 || c->nranks > 16) return;
-  const size_t bytes = p2p_mailbox_bytes(c->nranks, kSlotBytes);
-  void* mine = nullptr;
-  cudaIpcMemHandle_t* dev_handles = nullptr;
-  std::vector<cudaIpcMemHandle_t> handles(c->nranks);
-  int ok = 1;
-  if (cudaMalloc(&mine, bytes) != cudaSuccess) ok = 0;
-  if (ok && cudaMemset(mine, 0, bytes) != cudaSuccess) ok = 0;
-  if (ok && cudaIpcGetMemHandle(&handles[c->rank], mine) != cudaSuccess) ok = 0;
-  if (cudaMalloc((void**)&dev_handles, sizeof(cudaIpcMemHandle_t) * c->nranks) != cudaSuccess) { ok = 0; dev_handles = nullptr; }
-  // every rank takes part in the two collectives below even if its own setup failed, so nobody hangs
-  int* dev_ok = nullptr;
-  std::vector<int> oks(c->nranks, 0);
-  if (dev_handles && cudaMalloc((void**)&dev_ok, sizeof(int) * c->nranks) == cudaSuccess) {
-    cudaMemcpy((char*)dev_handles + sizeof(cudaIpcMemHandle_t) * c->rank, &handles[c->rank], sizeof(cudaIpcMemHandle_t), cudaMemcpyHostToDevice);
-    cudaMemcpy(dev_ok + c->rank, &ok, sizeof(int), cudaMemcpyHostToDevice);
-    cudaDeviceSynchronize();
-    int rc = nccl().GroupStart();
-    if (rc == ncclSuccess) rc = nccl().AllGather((char*)dev_handles + sizeof(cudaIpcMemHandle_t) * c->rank, dev_handles, sizeof(cudaIpcMemHandle_t), ncclInt8, c->comm, 0);
-    if (rc == ncclSuccess) rc = nccl().AllGather(dev_ok + c->rank, dev_ok, sizeof(int), ncclInt8, c->comm, 0);
-    int rc2 = nccl().GroupEnd();
-    if (rc != ncclSuccess || rc2 != ncclSuccess) ok = 0;
-    if (cudaStreamSynchronize(0) != cudaSuccess) ok = 0;
-    cudaMemcpy(handles.data(), dev_handles, sizeof(cudaIpcMemHandle_t) * c->nranks, cudaMemcpyDeviceToHost);
-    cudaMemcpy(oks.data(), dev_ok, sizeof(int) * c->nranks, cudaMemcpyDeviceToHost);
-  } else {
-    ok = 0;
+// failure (no peer access, IPC unavailable in the container, HPTB_NO_P2P=1 on ANY rank) leaves p2p off and NCCL carries
+// the data.  Every rank takes part in every collective below whatever happened to its own setup — the tiny device
+// buffers those collectives need are allocated before anything that may fail, and a rank that cannot even get those
+// reports an error from hptb_comm_init_rank.
+hptb_status setup_p2p(hptb_comm* c) {
+  if (c->nranks < 2 || c->nranks > 16) return HPTB_OK;  // same on every rank
+  const int k = c->nranks;
+  struct Rec {
+    cudaIpcMemHandle_t h;
+    int ok;
+  };
+  Rec* dev = nullptr;
+  if (cudaMalloc((void**)&dev, sizeof(Rec) * k) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(HPTB_ERR_OOM, "comm_init_rank: cannot allocate the %zu-byte handle exchange buffer", sizeof(Rec) * k);
   }
-  for (int r = 0; r < c->nranks && ok; ++r) ok = oks[r];
-  if (ok) {
-    for (int r = 0; r < c->nranks && ok; ++r) {
+  std::vector<Rec> recs(k);
+  memset(recs.data(), 0, sizeof(Rec) * k);
+  const char* off = getenv("HPTB_NO_P2P");
+  int ok = !(off && off[0] == '1');
+  const size_t ll_bytes = xchg_mailbox_bytes(k, kLLSlotBytes);
+  const size_t bytes = ll_bytes + p2p_mailbox_bytes(k, kSlotBytes);
+  void* mine = nullptr;
+  if (ok && cudaMalloc(&mine, bytes) != cudaSuccess) { ok = 0; mine = nullptr; }
+  if (ok && cudaMemset(mine, 0, bytes) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&recs[c->rank].h, mine) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  auto gather = [&](int my_ok) -> bool {  // all-gather {handle, ok}; false = the collective itself failed
+    recs[c->rank].ok = my_ok;
+    if (cudaMemcpy(dev + c->rank, &recs[c->rank], sizeof(Rec), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    cudaDeviceSynchronize();
+    if (nccl().AllGather(dev + c->rank, dev, sizeof(Rec), ncclInt8, c->comm, 0) != ncclSuccess) return false;
+    if (cudaStreamSynchronize(0) != cudaSuccess) return false;
+    return cudaMemcpy(recs.data(), dev, sizeof(Rec) * k, cudaMemcpyDeviceToHost) == cudaSuccess;
+  };
+  bool coll_ok = gather(ok);
+  for (int r = 0; r < k && coll_ok && ok; ++r) ok = recs[r].ok;
+  if (coll_ok && ok) {
+    for (int r = 0; r < k && ok; ++r) {
       if (r == c->rank) { c->box[r] = mine; continue; }
-      if (cudaIpcOpenMemHandle(&c->box[r], handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0;
+      if (cudaIpcOpenMemHandle(&c->box[r], recs[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; c->box[r] = nullptr; }
     }
   }
   // agree on the outcome: p2p is used only if EVERY rank mapped every mailbox (a mixed choice would deadlock)
-  int all_ok = ok;
-  if (dev_ok) {
-    cudaMemcpy(dev_ok + c->rank, &ok, sizeof(int), cudaMemcpyHostToDevice);
-    cudaDeviceSynchronize();
-    if (nccl().AllGather(dev_ok + c->rank, dev_ok, sizeof(int), ncclInt8, c->comm, 0) == ncclSuccess && cudaStreamSynchronize(0) == cudaSuccess) {
-      cudaMemcpy(oks.data(), dev_ok, sizeof(int) * c->nranks, cudaMemcpyDeviceToHost);
-      for (int r = 0; r < c->nranks; ++r) all_ok = all_ok && oks[r];
-    } else {
-      all_ok = 0;
-    }
+  int all_ok = coll_ok && ok;
+  if (coll_ok) {
+    coll_ok = gather(all_ok);
+    for (int r = 0; r < k && coll_ok; ++r) all_ok = all_ok && recs[r].ok;
   }
+  if (!coll_ok) all_ok = 0;
   cudaGetLastError();
-  if (dev_handles) cudaFree(dev_handles);
-  if (dev_ok) cudaFree(dev_ok);
+  cudaFree(dev);
   if (all_ok) {
     c->p2p = true;
     c->slot_bytes = kSlotBytes;
+    c->ll_slot_bytes = kLLSlotBytes;
+    c->ll_bytes = ll_bytes;
+    for (int r = 0; r < k; ++r) c->box_ar[r] = static_cast<char*>(c->box[r]) + ll_bytes;
   } else {
-    for (int r = 0; r < c->nranks; ++r)
+    for (int r = 0; r < k; ++r)
       if (r != c->rank && c->box[r]) cudaIpcCloseMemHandle(c->box[r]);
     if (mine) cudaFree(mine);
     memset(c->box, 0, sizeof(c->box));
+    cudaGetLastError();
   }
+  return HPTB_OK;
 }
 }  // namespace
 }  // namespace hptb
@@ -221,7 +231,8 @@ hptb_status hptb_comm_init_rank(hptb_ctx* ctx, int nranks, int rank, const void*
   c->rank = rank;
   int rc = nccl().CommInitRank(&c->comm, nranks, id, rank);
   if (rc != ncclSuccess) { delete c; return nccl_fail("ncclCommInitRank", rc); }
-  setup_p2p(c);
+  hptb_status st = setup_p2p(c);
+  if (st != HPTB_OK) { nccl().CommDestroy(c->comm); delete c; return st; }
   *out = c;
   return HPTB_OK;
 }
@@ -299,7 +310,7 @@ hptb_status hptb_allreduce(hptb_comm* comm, int op, hptb_tensor* t, void* stream
   if (comm->p2p && n > 0 && (size_t)n * dtype_size(t->dtype) <= 16 * 1024 && (size_t)n * dtype_size(t->dtype) <= comm->slot_bytes) {
     const int pop = nop == ncclProd ? HPTB_PROD : nop == ncclMax ? HPTB_MAX : nop == ncclMin ? HPTB_MIN : HPTB_SUM;
     const int pdt = (t->dtype == HPTB_BOOL) ? HPTB_U8 : t->dtype;  // bool OR / AND = max / min of 0/1 bytes
-    HPTB_TRY(p2p_allreduce(pdt, pop, t->data, n, comm->box, comm->nranks, comm->rank, comm->slot_bytes, ++comm->seq, (cudaStream_t)stream));
+    HPTB_TRY(p2p_allreduce(pdt, pop, t->data, n, comm->box_ar, comm->nranks, comm->rank, comm->slot_bytes, ++comm->seq, (cudaStream_t)stream));
     count_launches(1);
     return HPTB_OK;
   }
@@ -321,115 +332,57 @@ hptb_status hptb_reduce_sharded(hptb_comm* comm, int op, const hptb_tensor* shar
   HPTB_TRY(hptb_shard_plan_reduce(op, axes, naxes, shard_axis, comm->nranks, &sp));
   const bool crosses = sp.crosses != 0;
   const bool is_arg = op == HPTB_ARGMAX || op == HPTB_ARGMIN;
-  if (!crosses || comm->nranks == 1) {
-    HPTB_TRY(hptb_reduce(comm->ctx, op, shard, axes, naxes, out, 1, stream));
-    // a lone rank may still hold a shard that does not start at 0 (indices are GLOBAL along the shard axis)
-    if (is_arg && crosses && shard_offset != 0 && is_contiguous(*out)) {
-      DeviceGuard g(comm->ctx->device);
-      count_launches(1);
-      return add_offset_i64((int64_t*)out->data, shard_offset, numel(*out), (cudaStream_t)stream);
-    }
-    return HPTB_OK;
+  const bool offset_only = comm->nranks == 1 && crosses && is_arg && shard_offset != 0;  // a lone shard that does not start at 0
+  if ((!crosses || comm->nranks == 1) && !offset_only) return hptb_reduce(comm->ctx, op, shard, axes, naxes, out, 1, stream);
+  // ---- the reduction crosses the shard axis: every rank reduces its shard to one ACCUMULATOR per output (f32 for
+  // f16/bf16/f32, (value, global index) for argmax/argmin, Σexp for logsumexp, the power sum for reducel2/3), the k
+  // accumulators are combined in rank order and the op's post step (÷ GLOBAL count, ln, root, index) runs once — the
+  // sharded result is rounded exactly like the single-GPU one.  With peer memory the exchange is part of the reduce
+  // kernel (xchg.cuh: one launch per rank) or, for launch shapes that cannot host it, of one small follow-up kernel;
+  // without it NCCL all-gathers the accumulators.
+  if (is_arg && naxes != 1) return fail(HPTB_ERR_AXIS, "argmax/argmin take exactly one axis (got %d)", naxes);
+  const int odt = hptb_reduce_out_dtype(op, shard->dtype);
+  if (out->dtype != odt) return fail(HPTB_ERR_DTYPE, "reduce_sharded: out dtype is %s, expected %s", dtype_name(out->dtype), dtype_name(odt));
+  const int64_t M = numel(*out);
+  if (M == 0) return HPTB_OK;
+  double count = (double)global_axis_len;
+  for (int i = 0; i < naxes; ++i)
+    if (axes[i] != shard_axis) count *= (double)shard->shape[axes[i]];
+  hptb_tensor lay = *out;  // out's shape, row-major
+  int64_t st = 1;
+  for (int i = lay.ndim - 1; i >= 0; --i) { lay.strides[i] = st; st *= lay.shape[i]; }
+  lay.data = is_contiguous(*out) ? out->data : nullptr;
+  const int k = comm->nranks;
+  const bool use_ll = comm->p2p && k > 1 && (uint64_t)M * kLLEntryMax <= comm->ll_slot_bytes;  // the same on every rank
+  XchgParams x;
+  memset(&x, 0, sizeof(x));
+  if (use_ll) {
+    for (int r = 0; r < k; ++r) x.box[r] = static_cast<unsigned char*>(comm->box[r]);
+    x.slot_bytes = comm->ll_slot_bytes;
+    x.idx_offset = is_arg ? shard_offset : 0;
+    x.seq = ++comm->ll_seq;
+    x.nranks = k;
+    x.rank = comm->rank;
   }
-  if (!is_contiguous(*out)) return fail(HPTB_ERR_SHAPE, "reduce_sharded: out must be contiguous when partials are exchanged");
-  if (is_arg) {
-    // (extreme value, global index) per rank → all-gather → rank-ordered strict combine (sharded.cu)
-    if (naxes != 1) return fail(HPTB_ERR_AXIS, "argmax/argmin take exactly one axis (got %d)", naxes);
-    if (out->dtype != HPTB_I64) return fail(HPTB_ERR_DTYPE, "reduce_sharded: out dtype is %s, expected i64", dtype_name(out->dtype));
-    const int64_t M = numel(*out);
-    if (M == 0) return HPTB_OK;
-    const size_t esz = dtype_size(shard->dtype);
-    const int k = comm->nranks;
-    Scratch sv, sva, sia;
-    HPTB_TRY(sv.get(comm->ctx, (size_t)M * esz, stream));
-    HPTB_TRY(sva.get(comm->ctx, (size_t)M * esz * k, stream));
-    HPTB_TRY(sia.get(comm->ctx, (size_t)M * sizeof(int64_t) * k, stream));
-    hptb_tensor val = *out;
-    val.data = sv.ptr;
-    val.dtype = shard->dtype;
-    HPTB_TRY(hptb_reduce(comm->ctx, op == HPTB_ARGMAX ? HPTB_MAX : HPTB_MIN, shard, axes, naxes, &val, 1, stream));
-    HPTB_TRY(hptb_reduce(comm->ctx, op, shard, axes, naxes, out, 1, stream));
-    DeviceGuard g(comm->ctx->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    HPTB_TRY(add_offset_i64((int64_t*)out->data, shard_offset, M, s));
-    int rc = nccl().GroupStart();
-    if (rc != ncclSuccess) return nccl_fail("ncclGroupStart", rc);
-    rc = nccl().AllGather(sv.ptr, sva.ptr, (size_t)M * esz, ncclInt8, comm->comm, s);
-    if (rc == ncclSuccess) rc = nccl().AllGather(out->data, sia.ptr, (size_t)M * sizeof(int64_t), ncclInt8, comm->comm, s);
-    int rc2 = nccl().GroupEnd();
-    if (rc != ncclSuccess) return nccl_fail("ncclAllGather", rc);
-    if (rc2 != ncclSuccess) return nccl_fail("ncclGroupEnd", rc2);
-    HPTB_TRY(arg_combine(shard->dtype, op == HPTB_ARGMAX, sva.ptr, (const int64_t*)sia.ptr, k, M, (int64_t*)out->data, s));
-    count_launches(shard_offset != 0 ? 2 : 1);
-    return HPTB_OK;
+  Scratch raw;
+  HPTB_TRY(raw.get(comm->ctx, (size_t)M * 16, stream));
+  bool fused = false;
+  size_t accb = 0;
+  HPTB_TRY(reduce_for_exchange(comm->ctx, op, shard, axes, naxes, &lay, count, use_ll ? &x : nullptr, raw.ptr, &fused, &accb, stream));
+  if (fused) return HPTB_OK;
+  if (use_ll) return reduce_combine(comm->ctx, op, shard->dtype, count, raw.ptr, 0, &x, out, stream);
+  DeviceGuard g(comm->ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (is_arg && shard_offset != 0) {
+    HPTB_TRY(add_offset_pairs(raw.ptr, shard_offset, M, s));
+    count_launches(1);
   }
-  if (sp.global_count) {
-    // each rank computes Σ_local / n_GLOBAL, the allreduce-sum of those is the global mean
-    double count = (double)global_axis_len;
-    for (int i = 0; i < naxes; ++i)
-      if (axes[i] != shard_axis) count *= (double)shard->shape[axes[i]];
-    HPTB_TRY(reduce_impl(comm->ctx, HPTB_MEAN, shard, axes, naxes, out, 1, count, stream));
-    return hptb_allreduce(comm, HPTB_SUM, out, stream);
-  }
-  if (sp.pre_exp) {
-    HPTB_TRY(hptb_reduce(comm->ctx, HPTB_LOGSUMEXP, shard, axes, naxes, out, 1, stream));
-    HPTB_TRY(hptb_unary(comm->ctx, HPTB_EXP, out, out, 0, 0, stream));  // back to Σ exp (naive domain, as the reference)
-    HPTB_TRY(hptb_allreduce(comm, HPTB_SUM, out, stream));
-    return hptb_unary(comm->ctx, HPTB_LN, out, out, 0, 0, stream);
-  }
-  if (sp.post_root) {
-    // Σ|x|^p is exchanged, then the reference's root: sqrt, or pow with the exponent 1/3 rounded to the OUTPUT dtype
-    // (reduce.cuh ReduceOp<HPTB_REDUCEL3>).  f32/f64 outputs: the local kernel leaves the power sum unrooted in `out`.
-    // f16/bf16 outputs (8- and 16-bit inputs): a power sum does not fit half precision, so the rooted local result
-    // is widened to an f32 scratch, raised to p again, exchanged and rooted there, and rounded to `out` once.
-    const bool half = out->dtype == HPTB_F16 || out->dtype == HPTB_BF16;
-    const int64_t M = numel(*out);
-    Scratch s64, sod, swide, sthird;
-    HPTB_TRY(s64.get(comm->ctx, 8, stream));
-    HPTB_TRY(sod.get(comm->ctx, 8, stream));
-    HPTB_TRY(sthird.get(comm->ctx, 8, stream));
-    hptb_tensor acc = *out;  // where the exchange happens
-    if (half) {
-      HPTB_TRY(swide.get(comm->ctx, (size_t)(M > 0 ? M : 1) * sizeof(float), stream));
-      HPTB_TRY(hptb_reduce(comm->ctx, op, shard, axes, naxes, out, 1, stream));
-      acc.data = swide.ptr;
-      acc.dtype = HPTB_F32;
-      HPTB_TRY(hptb_copy(comm->ctx, out, &acc, stream));
-      hptb_tensor base = acc;
-      Scratch sbase;
-      if (sp.post_root == 3) {  // acc = base³ needs base kept
-        HPTB_TRY(sbase.get(comm->ctx, (size_t)(M > 0 ? M : 1) * sizeof(float), stream));
-        base.data = sbase.ptr;
-        HPTB_TRY(hptb_copy(comm->ctx, &acc, &base, stream));
-        HPTB_TRY(hptb_binary(comm->ctx, HPTB_MUL, &acc, &base, &acc, stream));
-      }
-      HPTB_TRY(hptb_binary(comm->ctx, HPTB_MUL, &acc, &base, &acc, stream));
-    } else {
-      HPTB_TRY(reduce_impl(comm->ctx, op, shard, axes, naxes, out, 1, -2.0, stream));
-    }
-    HPTB_TRY(hptb_allreduce(comm, HPTB_SUM, &acc, stream));
-    if (sp.post_root == 2) {
-      HPTB_TRY(hptb_unary(comm->ctx, HPTB_SQRT, &acc, &acc, 0, 0, stream));
-    } else {
-      const double third = 1.0 / 3.0;
-      hptb_tensor t64;
-      memset(&t64, 0, sizeof(t64));
-      t64.data = s64.ptr; t64.dtype = HPTB_F64; t64.ndim = 1; t64.shape[0] = 1; t64.strides[0] = 1;
-      HPTB_TRY(hptb_fill(comm->ctx, &t64, &third, stream));
-      hptb_tensor tod = t64, tex = t64;
-      tod.data = sod.ptr; tod.dtype = out->dtype;
-      HPTB_TRY(hptb_copy(comm->ctx, &t64, &tod, stream));      // 1/3 rounded to the output dtype
-      tex.data = sthird.ptr; tex.dtype = acc.dtype;
-      HPTB_TRY(hptb_copy(comm->ctx, &tod, &tex, stream));      // … carried in the exchange dtype
-      hptb_tensor ex = acc;
-      ex.data = sthird.ptr;
-      for (int i = 0; i < ex.ndim; ++i) ex.strides[i] = 0;     // broadcast the exponent over the partials
-      HPTB_TRY(hptb_binary(comm->ctx, HPTB_POW, &acc, &ex, &acc, stream));
-    }
-    return half ? hptb_copy(comm->ctx, &acc, out, stream) : HPTB_OK;
-  }
-  HPTB_TRY(hptb_reduce(comm->ctx, op, shard, axes, naxes, out, 1, stream));
-  return hptb_allreduce(comm, op, out, stream);
+  if (k == 1) return reduce_combine(comm->ctx, op, shard->dtype, count, raw.ptr, 1, nullptr, out, stream);
+  Scratch all;
+  HPTB_TRY(all.get(comm->ctx, (size_t)M * accb * k, stream));
+  int rc = nccl().AllGather(raw.ptr, all.ptr, (size_t)M * accb, ncclInt8, comm->comm, s);
+  if (rc != ncclSuccess) return nccl_fail("ncclAllGather", rc);
+  return reduce_combine(comm->ctx, op, shard->dtype, count, all.ptr, k, nullptr, out, stream);
 }
 
 }  // extern "C"

@@ -30,6 +30,7 @@
 #include "promote.h"
 #include "reduce_plan.h"
 #include "scalar.cuh"
+#include "xchg.cuh"
 
 namespace hptb {
 
@@ -398,7 +399,8 @@ struct RowsRedParams {
   int32_t G;           // threads per output: a power of two, 1..kRedThreads
   int32_t logG;
   int32_t use64;
-  int32_t fold_out;    // combine with the previous contents of out
+  int32_t fold_out;    // 1: combine with the previous contents of out; 2 (kFoldRaw): store the bare accumulator
+  XchgParams xchg;     // sharded reductions: exchange fused into the epilogue (G == kRedThreads only)
 };
 
 struct ColsRedParams {
@@ -501,12 +503,19 @@ __device__ __forceinline__ bool take_ticket(uint32_t* ticket, uint32_t S) {
 }
 
 // final write of one output (or of the (mean, var) pair of the two-output extension op)
+// fold = kFoldRaw: `out` is an array of ACCUMULATORS (sharded reductions whose kernel shape cannot fuse the exchange:
+// the bare local accumulator goes to a scratch, xchg_combine_kernel exchanges, combines and applies post)
+constexpr int kFoldRaw = 2;
 template <typename Op>
 __device__ __forceinline__ void red_store(typename Op::Out* out, typename Op::Out* out2, int64_t off, typename Op::Acc a,
                                           double count, int fold) {
   if constexpr (Op::kTwoOutputs) {
     Op::store2(out, out2, off, a, count);
   } else {
+    if (fold == kFoldRaw) {
+      reinterpret_cast<typename Op::Acc*>(out)[off] = a;
+      return;
+    }
     if (fold) a = Op::combine(Op::from_out(out[off]), a);
     out[off] = Op::post(a, count);
   }
@@ -653,7 +662,12 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
     for (int w = 1; w < nw; ++w) a = Op::combine(a, s_part[w0 + w]);
   }
   if (p.S == 1) {
-    if (active && g == 0) red_store<Op>(out, out2, out_off, a, p.count, p.fold_out);
+    if (active && g == 0) {
+      if constexpr (!Op::kTwoOutputs) {
+        if (p.xchg.enabled) a = xchg_finish<Op>(p.xchg, out_off, a);  // host: only with G == kRedThreads
+      }
+      red_store<Op>(out, out2, out_off, a, p.count, p.fold_out);
+    }
     return;
   }
   // split outputs (G == kRedThreads, one output per CTA): fixed-slot partials + last-CTA combine → deterministic
@@ -668,6 +682,10 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
     if (tid == 0) {
       r = s_part[0];
       for (int w = 1; w < kRedThreads / 32; ++w) r = Op::combine(r, s_part[w]);
+      // sharded: this rank's accumulator goes to every peer, the k accumulators are combined in rank order (xchg.cuh)
+      if constexpr (!Op::kTwoOutputs) {
+        if (p.xchg.enabled) r = xchg_finish<Op>(p.xchg, out_off, r);
+      }
       red_store<Op>(out, out2, out_off, r, p.count, p.fold_out);
     }
   }
@@ -921,12 +939,31 @@ struct LeanColsParams {
   uint32_t col_tiles;
   int32_t use64;
   int32_t fold_out;
+  XchgParams xchg;       // sharded reductions: exchange fused into the epilogue
 };
 
 // VEC (value, index) pairs or 16-byte accumulators per thread need 64 registers: 4 CTAs/SM for those
 template <typename Op, int VEC>
 constexpr int lean_cols_min_blocks() {
   return sizeof(typename Op::Local) > 8 ? 3 : (Op::kIndexed || sizeof(typename Op::Local) * VEC > 16) ? 4 : HPTB_LEAN_MINB;
+}
+
+// final write of a thread's VEC adjacent outputs; sharded: all VEC accumulators are pushed to the peers before the
+// first one is awaited, so the k·VEC remote entries are in flight together (xchg.cuh)
+template <typename Op, int VEC>
+__device__ __forceinline__ void lean_cols_finish(typename Op::Out* out, typename Op::Out* out2, int64_t off0,
+                                                 const typename Op::Acc* vals, const LeanColsParams& p) {
+  if constexpr (!Op::kTwoOutputs) {
+    if (p.xchg.enabled) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) xchg_push<Op>(p.xchg, off0 + j, vals[j]);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, off0 + j, xchg_collect<Op>(p.xchg, off0 + j), p.count, p.fold_out);
+      return;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, off0 + j, vals[j], p.count, p.fold_out);
 }
 
 template <typename Op, typename T, int VEC>
@@ -984,10 +1021,7 @@ reduce_cols_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__
     __syncthreads();
   }
   if (p.S == 1) {
-    if (ty == 0 && col_ok) {
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, out_off + col + j, sm[tx * VEC + j], p.count, p.fold_out);
-    }
+    if (ty == 0 && col_ok) lean_cols_finish<Op, VEC>(out, out2, out_off + col, sm + tx * VEC, p);
     return;
   }
   const uint32_t group = k * p.col_tiles + tile;
@@ -1017,10 +1051,72 @@ reduce_cols_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__
       }
       __syncthreads();
     }
-    if (ty == 0 && col_ok) {
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, out_off + col + j, sm[tx * VEC + j], p.count, p.fold_out);
+    if (ty == 0 && col_ok) lean_cols_finish<Op, VEC>(out, out2, out_off + col, sm + tx * VEC, p);
+  }
+}
+
+// ---- standalone exchange + combine ---------------------------------------------------------------------------
+// The unfused half of a sharded reduction (xchg.cuh): `part` holds this rank's M bare accumulators (kFoldRaw), or —
+// without peer memory — the k·M accumulators of every rank as all-gathered by NCCL ([rank][M]).  Push everything
+// first, then collect: a push never waits, so no thread of any rank can block another's progress.  Rank-ordered
+// combine → the result is bit-identical on every rank and equal to what the fused epilogue produces.
+struct CombineParams {
+  int64_t M;
+  int32_t nk, gathered;
+  int64_t shape[kRedMaxDims], stride[kRedMaxDims];  // `out` dims, innermost first (M counts them row-major)
+  double count;
+  XchgParams xchg;
+};
+template <typename Op>
+__global__ void __launch_bounds__(256) xchg_combine_kernel(const typename Op::Acc* __restrict__ part, typename Op::Out* __restrict__ out,
+                                                           CombineParams p) {
+  pdl_prologue();
+  typedef typename Op::Acc Acc;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+  if (!p.gathered)
+    for (int64_t m = i0; m < p.M; m += step) xchg_push<Op>(p.xchg, m, part[m]);
+  for (int64_t m = i0; m < p.M; m += step) {
+    Acc a;
+    if (p.gathered) {
+      a = part[m];
+      for (int r = 1; r < p.gathered; ++r) a = Op::combine(a, part[(int64_t)r * p.M + m]);
+    } else {
+      a = xchg_collect<Op>(p.xchg, m);
     }
+    int64_t rest = m, off = 0;
+    for (int i = 0; i < p.nk; ++i) {
+      const int64_t q = rest / p.shape[i];
+      off += (rest - q * p.shape[i]) * p.stride[i];
+      rest = q;
+    }
+    out[off] = Op::post(a, p.count);
+  }
+}
+
+template <typename Op>
+hptb_status launch_combine(const ReducePlan& plan, cudaStream_t stream) {
+  if constexpr (Op::kTwoOutputs) {
+    return fail(HPTB_ERR_UNSUPPORTED, "sharded exchange of a two-output reduction");
+  } else {
+    if (plan.comb_M <= 0) return HPTB_OK;
+    CombineParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = plan.comb_M;
+    p.nk = plan.comb_nk;
+    p.gathered = plan.gathered;
+    for (int i = 0; i < plan.comb_nk; ++i) { p.shape[i] = plan.comb_shape[i]; p.stride[i] = plan.comb_stride[i]; }
+    p.count = plan.count;
+    if (!plan.gathered) {
+      if (!plan.xchg) return fail(HPTB_ERR_INVALID, "combine: no exchange parameters");
+      p.xchg = *plan.xchg;
+      p.xchg.enabled = 1;
+    }
+    int64_t blocks = (p.M + 255) / 256;
+    const int64_t cap = (int64_t)plan.ctx->sm_count * 4;
+    if (blocks > cap) blocks = cap;
+    HPTB_CUDA_CHECK(launch_kernel(xchg_combine_kernel<Op>, dim3((unsigned)blocks), dim3(256), 0, stream,
+                                  static_cast<const typename Op::Acc*>(plan.in), static_cast<typename Op::Out*>(plan.out), p));
+    return HPTB_OK;
   }
 }
 
@@ -1090,12 +1186,34 @@ template <typename Op, typename T>
 hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   typedef typename Op::Acc Acc;
   typedef typename Op::Out Out;
+  if (plan.acc_bytes) *plan.acc_bytes = sizeof(Acc);
+  if (plan.mode == kPlanCombine) return launch_combine<Op>(plan, stream);
   const Collapsed& c = plan.c;
   const T* in = static_cast<const T*>(plan.in);
   Out* out = static_cast<Out*>(plan.out);
   Out* out2 = static_cast<Out*>(plan.out2);
   constexpr int VECMAX = 16 / sizeof(T) > 8 ? 8 : 16 / sizeof(T);
   const int sms = plan.ctx->sm_count;
+  // Sharded reductions (plan.raw_out set; plan.xchg = peer mailboxes, if any): a kernel shape whose final accumulators sit in at most half of the resident CTA
+  // slots exchanges them itself (xchg.cuh: one launch per rank); any other shape stores bare accumulators to
+  // plan.raw_out (same element offsets as `out`) and xchg_combine_kernel follows.  `settle(fuse)` is called by
+  // every path right before its launch.
+  const bool want_x = plan.raw_out != nullptr && !Op::kTwoOutputs;
+  int fold = plan.fold_out;
+  XchgParams xp;
+  memset(&xp, 0, sizeof(xp));
+  if (plan.fused) *plan.fused = false;
+  auto settle = [&](bool fuse) {
+    if (!want_x) return;
+    if (fuse && plan.out && plan.xchg) {
+      xp = *plan.xchg;
+      xp.enabled = 1;
+      if (plan.fused) *plan.fused = true;
+    } else {
+      out = reinterpret_cast<Out*>(plan.raw_out);
+      fold = kFoldRaw;
+    }
+  };
 
   // split dims (innermost first lists)
   int kept[kRedMaxDims], red[kRedMaxDims], nk = 0, nr = 0;
@@ -1111,7 +1229,8 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
     memset(&e, 0, sizeof(e));
     e.M = M;
     e.nk = nk;
-    e.fold_out = plan.fold_out;
+    settle(false);
+    e.fold_out = fold;
     e.count = plan.count;
     for (int i = 0; i < nk; ++i) { e.shape[i] = c.shape[kept[i]]; e.stride[i] = c.strides[0][kept[i]]; }
     const int64_t blocks = (M + 255) / 256;
@@ -1171,10 +1290,13 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
         // ticket, so more, thinner slabs lose: f32 [8192,8192] max(0): 576 CTAs → 43.9 µs, 4096 CTAs → 47.8 µs;
         // [4096,4096] sum(0): 576 CTAs → 15.4 µs, 1024 → 18.0 µs), but never more than 4096 rows per slab
         // ([262144,16384] sum(0): 64 slabs → 7.28 TB/s, 5 slabs → 6.9 TB/s); at most 64 partials per column tile.
+        // Long columns (R ≥ 32768, the shards of config 5): MANY thin slabs of ≥ 512 rows — 9+ waves of CTAs, so the
+        // last wave is a few percent of the run ([32768,16384] sum(0): 8 slabs = 1.15 waves → 338 µs, 64 slabs → 297 µs;
+        // [262144,16384]: 64 → 2367 µs, 128 → 2347 µs; profiles/r02b_sweep_shard.txt).
         int64_t S = ((int64_t)sms * 4 + lgroups / 2) / lgroups;
-        const int64_t by_rows = (R + 4095) / 4096;
+        const int64_t by_rows = R >= 32768 ? R / 512 : (R + 4095) / 4096;
         if (S < by_rows) S = by_rows;
-        if (S > 64) S = 64;
+        if (S > (R >= 32768 ? 128 : 64)) S = R >= 32768 ? 128 : 64;
         const int64_t max_s = (R + (int64_t)LTY * HPTB_RED_UNROLL - 1) / ((int64_t)LTY * HPTB_RED_UNROLL);  // ≥ one batch per thread row
         if (S > max_s) S = max_s;
         if (S < 1) S = 1;
@@ -1194,6 +1316,10 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
             if (!tickets) return fail(HPTB_ERR_OOM, "reduce: ticket buffer allocation failed");
           }
           const size_t lsmem = (size_t)kRedThreads * VECMAX * sizeof(Acc);
+          static const int occ_l = ctas_per_sm(reduce_cols_lean_kernel<Op, T, VECMAX>, (size_t)kRedThreads * VECMAX * sizeof(Acc));
+          settle(lgroups * 2 <= (int64_t)sms * occ_l);  // one finishing CTA per column tile
+          q.fold_out = fold;
+          q.xchg = xp;
           HPTB_CUDA_CHECK(launch_kernel(reduce_cols_lean_kernel<Op, T, VECMAX>, dim3((unsigned)(lgroups * S)), dim3(kRedThreads), lsmem, stream, in, out,
                                         out2, (Acc*)scratch.ptr, tickets, q));
           return HPTB_OK;
@@ -1238,6 +1364,8 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
       if (!tickets) return fail(HPTB_ERR_OOM, "reduce: ticket buffer allocation failed");
     }
     unsigned grid = (unsigned)(groups * S);
+    settle(false);
+    p.fold_out = fold;
     if (vec == VECMAX && VECMAX > 1)
       HPTB_CUDA_CHECK(launch_kernel(reduce_cols_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)>, dim3(grid), dim3(kRedThreads), smem, stream, in, out, out2, (Acc*)scratch.ptr, tickets, p));
     else
@@ -1315,10 +1443,12 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   }
   // lean path: unsplit outputs made of aligned unit-stride runs (one run, or runs along ONE more reduced dim),
   // ≤ 1 kept dim, 32-bit counters
+  // sharded: one CTA per output and at most half of the resident slots spinning → exchange in the epilogue
+  const bool fuse_rows = want_x && plan.out && plan.xchg && G == kRedThreads && M * 2 <= cta_slots;
   if constexpr (VECMAX > 1) {
     const bool multi = nr == 2;
     if (S == 1 && vec == VECMAX && nr >= 1 && nr <= 2 && nk <= 1 && !big && !(multi && Op::kIndexed) && p.chunks < (int64_t(1) << 31) &&
-        !tune_knob("HPTB_TUNE_NOLEAN")) {
+        !fuse_rows && !tune_knob("HPTB_TUNE_NOLEAN")) {
       int logG = 0;
       while ((1 << logG) < G) ++logG;
       const int64_t lean_blocks = (M + (kRedThreads >> logG) - 1) / (kRedThreads >> logG);
@@ -1333,7 +1463,8 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
         q.cpr = (uint32_t)p.cpr;
         q.chunks = (uint32_t)p.chunks;
         q.logG = logG;
-        q.fold_out = plan.fold_out;
+        settle(false);
+        q.fold_out = fold;
         q.reverse = plan.reverse;
         if (multi)
           HPTB_CUDA_CHECK(launch_kernel(reduce_rows_lean_kernel<Op, T, VECMAX, true>, dim3((unsigned)lean_blocks), dim3(kRedThreads), 0, stream, in, out, out2, q));
@@ -1344,6 +1475,7 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
     }
   }
   p.chunks_per_split = (p.chunks + S - 1) / S;
+  if (int64_t al = tune_knob("HPTB_TUNE_CPS_ALIGN")) p.chunks_per_split = (p.chunks_per_split + al - 1) / al * al;
   S = (p.chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   if (S < 1) S = 1;
   if (p.chunks_per_split >= (int64_t(1) << 31))
@@ -1366,6 +1498,9 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
     if (!tickets) return fail(HPTB_ERR_OOM, "reduce: ticket buffer allocation failed");
   }
   const unsigned grid = (unsigned)blocks;
+  settle(fuse_rows);
+  p.fold_out = fold;
+  p.xchg = xp;
   if (vec == VECMAX && VECMAX > 1)
     HPTB_CUDA_CHECK(launch_kernel(reduce_rows_kernel<Op, T, (VECMAX > 1 ? VECMAX : 1)>, dim3(grid), dim3(kRedThreads), 0, stream, in, out, out2, (Acc*)scratch.ptr, tickets, p));
   else

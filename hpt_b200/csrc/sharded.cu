@@ -1,51 +1,23 @@
-// sharded.cu — device helpers for reductions that cross the shard axis of an outer-axis-sharded tensor.
+// sharded.cu — device helpers of the multi-GPU path that are not part of a reduce kernel.
 //
-// argmax / argmin cannot be expressed as an allreduce: every rank reduces its shard to (extreme value, local
-// index), turns the index into a GLOBAL one (+ the shard's offset along the axis), the k (value, index) arrays
-// are all-gathered and combined here with the reference's rule — strict "better" from the identity with index 0,
-// scanning shards in rank order, so ties resolve to the lowest global index, NaN never wins and an all-NaN /
-// all-identity row yields 0 (hpt/src/backends/cpu/kernels/argreduce_kernels.rs:13-21,49-57).
+// The exchange of reduction accumulators lives in xchg.cuh (fused into the reduce kernels' epilogue, or run by
+// xchg_combine_kernel in reduce.cuh).  Here: the index offset for NCCL-gathered (value, index) accumulators, and the
+// plain small-message allreduce behind hptb_allreduce.
 #include "dtypes_x.h"
 #include "reduce.cuh"
 
 namespace hptb {
 namespace {
 
-template <typename T, bool IS_MAX>
-__global__ void __launch_bounds__(256) arg_combine_kernel(const T* __restrict__ vals, const int64_t* __restrict__ idx, int k,
-                                                          int64_t M, int64_t* __restrict__ out) {
-  pdl_prologue();
-  typedef ArgOp<T, IS_MAX> Op;
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  typename Op::V best = Op::identity().val;
-  int64_t bi = 0;
-  for (int r = 0; r < k; ++r) {
-    const typename Op::V v = to_compute<T>(vals[(int64_t)r * M + m]);
-    if (Op::better(v, best)) {
-      best = v;
-      bi = idx[(int64_t)r * M + m];
-    }
-  }
-  out[m] = bi;
-}
-
-__global__ void __launch_bounds__(256) add_offset_kernel(int64_t* __restrict__ p, int64_t off, int64_t n) {
+// argmax/argmin accumulators are ArgPair{value (≤ 8 bytes, padded to 8), int64 index}: 16 bytes, index in the second
+// half.  Turns the local index into a GLOBAL one before NCCL gathers the pairs (the mailbox path does it while pushing).
+__global__ void __launch_bounds__(256) add_offset_pairs_kernel(int64_t* __restrict__ pairs, int64_t off, int64_t n) {
   pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] += off;
+  if (i < n) pairs[2 * i + 1] += off;
 }
-
-template <typename T>
-hptb_status combine_t(bool is_max, const void* vals, const int64_t* idx, int k, int64_t M, int64_t* out, cudaStream_t s) {
-  const unsigned grid = (unsigned)((M + 255) / 256);
-  if (is_max)
-    HPTB_CUDA_CHECK(launch_kernel(arg_combine_kernel<T, true>, dim3(grid), dim3(256), 0, s, (const T*)vals, idx, k, M, out));
-  else
-    HPTB_CUDA_CHECK(launch_kernel(arg_combine_kernel<T, false>, dim3(grid), dim3(256), 0, s, (const T*)vals, idx, k, M, out));
-  return HPTB_OK;
-}
-
+static_assert(sizeof(ArgPair<b8>) == 16 && sizeof(ArgPair<double>) == 16 && offsetof(ArgPair<float>, idx) == 8,
+              "add_offset_pairs_kernel assumes 16-byte (value, index) accumulators");
 
 // ---- peer-memory allreduce of small partials -------------------------------------------------------------------
 // The exchange step of a sharded reduction moves 4 B – 64 KB per rank; a library allreduce costs 20–35 µs of
@@ -151,24 +123,11 @@ hptb_status p2p_launch(T* inout, const P2PParams& p, cudaStream_t s) {
 
 }  // namespace
 
-hptb_status arg_combine(int dtype, bool is_max, const void* vals, const int64_t* idx, int k, int64_t M, int64_t* out, cudaStream_t s) {
-  if (M <= 0) return HPTB_OK;
-  if (M > (int64_t)0x7fffffff * 256) return fail(HPTB_ERR_UNSUPPORTED, "arg_combine: too many outputs");
-  switch (dtype) {
-#define X(T, N, E) \
-  case E: return combine_t<T>(is_max, vals, idx, k, M, out, s);
-    HPTB_FOR_DTYPES(X)
-#undef X
-    default: return fail(HPTB_ERR_DTYPE, "arg_combine: bad dtype");
-  }
-}
-
-hptb_status add_offset_i64(int64_t* p, int64_t off, int64_t n, cudaStream_t s) {
+hptb_status add_offset_pairs(void* pairs, int64_t off, int64_t n, cudaStream_t s) {
   if (n <= 0 || off == 0) return HPTB_OK;
-  HPTB_CUDA_CHECK(launch_kernel(add_offset_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, p, off, n));
+  HPTB_CUDA_CHECK(launch_kernel(add_offset_pairs_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, static_cast<int64_t*>(pairs), off, n));
   return HPTB_OK;
 }
-
 
 size_t p2p_mailbox_bytes(int nranks, size_t slot_bytes) {
   return (size_t)2 * nranks * slot_bytes + (size_t)2 * nranks * kP2PMaxCtas * 32;

@@ -11,7 +11,7 @@ import math
 import numpy as np
 import pytest
 
-from util import DTYPES, ENUM, O, assert_exact, assert_ulp, rand, to_numpy, to_torch
+from util import DTYPES, ENUM, O, assert_exact, assert_reduce_bar, assert_ulp, rand, to_numpy, to_torch
 
 pytestmark = pytest.mark.gpu
 
@@ -31,31 +31,7 @@ def _check(hb, op, x, d, axes, keep=False, view=None):
     assert got_t.dtype == ENUM[od]
     assert tuple(got_t.shape) == tuple(want.shape), (got_t.shape, want.shape)
     got = to_numpy(got_t.to_cpu(), od)
-    what = f"{op} {d} shape={x.shape} axes={axes}"
-    if exact:
-        assert_exact(got, want, od, what)
-        return
-    ax = O.process_axes(axes, x.ndim)
-    n = max(2, int(np.prod([x.shape[a] for a in ax])))
-    ref = O.reduce_f64(op, x, d, axes).reshape(want.shape)
-    # the sum bound is relative to Σ|x| (a pure relative bound on Σx is unattainable under cancellation)
-    scale = np.abs(ref)
-    if op in ("sum", "mean"):
-        mag = O.reduce_f64(op, np.abs(O.to_compute(x, d).astype(np.float64)), "f64", axes).reshape(want.shape)
-        scale = np.maximum(scale, mag)
-    if op == "sum_square":
-        scale = np.abs(ref)
-    tol = 1e-6 * math.log2(n) * scale
-    err = np.abs(np.asarray(got, np.float64) - ref)
-    if od in ("f16", "bf16"):
-        ok = (err <= tol) | (O.ulp_diff(got, want, od) <= 1)
-    elif od == "f64":
-        ok = err <= 1e-13 * math.log2(n) * np.maximum(scale, 1e-300)
-    else:
-        ok = (err <= tol) | (O.ulp_diff(got, want, od) <= 1)
-    ok |= np.isnan(ref) & np.isnan(np.asarray(got, np.float64))
-    ok |= np.isinf(ref) & (np.asarray(got, np.float64) == ref)
-    assert ok.all(), f"{what}: {np.count_nonzero(~ok)} outside tolerance; max err {err.max()} (tol {tol.max()})"
+    assert_reduce_bar(op, x, d, axes, got, want, od, exact, f"{op} {d} shape={x.shape} axes={axes}")
 
 
 ALL_OPS = ["sum", "mean", "max", "min", "argmax", "argmin", "logsumexp", "sum_square", "prod"]

@@ -73,3 +73,31 @@ def assert_ulp(got, want, d, max_ulp, what=""):
     if (u > max_ulp).any():
         idx = tuple(np.argwhere(u > max_ulp)[0])
         raise AssertionError(f"{what}: max ulp {u.max()} > {max_ulp}; first at {idx}: got {g[idx]!r} want {w[idx]!r}")
+
+
+def assert_reduce_bar(op, x, d, axes, got, want, od, exact, what=""):
+    """The reduction bars of BASELINE.json north_star, shared by the single-GPU and the sharded tests: integers, bools,
+    max/min and arg indices bit-exact; sums/means within 1e-6·log2(n) of an f64 accumulation (relative to Σ|x|: a pure
+    relative bound on Σx is unattainable under cancellation) or within 1 ulp of the output dtype (f16/bf16 outputs:
+    the final rounding alone is 2^-9 / 2^-11); f64 within 1e-13·log2(n)."""
+    import math
+    if exact:
+        assert_exact(got, want, od, what)
+        return
+    ax = O.process_axes(axes, x.ndim)
+    n = max(2, int(np.prod([x.shape[a] for a in ax])))
+    ref = O.reduce_f64(op, x, d, axes).reshape(np.asarray(want).shape)
+    scale = np.abs(ref)
+    if op in ("sum", "mean", "nansum"):
+        mag = O.reduce_f64(op, np.abs(O.to_compute(x, d).astype(np.float64)), "f64", axes).reshape(np.asarray(want).shape)
+        scale = np.maximum(scale, mag)
+    tol = 1e-6 * math.log2(n) * scale
+    g64 = np.asarray(got, np.float64)
+    err = np.abs(g64 - ref)
+    if od == "f64":
+        ok = err <= 1e-13 * math.log2(n) * np.maximum(scale, 1e-300)
+    else:
+        ok = (err <= tol) | (O.ulp_diff(got, want, od) <= 1)
+    ok |= np.isnan(ref) & np.isnan(g64)
+    ok |= np.isinf(ref) & (g64 == ref)
+    assert ok.all(), f"{what}: {np.count_nonzero(~ok)} outside tolerance; max err {np.nanmax(err)} (tol {np.nanmax(tol)})"
