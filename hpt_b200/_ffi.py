@@ -98,6 +98,7 @@ SIGNATURES = {
     "hptb_stream_sync": (c_int, [c_void_p, c_void_p]),
     "hptb_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p), c_void_p]),
     "hptb_free": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "hptb_record_stream": (c_int, [c_void_p, c_void_p, c_void_p]),
     "hptb_empty_cache": (c_int, [c_void_p]),
     "hptb_alloc_get_stats": (c_int, [c_void_p, POINTER(HptbAllocStats)]),
     "hptb_alloc_selftest": (c_int, []),

@@ -14,6 +14,23 @@ CachingAllocator::~CachingAllocator() {
   for (void* ev : event_pool_) api_->event_destroy(ev);
 }
 
+void* CachingAllocator::take_event() {
+  void* ev = nullptr;
+  if (!event_pool_.empty()) { ev = event_pool_.back(); event_pool_.pop_back(); }
+  else if (api_->event_create(&ev) != 0) ev = nullptr;
+  return ev;
+}
+
+bool CachingAllocator::events_done(const Block& b, bool include_own) {
+  bool done = false;
+  if (include_own && !(b.event && api_->event_done(b.event, &done) == 0 && done)) return false;
+  for (void* ev : b.user_evs) {
+    done = false;
+    if (!(ev && api_->event_done(ev, &done) == 0 && done)) return false;
+  }
+  return true;
+}
+
 int CachingAllocator::allocate(size_t bytes, void* stream, void** out) {
   size_t sz = round_size(bytes);
   std::lock_guard<std::mutex> g(mu_);
@@ -22,18 +39,21 @@ int CachingAllocator::allocate(size_t bytes, void* stream, void** out) {
   auto range = free_.equal_range(sz);
   auto pick = free_.end();
   for (auto it = range.first; it != range.second; ++it) {
-    if (it->second.stream == stream) { pick = it; break; }
+    // stream order covers the free stream only: work recorded from other streams must have completed
+    if (it->second.stream == stream && events_done(it->second, false)) { pick = it; break; }
   }
   if (pick == free_.end()) {
     for (auto it = range.first; it != range.second; ++it) {
-      bool done = false;
-      if (api_->event_done(it->second.event, &done) == 0 && done) { pick = it; break; }
+      if (events_done(it->second, true)) { pick = it; break; }
     }
   }
   if (pick != free_.end()) {
     Block b = pick->second;
     free_.erase(pick);
     if (b.event) { event_pool_.push_back(b.event); b.event = nullptr; }
+    for (void* ev : b.user_evs) event_pool_.push_back(ev);
+    b.user_evs.clear();
+    b.users.clear();
     b.stream = stream;
     live_[b.ptr] = b;
     st_.n_cache_hit++;
@@ -51,7 +71,7 @@ int CachingAllocator::allocate(size_t bytes, void* stream, void** out) {
   }
   if (rc != 0) return rc;
   st_.n_device_malloc++;
-  Block b{p, sz, stream, nullptr};
+  Block b{p, sz, stream, nullptr, {}, {}};
   live_[p] = b;
   st_.bytes_in_use += sz;
   uint64_t reserved = st_.bytes_in_use + st_.bytes_cached;
@@ -67,15 +87,32 @@ int CachingAllocator::release(void* ptr, void* stream) {
   if (it == live_.end()) return 1;
   Block b = it->second;
   live_.erase(it);
-  void* ev = nullptr;
-  if (!event_pool_.empty()) { ev = event_pool_.back(); event_pool_.pop_back(); }
-  else if (api_->event_create(&ev) != 0) ev = nullptr;
+  void* ev = take_event();
   b.stream = stream;
   b.event = ev;
   if (ev) api_->event_record(ev, stream);
+  for (void* us : b.users) {
+    if (us == stream) continue;
+    void* uev = take_event();
+    if (uev) api_->event_record(uev, us);
+    b.user_evs.push_back(uev);  // a null event never reads as done: the block then waits for empty_cache's device sync
+  }
+  b.users.clear();
   st_.bytes_in_use -= b.size;
   st_.bytes_cached += b.size;
   free_.emplace(b.size, b);
+  return 0;
+}
+
+int CachingAllocator::record_stream(void* ptr, void* stream) {
+  if (!ptr) return 0;
+  std::lock_guard<std::mutex> g(mu_);
+  auto it = live_.find(ptr);
+  if (it == live_.end()) return 1;
+  Block& b = it->second;
+  for (void* us : b.users)
+    if (us == stream) return 0;
+  b.users.push_back(stream);
   return 0;
 }
 
@@ -92,6 +129,8 @@ int CachingAllocator::empty_cache_locked() {
     st_.n_device_free++;
     st_.bytes_cached -= kv.second.size;
     if (kv.second.event) event_pool_.push_back(kv.second.event);
+    for (void* ev : kv.second.user_evs)
+      if (ev) event_pool_.push_back(ev);
   }
   free_.clear();
   return 0;

@@ -6,9 +6,12 @@
 // launch sits on a single stream and frees are host-synchronous.  Here:
 //   * requests are rounded to size classes (512 B granules below 1 MiB, 2 MiB granules above), so
 //     near-equal shapes reuse each other's blocks;
-//   * a freed block remembers the stream it was last used on and an event recorded at free time;
-//     it can be handed out again immediately on the same stream (stream order makes that safe)
-//     and on another stream once the event has completed — no host synchronisation on the hot path;
+//   * a freed block carries the stream it was freed on and an event recorded there at free time, plus one
+//     event per OTHER stream that consumed it while it was live (record_stream — a tensor uploaded on a copy
+//     stream, read by kernels on a compute stream, dropped by the host right after enqueueing).  It is handed
+//     out again immediately on the free stream when no other stream used it (stream order makes that safe),
+//     and otherwise — or on another stream — once every one of its events has completed.  No host
+//     synchronisation on the hot path;
 //   * on device OOM the cache is emptied and the allocation retried once.
 // The device is reached through a small virtual interface so the caching logic is unit-tested on a
 // fake device without a GPU (hptb_alloc_selftest).
@@ -45,6 +48,9 @@ class CachingAllocator {
   // returns 0 ok, 2 OOM, else device error code
   int allocate(size_t bytes, void* stream, void** out);
   int release(void* ptr, void* stream);  // returns 1 if ptr is unknown
+  // `ptr` (a live block) is being used by work enqueued on `stream`, which is not the stream it will be freed on:
+  // the block is not reused until that work has completed.  Returns 1 if ptr is unknown.
+  int record_stream(void* ptr, void* stream);
   int empty_cache();
   AllocStats stats();
   static size_t round_size(size_t bytes);
@@ -54,8 +60,12 @@ class CachingAllocator {
     void* ptr;
     size_t size;
     void* stream;
-    void* event;  // recorded at release; null while in use
+    void* event;                  // recorded on `stream` at release; null while in use
+    std::vector<void*> users;     // live: other streams that consumed the block (record_stream)
+    std::vector<void*> user_evs;  // cached: one event per such stream, recorded at release
   };
+  void* take_event();
+  bool events_done(const Block& b, bool include_own);
   int empty_cache_locked();
   DeviceApi* api_;
   std::mutex mu_;

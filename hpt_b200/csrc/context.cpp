@@ -206,6 +206,11 @@ hptb_status hptb_free(hptb_ctx* ctx, void* ptr, void* stream) {
   if (ctx->alloc->release(ptr, stream)) return fail(HPTB_ERR_INVALID, "free: pointer %p was not allocated by this context", ptr);
   return HPTB_OK;
 }
+hptb_status hptb_record_stream(hptb_ctx* ctx, void* ptr, void* stream) {
+  if (!ctx) return fail(HPTB_ERR_INVALID, "record_stream: null ctx");
+  if (ctx->alloc->record_stream(ptr, stream)) return fail(HPTB_ERR_INVALID, "record_stream: pointer %p is not a live allocation of this context", ptr);
+  return HPTB_OK;
+}
 hptb_status hptb_empty_cache(hptb_ctx* ctx) {
   if (!ctx) return fail(HPTB_ERR_INVALID, "empty_cache: null ctx");
   ctx->alloc->empty_cache();
@@ -250,10 +255,27 @@ hptb_status hptb_alloc_selftest(void) {
     SELFTEST(st.bytes_in_use == 2048 && st.bytes_cached == 0);
     a.release(p3, s2);
     a.release(p4, s2);
+    api.device_sync();
+    // cross-stream use: allocated and freed on s1, consumed on s2 in between (record_stream) → no immediate same-stream
+    // reuse while s2's work is pending; reuse once it has completed
+    void *q1, *q2, *q3;
+    SELFTEST(a.allocate(5000, s1, &q1) == 0);
+    SELFTEST(a.record_stream(q1, s2) == 0 && a.record_stream(q1, s2) == 0);
+    SELFTEST(a.record_stream((void*)0xdead, s2) == 1);
+    SELFTEST(a.release(q1, s1) == 0);
+    SELFTEST(a.allocate(5000, s1, &q2) == 0 && q2 != q1);  // s2 may still be reading q1
+    api.device_sync();
+    SELFTEST(a.allocate(5000, s1, &q3) == 0 && q3 == q1);  // both events completed
+    // … and a block used on ONE stream only keeps its immediate same-stream reuse
+    a.release(q3, s1);
+    void* q4;
+    SELFTEST(a.allocate(5000, s1, &q4) == 0 && q4 == q1);
+    a.release(q2, s1);
+    a.release(q4, s1);
     // OOM: cache is emptied and the allocation retried
     void* big;
     SELFTEST(a.allocate(size_t(63) << 20, s1, &big) == 0);
-    SELFTEST(api.frees == 2);
+    SELFTEST(api.frees == 4);  // the four cached blocks (two sizes) went back to the device
     void* too_big;
     SELFTEST(a.allocate(size_t(32) << 20, s1, &too_big) == 2);
     a.release(big, s1);

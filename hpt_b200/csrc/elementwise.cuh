@@ -121,6 +121,10 @@ __device__ __forceinline__ void apply_pack(const F& f, Pack<O, E>& r, const Pack
   for (int k = 0; k < E; ++k) r.v[k] = f(x.v[k]);
 }
 
+}  // namespace hptb
+#include "tma_tile.cuh"  // needs apply_pack
+namespace hptb {
+
 template <int NIN, int VEC, int UNROLL, typename F, typename O, typename A, typename B>
 __global__ void __launch_bounds__(kMapThreads)
 map_flat_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, FlatParams p, F f) {
@@ -381,7 +385,7 @@ map_tiled_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restri
 // — the output's unit-stride dim — for the 16-byte global stores.  16-byte chunk c of tile row b lives at chunk
 // c ^ ((b / E) & 7), which makes the scatter and the gather bank-conflict free.  16 L1 wavefronts per 512 bytes
 // in + out instead of 36.
-constexpr int kSmemModeStaged = 1, kSmemModeDirect = 2, kSmemModeScalar = 3;
+// (kSmemModeStaged / Direct / Scalar: tma_tile.cuh)
 
 // one tile; pointers are already at the tile origin, in-tile offsets are 32-bit (the host checks the strides)
 template <int NIN, typename F, typename T, bool FULL>
@@ -716,6 +720,52 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
     }
     for (int o = 0; o <= NIN && ok; ++o)
       if (std::llabs(p.sa[o]) > 0x7fffffffLL || std::llabs(p.sb[o]) > 0x7fffffffLL) ok = false;
+    // one staged operand of a 2- or 4-byte type whose layout a tensor map can describe: TMA-staged tiles (tma_tile.cuh)
+    if constexpr (sizeof(O) == 2 || sizeof(O) == 4) {
+      bool tma_ok = ok && nstaged == 1 && p.nbatch <= 3 && batch <= 65535 && !big && !tma_disabled() &&
+                    p.A * p.B * batch >= 4096 && !tune_flag("HPTB_TUNE_NO_TMA");
+      int so = 0;  // the staged operand
+      for (int o = 1; o <= NIN && tma_ok; ++o) {
+        if (p.mode[o] == 1) so = o;
+        else if (p.mode[o] == 2) {}
+        else if (p.sa[o] == 0 && p.sb[o] == 0) {}
+        else tma_ok = false;
+      }
+      if (tma_ok && so > 0) {
+        typedef TmaGeom<sizeof(O)> TG;
+        const int64_t tiles_a = (p.A + kTmaTA - 1) / kTmaTA, tiles_b = (p.B + (int64_t)kTmaSub * TG::BW - 1) / ((int64_t)kTmaSub * TG::BW);
+        CUtensorMap tmap;
+        const O* staged = so == 1 ? reinterpret_cast<const O*>(a) : reinterpret_cast<const O*>(b);
+        if (tiles_a <= 0x7fffffffLL && tiles_b <= 65535 &&
+            tma_make_map<O>(&tmap, staged, p.A, p.B, p.sa[so], p.nbatch, p.batch_shape, p.batch_stride[so])) {
+          TmaTileParams q;
+          memset(&q, 0, sizeof(q));
+          q.A = p.A;
+          q.B = p.B;
+          q.out_sb = p.sb[0];
+          q.nbatch = p.nbatch;
+          const int other = NIN == 2 ? 3 - so : 0;
+          const O* in1 = other == 1 ? reinterpret_cast<const O*>(a) : reinterpret_cast<const O*>(b);
+          if (other) {
+            q.in1_sb = p.sb[other];
+            q.in1_mode = p.mode[other] == 2 ? kSmemModeDirect : kSmemModeScalar;
+            q.swap = other == 1 ? 1 : 0;
+          }
+          for (int i = 0; i < 3; ++i) {
+            q.batch_shape[i] = i < p.nbatch ? p.batch_shape[i] : 1u;
+            q.batch_out[i] = i < p.nbatch ? p.batch_stride[0][i] : 0;
+            q.batch_in1[i] = (other && i < p.nbatch) ? p.batch_stride[other][i] : 0;
+          }
+          auto kern = map_tma_tile_kernel<NIN, F, O>;
+          constexpr int smem_bytes = kTmaSub * TG::kSubStride + 64;
+          static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+          if (attr != cudaSuccess) return fail(HPTB_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(attr));
+          HPTB_CUDA_CHECK(launch_kernel(kern, dim3((unsigned)tiles_a, (unsigned)tiles_b, (unsigned)batch), dim3(kTmaThreads), smem_bytes, stream, out, in1,
+                                        tmap, q, f));
+          return HPTB_OK;
+        }
+      }
+    }
     if (ok && nstaged > 0) {
       constexpr int T2 = 16 * E;
       SmemTileParams q;

@@ -1430,6 +1430,10 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
     if (S > maxC) S = maxC;
     if (S > 8192) S = 8192;
     if (S < 1) S = 1;
+    // a power of two: for the power-of-two extents that dominate in practice every split then starts on a large
+    // power-of-two boundary, and ≈ 7 waves of CTAs keep the last wave short (profiles/r02c_sweep_shard.txt: the
+    // full sum of [32768,16384] f32 305 µs at S = 4096 vs 315–318 at 4736 (8.0 waves) and 313 at 8192)
+    while (S & (S - 1)) S &= S - 1;
   }
   if (Op::kIndexed && S == 1 && G > 64 && M * 64 >= thread_slots) G = 64;
   (void)thread_slots;
@@ -1475,6 +1479,9 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
     }
   }
   p.chunks_per_split = (p.chunks + S - 1) / S;
+  // split boundaries on 4 KB (256 chunks of 16 bytes): a boundary inside a 128-byte line makes two CTAs fetch it, and
+  // odd split sizes were erratic (17 GB sum, S = 2960: 2603 µs unaligned, 2381 µs aligned; profiles/r02c_sweep_shard.txt)
+  if (S > 1 && p.chunks_per_split >= 4096) p.chunks_per_split = (p.chunks_per_split + 255) / 256 * 256;
   if (int64_t al = tune_knob("HPTB_TUNE_CPS_ALIGN")) p.chunks_per_split = (p.chunks_per_split + al - 1) / al * al;
   S = (p.chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   if (S < 1) S = 1;

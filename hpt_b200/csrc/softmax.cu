@@ -891,6 +891,20 @@ extern "C" hptb_status hptb_layernorm(hptb_ctx* ctx, const hptb_tensor* in, int 
     }
     if (!ok) return fail(HPTB_ERR_SHAPE, "layernorm: gamma / beta must be contiguous tensors of the normalized shape");
   }
+  // The kernels index gamma / beta by position in the normalized run, so that run must be the ROW-MAJOR order of the
+  // normalized dims in `in` and in `out`.  The collapse pass below orders reduced dims by stride and would happily
+  // merge a PERMUTED pair (in-place layernorm of x.transpose(-1, -2)) into one unit-stride run in memory order —
+  // gamma would then land on the wrong elements without any error.  Checked here, before the collapse.
+  for (const hptb_tensor* t : {in, static_cast<const hptb_tensor*>(out)}) {
+    int64_t exp = 1;
+    for (int i = in->ndim - 1; i >= first; --i) {
+      if (t->shape[i] != 1 && t->strides[i] != exp)
+        return fail(HPTB_ERR_UNSUPPORTED, "layernorm: the normalized dims must be dense and row-major in the input and the output "
+                                          "(dim %d has stride %lld, expected %lld); call contiguous() first",
+                    i, (long long)t->strides[i], (long long)exp);
+      exp *= t->shape[i];
+    }
+  }
   uint8_t mask[HPTB_MAX_DIMS] = {0};
   for (int i = first; i < in->ndim; ++i) mask[i] = 1;
   int64_t strides[kMaxOperands][HPTB_MAX_DIMS] = {{0}};

@@ -85,6 +85,12 @@ class _Storage:
         self.nbytes = nbytes
         self.stream = _s(stream)
 
+    def used_on(self, stream):
+        """The block is consumed by work enqueued on `stream`: if that is not the stream it will be freed on, tell the
+        allocator (hptb_record_stream) so the block is not reused before that work has completed."""
+        if stream != self.stream and self.ptr:
+            check(lib.hptb_record_stream(self.ctx.handle, c_void_p(self.ptr), stream))
+
     def __del__(self):
         try:
             if self.ptr and lib is not None:
@@ -98,6 +104,18 @@ class _Borrowed:
 
     def __init__(self, ctx, ptr, keepalive=None):
         self.ctx, self.ptr, self.keepalive, self.stream = ctx, ptr, keepalive, None
+
+    def used_on(self, stream):
+        pass
+
+
+def _on(stream, *tensors):
+    """Resolve the stream of a call and note it on every tensor the call touches (cross-stream reuse safety)."""
+    s = _s(stream)
+    for t in tensors:
+        if t is not None:
+            t.storage.used_on(s)
+    return s
 
 
 def _contig_strides(shape):
@@ -241,9 +259,9 @@ class Tensor:
         nbytes = host.numel() * host.element_size()
         if nbytes:
             if sync or out is None or not host.is_pinned():
-                check(lib.hptb_memcpy_d2h(self.ctx.handle, c_void_p(host.data_ptr()), c_void_p(src.ptr), nbytes, _s(stream)))
+                check(lib.hptb_memcpy_d2h(self.ctx.handle, c_void_p(host.data_ptr()), c_void_p(src.ptr), nbytes, _on(stream, src)))
             else:  # pinned destination, caller synchronises the stream before reading `out`
-                check(lib.hptb_memcpy_d2h_async(self.ctx.handle, c_void_p(host.data_ptr()), c_void_p(src.ptr), nbytes, _s(stream)))
+                check(lib.hptb_memcpy_d2h_async(self.ctx.handle, c_void_p(host.data_ptr()), c_void_p(src.ptr), nbytes, _on(stream, src)))
                 host._hptb_src = src  # keep the device buffer alive until the caller has synchronised
         return host
 
@@ -352,17 +370,17 @@ class Tensor:
     # ---- copy / cast ------------------------------------------------------------------------------
     def contiguous(self, stream=None):
         out = Tensor.empty(self.shape, self.dtype, self.ctx.device, stream)
-        check(lib.hptb_copy(self.ctx.handle, byref(self._c()), byref(out._c()), _s(stream)))
+        check(lib.hptb_copy(self.ctx.handle, byref(self._c()), byref(out._c()), _on(stream, self, out)))
         return out
 
     def astype(self, dtype, stream=None):
         out = Tensor.empty(self.shape, dtype, self.ctx.device, stream)
-        check(lib.hptb_copy(self.ctx.handle, byref(self._c()), byref(out._c()), _s(stream)))
+        check(lib.hptb_copy(self.ctx.handle, byref(self._c()), byref(out._c()), _on(stream, self, out)))
         return out
 
     def fill_(self, value, stream=None):
         host = Tensor._scalar(value, self.dtype)
-        check(lib.hptb_fill(self.ctx.handle, byref(self._c()), c_void_p(host.data_ptr()), _s(stream)))
+        check(lib.hptb_fill(self.ctx.handle, byref(self._c()), c_void_p(host.data_ptr()), _on(stream, self)))
         return self
 
     # ---- NormalBinOps / std::ops (hpt/src/backends/cuda/std_ops.rs, tensor_external/binary.rs) ----------
@@ -387,7 +405,7 @@ class Tensor:
         oshape = tuple(bshape[i] for i in range(bn.value))
         if out is None:
             out = Tensor.empty(oshape, odt, self.ctx.device, stream)
-        check(lib.hptb_binary(self.ctx.handle, op, byref(self._c()), byref(rhs._c()), byref(out._c()), _s(stream)))
+        check(lib.hptb_binary(self.ctx.handle, op, byref(self._c()), byref(rhs._c()), byref(out._c()), _on(stream, self, rhs, out)))
         return out
 
     def add_(self, rhs, out, stream=None): return self._binary("add", rhs, out, stream)
@@ -426,7 +444,7 @@ class Tensor:
         check(lib.hptb_broadcast_shape((c_int64 * max(self.ndim, 1))(*self.shape), self.ndim,
                                        (c_int64 * max(rhs.ndim, 1))(*rhs.shape), rhs.ndim, bshape, byref(bn)))
         out = Tensor.empty(tuple(bshape[i] for i in range(bn.value)), _ffi.BOOL, self.ctx.device, stream)
-        check(lib.hptb_compare(self.ctx.handle, op, byref(self._c()), byref(rhs._c()), byref(out._c()), _s(stream)))
+        check(lib.hptb_compare(self.ctx.handle, op, byref(self._c()), byref(rhs._c()), byref(out._c()), _on(stream, self, rhs, out)))
         return out
 
     def tensor_eq(self, rhs): return self._compare("eq", rhs)
@@ -444,7 +462,7 @@ class Tensor:
             raise HptError(2, f"{name} is not supported for {_ffi.DTYPE_NAMES[self.dtype]}")
         if out is None:
             out = Tensor.empty(self.shape, odt, self.ctx.device, stream)
-        check(lib.hptb_unary(self.ctx.handle, op, byref(self._c()), byref(out._c()), float(alpha), float(beta), _s(stream)))
+        check(lib.hptb_unary(self.ctx.handle, op, byref(self._c()), byref(out._c()), float(alpha), float(beta), _on(stream, self, out)))
         return out
 
     def selu(self, out=None, stream=None):
@@ -480,7 +498,7 @@ class Tensor:
                 raise HptError(1, f"out has shape {out.shape}/{_ffi.DTYPE_NAMES[out.dtype]}, expected {red_shape}/{_ffi.DTYPE_NAMES[odt]}")
             res = out if out.shape == red_shape else Tensor(out.storage, out.ptr, out.dtype, red_shape, _contig_strides(red_shape))
         check(lib.hptb_reduce(self.ctx.handle, op, byref(self._c()), ax, len(ax_in), byref(res._c()),
-                              1 if init_out else 0, _s(stream)))
+                              1 if init_out else 0, _on(stream, self, res)))
         if keep_dims:
             check(lib.hptb_reduce_shape(shp, self.ndim, ax, len(ax_in), 1, oshape, byref(on)))
             ks = tuple(oshape[i] for i in range(on.value))
@@ -526,7 +544,7 @@ class Tensor:
         red_shape = tuple(oshape[i] for i in range(on.value))
         res = out if out is not None else Tensor.empty(red_shape, odt, self.ctx.device, stream)
         check(lib.hptb_binary_reduce(self.ctx.handle, bop, rop, byref(self._c()), byref(rhs._c()), ax, len(ax_in),
-                                     byref(res._c()), 1, _s(stream)))
+                                     byref(res._c()), 1, _on(stream, self, rhs, res)))
         if keep_dims:
             check(lib.hptb_reduce_shape(bshape, bn.value, ax, len(ax_in), 1, oshape, byref(on)))
             ks = tuple(oshape[i] for i in range(on.value))
@@ -545,7 +563,7 @@ class Tensor:
         red_shape = tuple(oshape[i] for i in range(on.value))
         m = Tensor.empty(red_shape, odt, self.ctx.device, stream)
         v = Tensor.empty(red_shape, odt, self.ctx.device, stream)
-        check(lib.hptb_mean_var(self.ctx.handle, byref(self._c()), ax, len(ax_in), byref(m._c()), byref(v._c()), _s(stream)))
+        check(lib.hptb_mean_var(self.ctx.handle, byref(self._c()), ax, len(ax_in), byref(m._c()), byref(v._c()), _on(stream, self, m, v)))
         return m, v
 
     # ---- NormalizationOps (hpt/src/backends/cuda/tensor_internal/softmax.rs) ------------------------------
@@ -557,7 +575,7 @@ class Tensor:
             raise HptError(3, f"axis {axis} out of range for ndim {self.ndim}")
         odt = lib.hptb_unary_out_dtype(0, self.dtype)
         out = Tensor.empty(self.shape, odt, self.ctx.device, stream)
-        check(lib.hptb_softmax(self.ctx.handle, byref(self._c()), axis, log, byref(out._c()), _s(stream)))
+        check(lib.hptb_softmax(self.ctx.handle, byref(self._c()), axis, log, byref(out._c()), _on(stream, self, out)))
         return out
 
     def layernorm(self, normalized_shape, gamma=None, beta=None, eps=1e-5, stream=None):
@@ -569,7 +587,7 @@ class Tensor:
         out = Tensor.empty(self.shape, odt, self.ctx.device, stream)
         g = byref(gamma._c()) if gamma is not None else None
         b = byref(beta._c()) if beta is not None else None
-        check(lib.hptb_layernorm(self.ctx.handle, byref(self._c()), len(ns), g, b, float(eps), byref(out._c()), _s(stream)))
+        check(lib.hptb_layernorm(self.ctx.handle, byref(self._c()), len(ns), g, b, float(eps), byref(out._c()), _on(stream, self, gamma, beta, out)))
         return out
 
     def softmax(self, axis): return self._softmax(axis, 0)

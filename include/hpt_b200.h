@@ -154,6 +154,11 @@ hptb_status hptb_stream_sync(hptb_ctx* ctx, void* stream);
  *      utils/allocate.rs:66-124, utils/deallocate.rs:11-32) with a stream-ordered caching pool ------- */
 hptb_status hptb_alloc(hptb_ctx* ctx, size_t bytes, void** ptr, void* stream);
 hptb_status hptb_free(hptb_ctx* ctx, void* ptr, void* stream);
+/* `ptr` (from hptb_alloc, still live) is consumed by work enqueued on `stream`, which is not the stream it will be
+ * freed on: the block is not handed out again before that work has completed (one event per recorded stream at free
+ * time).  Call it whenever a tensor is used on a stream other than its allocation / free stream — without it a block
+ * dropped right after enqueueing cross-stream work could be reused while that work still reads it. */
+hptb_status hptb_record_stream(hptb_ctx* ctx, void* ptr, void* stream);
 hptb_status hptb_empty_cache(hptb_ctx* ctx);              /* resize_cuda_lru_cache(0) analogue, hpt/src/lib.rs:441-511 */
 typedef struct {
   uint64_t bytes_in_use, bytes_cached, bytes_reserved_peak;

@@ -34,6 +34,76 @@ def test_rust_sys_crate_binds_exactly_the_header():
     assert declared == rs, declared ^ rs
 
 
+def test_rust_sys_crate_is_generated_from_the_header_and_ctypes_agrees():
+    """One source of truth: rust/hpt-b200-sys/src/lib.rs is exactly what tools/gen_rust_sys.py emits for the current
+    header, and the ctypes mirror carries the same enum VALUES and struct FIELD LISTS (names, order, types, array extents)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_rust_sys as g
+    assert g.generate() == open(g.OUT).read(), "rust/hpt-b200-sys/src/lib.rs is stale: run python tools/gen_rust_sys.py"
+    h = g.parse_header()
+    enums = {k: dict(v) for k, v in h["enums"].items()}
+
+    def by_name(enum, prefix, table, count):
+        for name, val in table.items():
+            assert enums[enum][prefix + name.upper()] == val, (enum, name)
+        assert enums[enum][count] == len(table), (enum, "count")
+    by_name("hptb_binary_op", "HPTB_", _ffi.BINARY_OPS, "HPTB_BINARY_COUNT")
+    by_name("hptb_cmp_op", "HPTB_", _ffi.CMP_OPS, "HPTB_CMP_COUNT")
+    by_name("hptb_unary_op", "HPTB_", _ffi.UNARY_OPS, "HPTB_UNARY_COUNT")
+    by_name("hptb_reduce_op", "HPTB_", _ffi.REDUCE_OPS, "HPTB_REDUCE_COUNT")
+    assert enums["hptb_unary_op"]["HPTB_FLOOR"] == _ffi.FLOAT_UNARY_COUNT
+    for i, n in enumerate(_ffi.DTYPE_NAMES):
+        assert enums["hptb_dtype"]["HPTB_" + n.upper()] == i
+    for code, n in _ffi.STATUS_NAMES.items():
+        assert enums["hptb_status"]["HPTB_" + ("OK" if n == "OK" else "ERR_" + n)] == code
+    for i, n in enumerate(_ffi.ROUTES):
+        assert enums["hptb_route_kind"]["HPTB_ROUTE_" + n.upper()] == i
+    for i, n in enumerate(_ffi.COLLECTIVES):
+        assert enums["hptb_collective"]["HPTB_COLL_" + n.upper()] == i
+    assert (_ffi.PROMOTE_NORMAL, _ffi.PROMOTE_FLOAT_BINARY, _ffi.PROMOTE_FLOAT_UNARY) == tuple(
+        enums["hptb_promote_kind"][k] for k in ("HPTB_PROMOTE_NORMAL", "HPTB_PROMOTE_FLOAT_BINARY", "HPTB_PROMOTE_FLOAT_UNARY"))
+    cmap = {"void*": ctypes.c_void_p, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
+            "uint8_t": ctypes.c_uint8}
+    for cname, cls in (("hptb_tensor", _ffi.HptbTensor), ("hptb_alloc_stats", _ffi.HptbAllocStats),
+                       ("hptb_collapse_plan", _ffi.HptbCollapsePlan), ("hptb_reduce_route_t", _ffi.HptbReduceRoute),
+                       ("hptb_shard_plan", _ffi.HptbShardPlan)):
+        want = []
+        for fname, ctype, dims in h["structs"][cname]:
+            t = cmap[ctype]
+            for d in reversed(dims):
+                t = t * d
+            want.append((fname, t))
+        got = [(n, t) for n, t in cls._fields_]
+        assert [n for n, _ in got] == [n for n, _ in want], cname
+        for (n, tg), (_, tw) in zip(got, want):
+            assert ctypes.sizeof(tg) == ctypes.sizeof(tw) and tg._type_ == tw._type_ if hasattr(tw, "_length_") else tg is tw, (cname, n)
+        assert ctypes.sizeof(cls) == sum(ctypes.sizeof(t) for _, t in want) or cname in ("hptb_collapse_plan",), cname
+
+
+def test_rust_shim_op_tables_match_the_header():
+    """rust/hpt-b200-shim maps the reference's op-name strings to the library's enums: the unary table is positional,
+    the binary / reduce tables name the constants — both must agree with the header."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_rust_sys as g
+    enums = {k: dict(v) for k, v in g.parse_header()["enums"].items()}
+    shim = os.path.join(ROOT, "rust", "hpt-b200-shim", "src")
+    un = open(os.path.join(shim, "unary.rs")).read()
+    names = re.findall(r'"(\w+)"', re.search(r"const NAMES: \[&str; (\d+)\] = \[(.*?)\];", un, flags=re.S).group(2))
+    assert len(names) == enums["hptb_unary_op"]["HPTB_UNARY_COUNT"] == int(re.search(r"const NAMES: \[&str; (\d+)\]", un).group(1))
+    for i, n in enumerate(names):
+        assert enums["hptb_unary_op"]["HPTB_" + n.upper()] == i, n
+    for fname, enum in (("binary.rs", ("hptb_binary_op", "hptb_cmp_op")), ("reduce.rs", ("hptb_reduce_op",))):
+        src = open(os.path.join(shim, fname)).read()
+        pairs = re.findall(r'"(\w+)" => \(?(?:true, |false, )?sys::(HPTB_\w+)', src)
+        assert len(pairs) >= 16
+        for name, const in pairs:
+            assert any(const in enums[e] for e in enum), const
+            want = {"max": "MAXIMUM", "min": "MINIMUM"}.get(name, name.upper()) if fname == "binary.rs" else name.upper()
+            assert const == "HPTB_" + want, (name, const)
+
+
 def test_version_and_dtype_sizes():
     assert lib.hptb_version() == 100
     for i, n in enumerate(DTYPES):

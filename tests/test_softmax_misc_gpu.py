@@ -210,6 +210,21 @@ def test_layernorm(hb):
     check(rand(rng, (16, 512), "bf16"), "bf16", 1, True, True)
     with pytest.raises(hb.HptError):
         hb.Tensor.to_cuda(to_torch(x, "f32")).layernorm((128,))
+    # C ABI: `in` and `out` sharing a PERMUTED layout over the normalized dims (in-place layernorm of x.transpose(-1, -2))
+    # would merge into one unit-stride run in MEMORY order and put gamma on the wrong elements — it must be refused
+    from ctypes import byref
+    from hpt_b200 import _ffi
+    xs = rand(rng, (4, 24, 16), "f32")
+    X = hb.Tensor.to_cuda(to_torch(xs, "f32"))
+    V = X.transpose(-1, -2)  # logical [4, 16, 24], strides [384, 1, 16]
+    g = rand(rng, (16, 24), "f32")
+    G = hb.Tensor.to_cuda(to_torch(g, "f32"))
+    st = hb.lib.hptb_layernorm(X.ctx.handle, byref(V._c()), 2, byref(G._c()), None, 1e-5, byref(V._c()), hb.get_stream())
+    assert st == 8, f"permuted normalized dims: expected HPTB_ERR_UNSUPPORTED, got status {st}"
+    # … and through a contiguous copy the result is the oracle's
+    got = V.contiguous().layernorm((16, 24), G, None, 1e-5).to_cpu().numpy()
+    ref, _ = O.layernorm(np.transpose(xs, (0, 2, 1)), "f32", 2, g, None, 1e-5)
+    assert (np.abs(got - ref) <= 2e-5 * (1 + np.abs(ref))).all()
 
 
 @pytest.mark.gpu
