@@ -16,6 +16,8 @@
 //                        write pass (two reads, one write).
 //   softmax_cols         axis is strided and another dim is contiguous: one thread per output column,
 //                        lanes along the contiguous dim (coalesced), online pass + write pass.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include "context.h"
 #include "dtypes_x.h"
@@ -188,13 +190,71 @@ __device__ __forceinline__ void ms_push(MS<C>& a, C x) {
   else a.s += x;  // NaN element: poison the row as exp(NaN) would
 }
 
-// the same with the streaming exp (fast_expf, no TwoSum on x − max: the accuracy class of softmax_rows_reg)
-template <typename C>
-__device__ __forceinline__ void ms_push_fast(MS<C>& a, C x) {
-  if (a.s == (C)0) { a.m = x; a.s = (C)1; return; }
-  if (x <= a.m) a.s += sm_exp_fast(x - a.m);
-  else if (x > a.m) { a.s = a.s * sm_exp_fast(a.m - x) + (C)1; a.m = x; }
+// ---- exact-rescale online statistics (f32 compute type) -----------------------------------------------------------
+// The vectorised streaming kernels keep, instead of (max, Σ exp(x − max)), the pair (K, Σ 2^(x·log2e − K)) with K an
+// INTEGER: the smallest one ≥ every x·log2e seen so far.  Moving the reference from K to K' multiplies Σ by
+// 2^(K − K') — a pure exponent shift, exact — so however often the running maximum moves, and however many partial
+// pairs are merged (threads, warps, CTAs, axis splits), Σ carries only the rounding of its additions.
+// A term never forms x − max either: y = x·log2e is carried as hi + lo (≈ 2^-48 relative), split as n + f with
+// n = rint(hi), and 2^(y − K) = 2^f · 2^(n − K) — ex2 of a fraction, then an exponent shift.  Its error is that of
+// ex2 (≤ 2 ulp) whatever the distance to the maximum; exp(x − max) in f32 loses |x − max|/2 ulp to the subtraction.
+constexpr float kLog2eHi = 1.4426950216293335f, kLog2eLo = 1.9259629911266175e-8f;
+constexpr float kLn2Hi = 0.693145751953125f, kLn2Lo = 1.42860682030941723212e-6f;  // ln2 = hi + lo, hi with 9 trailing zero bits
+__device__ __forceinline__ float sm_exp2i(float d) {  // 2^d for an integer-valued d ≤ 0 (−inf → 0)
+  return d < -126.0f ? 0.0f : __int_as_float((127 + (int)d) << 23);
+}
+__device__ __forceinline__ float sm_term(float x, float K) {  // 2^(x·log2e − K) for x·log2e ≤ K; −inf → 0, NaN → NaN
+  const float hi = x * kLog2eHi;
+  const float lo = fmaf(x, kLog2eLo, fmaf(x, kLog2eHi, -hi));
+  const float n = rintf(hi);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((hi - n) + lo));  // hi − n is exact
+  const float r = e * sm_exp2i(n - K);
+  return x < -3.3e38f ? 0.0f : r;  // −inf: hi − n and lo are NaN
+}
+__device__ __forceinline__ double sm_term(double x, double m) { return exp(x - m); }
+// a.m holds K (f32) / the running maximum (f64: the inexact-rescale form, kept for the 64-bit types)
+__device__ __forceinline__ void ms_push_fast(MS<float>& a, float x) {
+  const float y = x * kLog2eHi;
+  if (y > a.m) {  // false for NaN and for −inf against the initial −inf
+    const float K = ceilf(y);
+    if (K > a.m) {  // +inf input: K = +inf, the terms become NaN as exp(inf − inf) does
+      a.s *= sm_exp2i(a.m - K);  // a.m = −inf initially: a.s is 0 anyway
+      a.m = K;
+    }
+  }
+  if (x > Limits<float>::lowest() || x != x) a.s += sm_term(x, a.m);  // −inf contributes nothing (and K may still be −inf)
+}
+__device__ __forceinline__ void ms_push_fast(MS<double>& a, double x) {
+  if (a.s == 0.0) { a.m = x; a.s = 1.0; return; }
+  if (x <= a.m) a.s += exp(x - a.m);
+  else if (x > a.m) { a.s = a.s * exp(a.m - x) + 1.0; a.m = x; }
   else a.s += x;
+}
+// merge two (K, Σ) pairs: exact scalings, one rounded addition
+__device__ __forceinline__ MS<float> ms_merge_fast(MS<float> a, MS<float> b) {
+  if (a.s == 0.0f) return b;
+  if (b.s == 0.0f) return a;
+  const float K = fmaxf(a.m, b.m);
+  return MS<float>{K, a.s * sm_exp2i(a.m - K) + b.s * sm_exp2i(b.m - K)};
+}
+__device__ __forceinline__ MS<double> ms_merge_fast(MS<double> a, MS<double> b) { return ms_combine<double>(a, b); }
+// the row's normalised output from its (K, Σ): softmax = 2^(x·log2e − K) / Σ; log_softmax = (x − K·ln2) − ln Σ with
+// K·ln2_hi exact (|K| < 2^9, ln2_hi has 9 trailing zero bits) so that the subtraction cancels without loss
+struct SmFinal {
+  float K, inv, lgK;
+};
+__device__ __forceinline__ SmFinal sm_final(MS<float> r) { return SmFinal{r.m, 1.0f / r.s, fmaf(r.m, kLn2Lo, logf(r.s))}; }
+__device__ __forceinline__ float sm_out(float x, const SmFinal& f, int log) {
+  return log ? fmaf(-f.K, kLn2Hi, x) - f.lgK : sm_term(x, f.K) * f.inv;
+}
+struct SmFinalD {
+  double m, inv, lg;
+};
+__device__ __forceinline__ SmFinalD sm_final(MS<double> r) { return SmFinalD{r.m, 1.0 / r.s, log(r.s)}; }
+__device__ __forceinline__ double sm_out(double x, const SmFinalD& f, int log) {
+  const double sh = x - f.m;
+  return log ? sh - f.lg : exp(sh) * f.inv;
 }
 
 template <typename T>
@@ -299,20 +359,20 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
       for (int u = 0; u < UN; ++u)
         if (c + (int64_t)u * NT < packs) {
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) ms_push_fast<C>(a, to_compute<O>(cast<O>(v[u].v[k])));
+          for (int k = 0; k < VEC; ++k) ms_push_fast(a, to_compute<O>(cast<O>(v[u].v[k])));
         }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       MS<C> b{shfl_xor<C>(a.m, off), shfl_xor<C>(a.s, off)};
-      a = (tid & off) == 0 ? ms_combine<C>(a, b) : ms_combine<C>(b, a);
+      a = (tid & off) == 0 ? ms_merge_fast(a, b) : ms_merge_fast(b, a);
     }
     __syncthreads();
     if ((tid & 31) == 0) { s_m[tid >> 5] = a.m; s_s[tid >> 5] = a.s; }
     __syncthreads();
     MS<C> r{Limits<C>::lowest(), (C)0};
-    for (int w = 0; w < NT / 32; ++w) r = ms_combine<C>(r, MS<C>{s_m[w], s_s[w]});
-    const C inv = (C)1 / r.s, lg = sm_log<C>(r.s);
+    for (int w = 0; w < NT / 32; ++w) r = ms_merge_fast(r, MS<C>{s_m[w], s_s[w]});
+    const auto fin = sm_final(r);
     for (int64_t c = tid; c < packs; c += (int64_t)NT * UN) {
       Pack<T, VEC> v[UN];
 #pragma unroll
@@ -323,10 +383,7 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
         if (c + (int64_t)u * NT < packs) {
           Pack<O, VEC> o;
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) {
-            const C sh = to_compute<O>(cast<O>(v[u].v[k])) - r.m;
-            o.v[k] = from_compute<O>(p.log ? sh - lg : sm_exp_fast(sh) * inv);
-          }
+          for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v[u].v[k])), fin, p.log));
           store_pack<O, VEC>(dst + (c + (int64_t)u * NT) * VEC, o);
         }
     }
@@ -375,7 +432,7 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
         for (int u = 0; u < UN; ++u)
           if (e + (int64_t)u * TY < e_end) {
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) ms_push_fast<C>(a[k], to_compute<O>(cast<O>(v[u].v[k])));
+            for (int k = 0; k < VEC; ++k) ms_push_fast(a[k], to_compute<O>(cast<O>(v[u].v[k])));
           }
       }
     }
@@ -387,7 +444,7 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
       if (ty < off) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-          a[k] = ms_combine<C>(a[k], MS<C>{s_m[ty + off][lane * VEC + k], s_s[ty + off][lane * VEC + k]});
+          a[k] = ms_merge_fast(a[k], MS<C>{s_m[ty + off][lane * VEC + k], s_s[ty + off][lane * VEC + k]});
           s_m[ty][lane * VEC + k] = a[k].m;
           s_s[ty][lane * VEC + k] = a[k].s;
         }
@@ -410,7 +467,7 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
       for (int sp = 0; sp < (int)gridDim.y; ++sp) {
         const C* pm = part + ((int64_t)sp * 2) * ncols + (int64_t)blockIdx.x * W + lane * VEC;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) a[k] = ms_combine<C>(a[k], MS<C>{pm[k], pm[ncols + k]});
+        for (int k = 0; k < VEC; ++k) a[k] = ms_merge_fast(a[k], MS<C>{pm[k], pm[ncols + k]});
       }
 #pragma unroll
       for (int k = 0; k < VEC; ++k) { s_m[0][lane * VEC + k] = a[k].m; s_s[0][lane * VEC + k] = a[k].s; }
@@ -418,13 +475,9 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
     __syncthreads();
   }
   if (!active) return;
-  C m[VEC], inv[VEC], lg[VEC];
+  decltype(sm_final(MS<C>{})) fin[VEC];  // one division per column; the per-element multiply adds ≤ 0.5 ulp
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    m[k] = s_m[0][lane * VEC + k];
-    inv[k] = (C)1 / s_s[0][lane * VEC + k];  // one division per column; the per-element multiply adds ≤ 0.5 ulp
-    lg[k] = sm_log<C>(s_s[0][lane * VEC + k]);
-  }
+  for (int k = 0; k < VEC; ++k) fin[k] = sm_final(MS<C>{s_m[0][lane * VEC + k], s_s[0][lane * VEC + k]});
   for (int64_t e = e_begin + ty; e < e_end; e += (int64_t)TY * UN) {
     Pack<T, VEC> v[UN];
 #pragma unroll
@@ -435,13 +488,32 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
       if (e + (int64_t)u * TY < e_end) {
         Pack<O, VEC> o;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          const C sh = to_compute<O>(cast<O>(v[u].v[k])) - m[k];
-          o.v[k] = from_compute<O>(p.log ? sh - lg[k] : sm_exp_fast(sh) * inv[k]);
-        }
+        for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v[u].v[k])), fin[k], p.log));
         store_pack<O, VEC>(dst + (e + (int64_t)u * TY) * p.sa_out, o);
       }
   }
+}
+
+#include "softmax_band.cuh"
+
+// CTAs per cluster for a band of `band_bytes`: the smallest power of two that brings a CTA's share under 64 KB (three
+// CTAs per SM), grown while the grid would leave SMs idle and every CTA keeps ≥ min_bytes; 0 = the band does not fit
+// (> 8 × 96 KB).
+inline int band_cluster(int64_t band_bytes, int64_t nbands, int sms, int64_t min_bytes) {
+  int cl = 1;
+  static const bool tune = [] { const char* e = getenv("HPTB_TUNE"); return e && e[0] == '1'; }();
+  const char* tb = tune ? getenv("HPTB_TUNE_BAND_KB") : nullptr;  // development: target KB per CTA (tools/band_sweep.py)
+  const int64_t target = tb ? atoll(tb) * 1024 : 65536;
+  while (cl < kBandMaxCl && band_bytes > (int64_t)cl * target) cl <<= 1;
+  if (band_bytes > (int64_t)cl * 98304) return 0;
+  while (cl < kBandMaxCl && nbands * cl < (int64_t)sms * 3 && band_bytes / (cl * 2) >= min_bytes) cl <<= 1;
+  return cl;
+}
+inline bool band_disabled() {
+  static const bool on = [] { const char* e = getenv("HPTB_TUNE"); return e && e[0] == '1'; }();
+  if (!on) return false;
+  const char* e = getenv("HPTB_TUNE_NO_BAND");
+  return e && e[0] == '1';
 }
 
 template <typename T>
@@ -527,6 +599,28 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
         if ((uint64_t)(std::llabs(c.strides[1][kept[i]]) * (int64_t)sizeof(T)) % ai) ok = false;
         if ((uint64_t)(std::llabs(c.strides[0][kept[i]]) * (int64_t)sizeof(O)) % ao) ok = false;
       }
+      if constexpr (std::is_same<T, O>::value && std::is_same<compute_t<O>, float>::value) {
+        // the row fits the shared memory of a cluster: one HBM read, exact maximum before the first exp (softmax_band.cuh)
+        const int cl = ok && !band_disabled() ? band_cluster(p.L * (int64_t)sizeof(T), M, ctx->sm_count, 4096) : 0;
+        if (cl > 0 && M * cl <= 0x7fffffffLL) {
+          BandParams q;
+          memset(&q, 0, sizeof(q));
+          q.kept = p.kept;
+          q.L = p.L;
+          const int64_t packs = p.L / VECMAX;
+          q.per_cta = (packs + cl - 1) / cl;
+          q.cl = cl;
+          q.log = log;
+          q.use64 = p.use64;
+          const size_t smem = (size_t)q.per_cta * 16;
+          auto kern = softmax_band_rows<T, VECMAX>;
+          static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+          if (attr != cudaSuccess) return fail(HPTB_ERR_CUDA, "cudaFuncSetAttribute(softmax_band_rows) failed: %s", cudaGetErrorString(attr));
+          HPTB_CUDA_CHECK(launch_kernel_cluster(kern, dim3((unsigned)(M * cl)), dim3(kSmThreads), smem, stream, (unsigned)cl, in, out, q));
+          count_launches(1);
+          return HPTB_OK;
+        }
+      }
       if (ok) {
         int64_t blocks = M < (int64_t)ctx->sm_count * 16 ? M : (int64_t)ctx->sm_count * 16;
         if (p.L / VECMAX >= 8192 && M < (int64_t)ctx->sm_count * 8)
@@ -559,6 +653,33 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
         if ((uint64_t)(std::llabs(c.strides[0][d]) * (int64_t)sizeof(O)) % ao) ok = false;
       }
       if (!ok) vec = 1;
+    }
+    if constexpr (std::is_same<T, O>::value && std::is_same<compute_t<O>, float>::value && VECMAX > 1) {
+      // a 128-byte-wide column band fits the shared memory of a cluster (softmax_band.cuh)
+      constexpr int BW = 8 * VECMAX;
+      const int64_t bctiles = (p.C + BW - 1) / BW;
+      const int cl = vec == VECMAX && p.L >= 64 && !band_disabled() ? band_cluster(p.L * 128, outer_n * bctiles, ctx->sm_count, 8192) : 0;
+      if (cl > 0 && outer_n * bctiles * cl <= 0x7fffffffLL && std::llabs(p.sa_in) < (int64_t(1) << 40)) {
+        BandParams q;
+        memset(&q, 0, sizeof(q));
+        q.kept = p.outer;
+        q.L = p.L;
+        q.per_cta = (p.L + cl - 1) / cl;
+        q.sa_in = p.sa_in;
+        q.sa_out = p.sa_out;
+        q.C = p.C;
+        q.ctiles = bctiles;
+        q.cl = cl;
+        q.log = log;
+        q.use64 = p.use64;
+        const size_t smem = (size_t)q.per_cta * 128;
+        auto kern = softmax_band_cols<T, VECMAX>;
+        static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+        if (attr != cudaSuccess) return fail(HPTB_ERR_CUDA, "cudaFuncSetAttribute(softmax_band_cols) failed: %s", cudaGetErrorString(attr));
+        HPTB_CUDA_CHECK(launch_kernel_cluster(kern, dim3((unsigned)(outer_n * bctiles * cl)), dim3(kSmThreads), smem, stream, (unsigned)cl, in, out, q));
+        count_launches(1);
+        return HPTB_OK;
+      }
     }
     // 32 lanes per row segment unless that leaves the GPU short of CTAs and 8 lanes still fill whole sectors
     int tx = 32;

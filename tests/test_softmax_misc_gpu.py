@@ -72,6 +72,41 @@ def test_dtypes_shapes_layouts(hb, log):
     _softmax_check(hb, rand(rng, (64, 4096), "f32"), "f32", -1, log)
 
 
+@pytest.mark.parametrize("log", [False, True])
+def test_cluster_band_and_streaming_kernels(hb, log):
+    """Rows beyond the register limit and strided axes: the cluster-resident band kernels (softmax_band.cuh: rows of up to
+    8 × 96 KB, 128-byte column bands of up to 6144 rows), and past those the streaming kernels with the exact power-of-two
+    rescale.  Same bound as the register kernel (4 + |x − max| ulp): no allowance for online rescaling any more.  Each
+    shape also runs with the band kernels switched off, i.e. through the streaming kernels, under the same bound."""
+    import os
+    rng = np.random.default_rng(33)
+    cases = [((6, 131072), 1, "f32"), ((3, 200000), 1, "f32"), ((40, 50000), 1, "f32"), ((2, 400000), 1, "f32"),   # rows; 400000 > 8 × 96 KB
+             ((5, 65536), 1, "bf16"), ((3, 300000), 1, "f16"),
+             ((4096, 256), 0, "f32"), ((6144, 96), 0, "f32"), ((3000, 520), 0, "f32"), ((7000, 64), 0, "f32"),      # cols; 7000 rows > 6144
+             ((2, 1000, 72), 1, "f32"), ((4096, 512), 0, "bf16"), ((777, 1032), 0, "f16"), ((64, 40), 0, "f32")]
+    for shape, axis, d in cases:
+        x = rand(rng, shape, d)
+        x = (x * 4).astype(x.dtype) if d == "f32" else x
+        if d == "f32":
+            x.flat[7] = 30.0          # a late, dominant maximum: every running reference moves
+            x.flat[x.size // 2] = -np.inf
+        for off in ("0", "1"):
+            os.environ["HPTB_TUNE_NO_BAND"] = off
+            try:
+                _softmax_check(hb, x, d, axis, log)
+            finally:
+                os.environ.pop("HPTB_TUNE_NO_BAND", None)
+    # increasing rows: the running maximum moves at every element
+    x = np.tile(np.linspace(-40, 40, 32768, dtype=np.float32), (3, 1))
+    for off in ("0", "1"):
+        os.environ["HPTB_TUNE_NO_BAND"] = off
+        try:
+            _softmax_check(hb, x, "f32", 1, log)
+            _softmax_check(hb, np.ascontiguousarray(x.T[:4096]), "f32", 0, log)
+        finally:
+            os.environ.pop("HPTB_TUNE_NO_BAND", None)
+
+
 def test_softmax_errors(hb):
     X = hb.Tensor.empty((4, 5), ENUM["f32"])
     with pytest.raises(hb.HptError) as e:
