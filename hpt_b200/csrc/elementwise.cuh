@@ -594,6 +594,51 @@ hptb_status launch_rows(const Collapsed& c, O* out, const A* a, const B* b, F f,
   return HPTB_OK;
 }
 
+// TMA-staged transposing launch (tma_tile.cuh) for a tile plan with exactly ONE operand read along b (mode 1), the output
+// and any partner operand along a (mode 2) or scalar.  HPTB_FALLBACK: the layout is outside what the tensor map or the
+// kernel's grid can describe — the caller takes its other kernels.
+template <int NIN, typename F, typename O>
+hptb_status launch_tma_tile(const TileParams& p, int64_t batch, bool big, O* out, const O* a, const O* b, F f, cudaStream_t stream) {
+  typedef TmaGeom<(sizeof(O) == 1 ? 2 : sizeof(O))> TG;
+  constexpr int BWE = TG::BW * (sizeof(O) == 1 ? 2 : 1);
+  if (p.nbatch > 3 || batch > 65535 || big || tma_disabled() || p.A * p.B * batch < 4096 || tune_flag("HPTB_TUNE_NO_TMA")) return HPTB_FALLBACK;
+  int so = 0;  // the staged operand
+  for (int o = 1; o <= NIN; ++o)
+    if (p.mode[o] == 1) so = o;
+  if (!so) return HPTB_FALLBACK;
+  for (int o = 0; o <= NIN; ++o)
+    if (std::llabs(p.sa[o]) > 0x7fffffffLL || std::llabs(p.sb[o]) > 0x7fffffffLL) return HPTB_FALLBACK;
+  const int64_t tiles_a = (p.A + kTmaTA - 1) / kTmaTA, tiles_b = (p.B + (int64_t)kTmaSub * BWE - 1) / ((int64_t)kTmaSub * BWE);
+  if (tiles_a > 0x7fffffffLL || tiles_b > 65535) return HPTB_FALLBACK;
+  CUtensorMap tmap;
+  const O* staged = so == 1 ? a : b;
+  if (!tma_make_map<O>(&tmap, staged, p.A, p.B, p.sa[so], p.nbatch, p.batch_shape, p.batch_stride[so])) return HPTB_FALLBACK;
+  TmaTileParams q;
+  memset(&q, 0, sizeof(q));
+  q.A = p.A;
+  q.B = p.B;
+  q.out_sb = p.sb[0];
+  q.nbatch = p.nbatch;
+  const int other = NIN == 2 ? 3 - so : 0;
+  const O* in1 = other == 1 ? a : b;
+  if (other) {
+    q.in1_sb = p.sb[other];
+    q.in1_mode = p.mode[other] == 2 ? kSmemModeDirect : kSmemModeScalar;
+    q.swap = other == 1 ? 1 : 0;
+  }
+  for (int i = 0; i < 3; ++i) {
+    q.batch_shape[i] = i < p.nbatch ? p.batch_shape[i] : 1u;
+    q.batch_out[i] = i < p.nbatch ? p.batch_stride[0][i] : 0;
+    q.batch_in1[i] = (other && i < p.nbatch) ? p.batch_stride[other][i] : 0;
+  }
+  auto kern = map_tma_tile_kernel<NIN, F, O>;
+  constexpr int smem_bytes = kTmaSub * TG::kSubStride + 64;
+  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (attr != cudaSuccess) return fail(HPTB_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(attr));
+  HPTB_CUDA_CHECK(launch_kernel(kern, dim3((unsigned)tiles_a, (unsigned)tiles_b, (unsigned)batch), dim3(kTmaThreads), smem_bytes, stream, out, in1, tmap, q, f));
+  return HPTB_OK;
+}
+
 template <int NIN, typename F, typename O, typename A, typename B>
 hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
   const Collapsed& c = plan.c;
@@ -720,50 +765,11 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
     }
     for (int o = 0; o <= NIN && ok; ++o)
       if (std::llabs(p.sa[o]) > 0x7fffffffLL || std::llabs(p.sb[o]) > 0x7fffffffLL) ok = false;
-    // one staged operand of a 2- or 4-byte type whose layout a tensor map can describe: TMA-staged tiles (tma_tile.cuh)
+    // one staged operand whose layout a tensor map can describe: TMA-staged tiles (tma_tile.cuh)
     if constexpr (sizeof(O) == 2 || sizeof(O) == 4) {
-      bool tma_ok = ok && nstaged == 1 && p.nbatch <= 3 && batch <= 65535 && !big && !tma_disabled() &&
-                    p.A * p.B * batch >= 4096 && !tune_flag("HPTB_TUNE_NO_TMA");
-      int so = 0;  // the staged operand
-      for (int o = 1; o <= NIN && tma_ok; ++o) {
-        if (p.mode[o] == 1) so = o;
-        else if (p.mode[o] == 2) {}
-        else if (p.sa[o] == 0 && p.sb[o] == 0) {}
-        else tma_ok = false;
-      }
-      if (tma_ok && so > 0) {
-        typedef TmaGeom<sizeof(O)> TG;
-        const int64_t tiles_a = (p.A + kTmaTA - 1) / kTmaTA, tiles_b = (p.B + (int64_t)kTmaSub * TG::BW - 1) / ((int64_t)kTmaSub * TG::BW);
-        CUtensorMap tmap;
-        const O* staged = so == 1 ? reinterpret_cast<const O*>(a) : reinterpret_cast<const O*>(b);
-        if (tiles_a <= 0x7fffffffLL && tiles_b <= 65535 &&
-            tma_make_map<O>(&tmap, staged, p.A, p.B, p.sa[so], p.nbatch, p.batch_shape, p.batch_stride[so])) {
-          TmaTileParams q;
-          memset(&q, 0, sizeof(q));
-          q.A = p.A;
-          q.B = p.B;
-          q.out_sb = p.sb[0];
-          q.nbatch = p.nbatch;
-          const int other = NIN == 2 ? 3 - so : 0;
-          const O* in1 = other == 1 ? reinterpret_cast<const O*>(a) : reinterpret_cast<const O*>(b);
-          if (other) {
-            q.in1_sb = p.sb[other];
-            q.in1_mode = p.mode[other] == 2 ? kSmemModeDirect : kSmemModeScalar;
-            q.swap = other == 1 ? 1 : 0;
-          }
-          for (int i = 0; i < 3; ++i) {
-            q.batch_shape[i] = i < p.nbatch ? p.batch_shape[i] : 1u;
-            q.batch_out[i] = i < p.nbatch ? p.batch_stride[0][i] : 0;
-            q.batch_in1[i] = (other && i < p.nbatch) ? p.batch_stride[other][i] : 0;
-          }
-          auto kern = map_tma_tile_kernel<NIN, F, O>;
-          constexpr int smem_bytes = kTmaSub * TG::kSubStride + 64;
-          static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-          if (attr != cudaSuccess) return fail(HPTB_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(attr));
-          HPTB_CUDA_CHECK(launch_kernel(kern, dim3((unsigned)tiles_a, (unsigned)tiles_b, (unsigned)batch), dim3(kTmaThreads), smem_bytes, stream, out, in1,
-                                        tmap, q, f));
-          return HPTB_OK;
-        }
+      if (ok && nstaged == 1) {
+        const hptb_status st = launch_tma_tile<NIN, F, O>(p, batch, big, out, reinterpret_cast<const O*>(a), reinterpret_cast<const O*>(b), f, stream);
+        if (st != HPTB_FALLBACK) return st;
       }
     }
     if (ok && nstaged > 0) {
@@ -800,6 +806,22 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
       }
       HPTB_CUDA_CHECK(launch_kernel(kern, grid, dim3(kMapThreads), smem, stream, out, reinterpret_cast<const O*>(a), reinterpret_cast<const O*>(b), q, f));
       return HPTB_OK;
+    }
+  }
+  // 1-byte types (i8 / u8 / bool): the same TMA tiles on a u16 view of the staged operand, bytes pulled apart with prmt
+  // (the register micro-tile kernel below runs a transposed i8 copy at 0.35 of peak)
+  if constexpr (std::is_same<O, A>::value && std::is_same<O, B>::value && sizeof(O) == 1) {
+    bool ok1 = db >= 0 && p.mode[0] == 2 && p.A % 8 == 0 && p.B % 2 == 0;
+    int nstaged = 0;
+    for (int o = 1; o <= NIN && ok1; ++o) {
+      if (p.mode[o] == 1) ++nstaged;
+      else if (p.mode[o] == 2) {}
+      else if (p.sa[o] == 0 && p.sb[o] == 0) {}
+      else ok1 = false;
+    }
+    if (ok1 && nstaged == 1) {
+      const hptb_status st = launch_tma_tile<NIN, F, O>(p, batch, big, out, reinterpret_cast<const O*>(a), reinterpret_cast<const O*>(b), f, stream);
+      if (st != HPTB_FALLBACK) return st;
     }
   }
   int64_t blocks = p.ntiles < 0x7fffffffLL ? p.ntiles : 0x7fffffffLL;

@@ -952,18 +952,18 @@ constexpr int lean_cols_min_blocks() {
 // first one is awaited, so the k·VEC remote entries are in flight together (xchg.cuh)
 template <typename Op, int VEC>
 __device__ __forceinline__ void lean_cols_finish(typename Op::Out* out, typename Op::Out* out2, int64_t off0,
-                                                 const typename Op::Acc* vals, const LeanColsParams& p) {
+                                                 const typename Op::Acc* vals, int vstride, const LeanColsParams& p) {
   if constexpr (!Op::kTwoOutputs) {
     if (p.xchg.enabled) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) xchg_push<Op>(p.xchg, off0 + j, vals[j]);
+      for (int j = 0; j < VEC; ++j) xchg_push<Op>(p.xchg, off0 + j, vals[j * vstride]);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, off0 + j, xchg_collect<Op>(p.xchg, off0 + j), p.count, p.fold_out);
       return;
     }
   }
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, off0 + j, vals[j], p.count, p.fold_out);
+  for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, off0 + j, vals[j * vstride], p.count, p.fold_out);
 }
 
 template <typename Op, typename T, int VEC>
@@ -976,7 +976,7 @@ reduce_cols_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__
   constexpr int UNROLL = HPTB_RED_UNROLL;
   constexpr int TX = 32, TY = kRedThreads / TX, W = TX * VEC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Acc* sm = reinterpret_cast<Acc*>(smem_raw);  // [TY][W]
+  Acc* sm = reinterpret_cast<Acc*>(smem_raw);  // [TY][VEC][TX]: lanes are adjacent, so 8- and 16-byte accumulators are conflict-free
   const uint32_t tid = threadIdx.x, tx = tid & (TX - 1), ty = tid / TX;
   // blockIdx.x = (split · K + k) · col_tiles + tile: CTAs that run together read adjacent column segments of the same rows
   uint32_t b = blockIdx.x;
@@ -1010,25 +1010,25 @@ reduce_cols_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__
     }
   }
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = Op::finish(acc[j], r_begin + ty, TY, 1, 0);
+  for (int j = 0; j < VEC; ++j) sm[(ty * VEC + j) * TX + tx] = Op::finish(acc[j], r_begin + ty, TY, 1, 0);
   __syncthreads();
 #pragma unroll
   for (int h = TY >> 1; h > 0; h >>= 1) {
     if (ty < h) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = Op::combine(sm[ty * W + tx * VEC + j], sm[(ty + h) * W + tx * VEC + j]);
+      for (int j = 0; j < VEC; ++j) sm[(ty * VEC + j) * TX + tx] = Op::combine(sm[(ty * VEC + j) * TX + tx], sm[((ty + h) * VEC + j) * TX + tx]);
     }
     __syncthreads();
   }
   if (p.S == 1) {
-    if (ty == 0 && col_ok) lean_cols_finish<Op, VEC>(out, out2, out_off + col, sm + tx * VEC, p);
+    if (ty == 0 && col_ok) lean_cols_finish<Op, VEC>(out, out2, out_off + col, sm + tx, TX, p);
     return;
   }
   const uint32_t group = k * p.col_tiles + tile;
   Acc* my = scratch + ((size_t)group * p.S + split) * W;
   if (ty == 0) {
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) my[tx * VEC + j] = sm[tx * VEC + j];
+    for (int j = 0; j < VEC; ++j) my[tx * VEC + j] = sm[j * TX + tx];
   }
   if (take_ticket(tickets + group, p.S)) {
     Acc part[VEC];
@@ -1041,17 +1041,17 @@ reduce_cols_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = part[j];
+    for (int j = 0; j < VEC; ++j) sm[(ty * VEC + j) * TX + tx] = part[j];
     __syncthreads();
 #pragma unroll
     for (int h = TY >> 1; h > 0; h >>= 1) {
       if (ty < h) {
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) sm[ty * W + tx * VEC + j] = Op::combine(sm[ty * W + tx * VEC + j], sm[(ty + h) * W + tx * VEC + j]);
+        for (int j = 0; j < VEC; ++j) sm[(ty * VEC + j) * TX + tx] = Op::combine(sm[(ty * VEC + j) * TX + tx], sm[((ty + h) * VEC + j) * TX + tx]);
       }
       __syncthreads();
     }
-    if (ty == 0 && col_ok) lean_cols_finish<Op, VEC>(out, out2, out_off + col, sm + tx * VEC, p);
+    if (ty == 0 && col_ok) lean_cols_finish<Op, VEC>(out, out2, out_off + col, sm + tx, TX, p);
   }
 }
 
@@ -1295,6 +1295,10 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
         // [262144,16384]: 64 → 2367 µs, 128 → 2347 µs; profiles/r02b_sweep_shard.txt).
         int64_t S = ((int64_t)sms * 4 + lgroups / 2) / lgroups;
         const int64_t by_rows = R >= 32768 ? R / 512 : (R + 4095) / 4096;
+        // kernels whose registers allow fewer than four CTAs per SM ((value, index) pairs of 8-byte types: three): keep
+        // the grid inside ONE wave of what is really resident (i64 [4096,8192] argmin(0): 640 CTAs on 444 slots, 73.6 µs)
+        static const int occ_s = ctas_per_sm(reduce_cols_lean_kernel<Op, T, VECMAX>, (size_t)kRedThreads * VECMAX * sizeof(Acc));
+        if (occ_s < 4 && S > 1 && lgroups * S > (int64_t)sms * occ_s) S = ((int64_t)sms * occ_s) / lgroups > 0 ? ((int64_t)sms * occ_s) / lgroups : 1;
         if (S < by_rows) S = by_rows;
         if (S > (R >= 32768 ? 128 : 64)) S = R >= 32768 ? 128 : 64;
         const int64_t max_s = (R + (int64_t)LTY * HPTB_RED_UNROLL - 1) / ((int64_t)LTY * HPTB_RED_UNROLL);  // ≥ one batch per thread row

@@ -1,4 +1,4 @@
-// tma_tile.cuh — transposing elementwise kernel with TMA-staged tiles (2- and 4-byte element types).
+// tma_tile.cuh — transposing elementwise kernel with TMA-staged tiles (1-, 2- and 4-byte element types).
 //
 // The case: a permuted operand whose unit-stride dim (b) is not the output's (a) — BASELINE config 2 `V = X.t();
 // V.sin()`.  map_tiled_smem_kernel (elementwise.cuh) stages such tiles with per-thread 16-byte loads and an
@@ -69,14 +69,18 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 template <int NIN, typename F, typename T>
 __global__ void __launch_bounds__(kTmaThreads, kTmaMinCtas)
 map_tma_tile_kernel(T* __restrict__ out, const T* __restrict__ in1, const __grid_constant__ CUtensorMap tmap, TmaTileParams p, F f) {
-  typedef TmaGeom<sizeof(T)> G;
-  constexpr int E = G::E;
+  // 1-byte types ride the 2-byte geometry: the tile is loaded and ldmatrix-transposed as u16 PAIRS along b, and the two
+  // bytes of every pair — rows 2·b2 and 2·b2 + 1 of the output — are pulled apart with four byte permutes per thread
+  constexpr bool kBytes = sizeof(T) == 1;
+  typedef TmaGeom<(kBytes ? 2 : sizeof(T))> G;
+  constexpr int E = G::E;  // elements per 16-byte pack of the transposed unit (8 for the byte variant: two 8-byte rows)
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTmaSub * G::kSubStride);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t a0 = (int64_t)blockIdx.x * kTmaTA;
-  const int64_t b0 = (int64_t)blockIdx.y * (kTmaSub * G::BW);
-  int nsub = (int)((p.B - b0 + G::BW - 1) / G::BW);
+  constexpr int BWE = G::BW * (kBytes ? 2 : 1);  // b-elements per sub-tile
+  const int64_t b0 = (int64_t)blockIdx.y * (kTmaSub * BWE);
+  int nsub = (int)((p.B - b0 + BWE - 1) / BWE);
   if (nsub > kTmaSub) nsub = kTmaSub;
   // batch coordinates (once per CTA)
   int32_t bc3[3] = {0, 0, 0};
@@ -104,7 +108,7 @@ map_tma_tile_kernel(T* __restrict__ out, const T* __restrict__ in1, const __grid
   if (tid < nsub * G::kBoxes) {
     const int s = tid / G::kBoxes, r = tid % G::kBoxes;
     const uint32_t dst = smem_addr(smem + s * G::kSubStride + G::region_off(r));
-    const int32_t c0 = (int32_t)(b0 + (int64_t)s * G::BW), c1 = (int32_t)(a0 + r);
+    const int32_t c0 = (int32_t)((b0 + (int64_t)s * BWE) / (kBytes ? 2 : 1)), c1 = (int32_t)(a0 + r);
     asm volatile(
         "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
         "l"(&tmap), "r"(c0), "r"(c1), "r"(bc3[0]), "r"(bc3[1]), "r"(bc3[2]), "r"(smem_addr(bars + s))
@@ -122,6 +126,11 @@ map_tma_tile_kernel(T* __restrict__ out, const T* __restrict__ in1, const __grid
       ld_off[i] = G::region_off(j) + (ah * 8 + row) * 128 + ((bc ^ row) << 4);
       a_loc[i] = ah * 32 + (lane >> 2) * 4;
       b_loc[i] = bc * 4 + (lane & 3);
+    } else if constexpr (kBytes) {
+      const int j = lane >> 3, row = lane & 7, t = row >> 1, reg = 2 * j + (row & 1), rl = ah * 4 + t;
+      ld_off[i] = G::region_off(reg) + rl * 128 + ((bc ^ ((rl + 4 * (reg & 1)) & 7)) << 4);
+      a_loc[i] = ah * 32 + (lane & 3) * 8;
+      b_loc[i] = 2 * (bc * 8 + (lane >> 2));  // the EVEN row of the pair
     } else {
       const int j = lane >> 3, row = lane & 7, t = row >> 1, reg = 2 * j + (row & 1), rl = ah * 4 + t;
       ld_off[i] = G::region_off(reg) + rl * 128 + ((bc ^ ((rl + 4 * (reg & 1)) & 7)) << 4);
@@ -140,26 +149,42 @@ map_tma_tile_kernel(T* __restrict__ out, const T* __restrict__ in1, const __grid
           : "memory");
     } while (!done);
   };
-  auto load_unit = [&](int s, int i, Pack<T, E>& x) {
+  // 16 bytes of the transposed unit: E consecutive a at one b — for 1-byte types 8 consecutive a of the EVEN row
+  // (bytes 0..7) followed by the same 8 a of the ODD row (bytes 8..15)
+  auto load_unit = [&](int s, int i, Pack<T, (kBytes ? 16 : E)>& x) {
     uint32_t r[4];
     const uint32_t addr = smem_addr(smem + s * G::kSubStride) + ld_off[i];
     if constexpr (sizeof(T) == 4)
       asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
     else
       asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-    memcpy(&x, r, 16);
+    if constexpr (kBytes) {
+      const uint32_t q[4] = {__byte_perm(r[0], r[1], 0x6420), __byte_perm(r[2], r[3], 0x6420), __byte_perm(r[0], r[1], 0x7531),
+                             __byte_perm(r[2], r[3], 0x7531)};
+      memcpy(&x, q, 16);
+    } else {
+      memcpy(&x, r, 16);
+    }
   };
   if constexpr (NIN == 1) {
     for (int s = 0; s < nsub; ++s) {
       wait_sub(s);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        Pack<T, E> x, y;
+        Pack<T, (kBytes ? 16 : E)> x, y;
         load_unit(s, i, x);
-        const int64_t bg = b0 + (int64_t)s * G::BW + b_loc[i];
-        if (bg >= p.B || a0 + a_loc[i] >= p.A) continue;  // A is a multiple of E: packs are all-in or all-out
-        apply_pack<F, T, T, E>(f, y, x);
-        store_pack<T, E>(dst_base + bg * p.out_sb + a_loc[i], y);
+        const int64_t bg = b0 + (int64_t)s * BWE + b_loc[i];
+        if (bg >= p.B || a0 + a_loc[i] >= p.A) continue;  // A is a multiple of E (B of 2): packs are all-in or all-out
+        apply_pack<F, T, T, (kBytes ? 16 : E)>(f, y, x);
+        if constexpr (kBytes) {
+          Pack<T, 8> lo, hi;
+          memcpy(&lo, &y, 8);
+          memcpy(&hi, reinterpret_cast<const char*>(&y) + 8, 8);
+          store_pack<T, 8>(dst_base + bg * p.out_sb + a_loc[i], lo);
+          store_pack<T, 8>(dst_base + (bg + 1) * p.out_sb + a_loc[i], hi);
+        } else {
+          store_pack<T, E>(dst_base + bg * p.out_sb + a_loc[i], y);
+        }
       }
     }
   } else {
@@ -171,12 +196,23 @@ map_tma_tile_kernel(T* __restrict__ out, const T* __restrict__ in1, const __grid
     const T* in1_base = in1 + off_in1 + (direct ? a0 : 0);
     T scalar1{};
     if (!direct) scalar1 = load_one(in1 + off_in1);
-    Pack<T, E> ring[kPre + 1][2];
-    auto fetch = [&](int s, Pack<T, E> (&dst)[2]) {
+    constexpr int PE = kBytes ? 16 : E;
+    Pack<T, PE> ring[kPre + 1][2];
+    auto fetch = [&](int s, Pack<T, PE> (&dst)[2]) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int64_t bg = b0 + (int64_t)s * G::BW + b_loc[i];
-        if (direct && s < nsub && bg < p.B && a0 + a_loc[i] < p.A) load_pack<T, E>(dst[i], in1_base + bg * p.in1_sb + a_loc[i]);
+        const int64_t bg = b0 + (int64_t)s * BWE + b_loc[i];
+        if (direct && s < nsub && bg < p.B && a0 + a_loc[i] < p.A) {
+          if constexpr (kBytes) {  // the even and the odd row of the pair, 8 bytes each
+            Pack<T, 8> lo, hi;
+            load_pack<T, 8>(lo, in1_base + bg * p.in1_sb + a_loc[i]);
+            load_pack<T, 8>(hi, in1_base + (bg + 1) * p.in1_sb + a_loc[i]);
+            memcpy(&dst[i], &lo, 8);
+            memcpy(reinterpret_cast<char*>(&dst[i]) + 8, &hi, 8);
+          } else {
+            load_pack<T, E>(dst[i], in1_base + bg * p.in1_sb + a_loc[i]);
+          }
+        }
       }
     };
 #pragma unroll
@@ -188,23 +224,31 @@ map_tma_tile_kernel(T* __restrict__ out, const T* __restrict__ in1, const __grid
       wait_sub(s);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        Pack<T, E> x, y;
+        Pack<T, PE> x, y;
         load_unit(s, i, x);
-        const int64_t bg = b0 + (int64_t)s * G::BW + b_loc[i];
+        const int64_t bg = b0 + (int64_t)s * BWE + b_loc[i];
         if (bg >= p.B || a0 + a_loc[i] >= p.A) continue;
-        Pack<T, E> o = ring[s % (kPre + 1)][i];
+        Pack<T, PE> o = ring[s % (kPre + 1)][i];
         if (!direct) {
 #pragma unroll
-          for (int k = 0; k < E; ++k) o.v[k] = scalar1;
+          for (int k = 0; k < PE; ++k) o.v[k] = scalar1;
         }
         if (p.swap) {
 #pragma unroll
-          for (int k = 0; k < E; ++k) y.v[k] = f(o.v[k], x.v[k]);
+          for (int k = 0; k < PE; ++k) y.v[k] = f(o.v[k], x.v[k]);
         } else {
 #pragma unroll
-          for (int k = 0; k < E; ++k) y.v[k] = f(x.v[k], o.v[k]);
+          for (int k = 0; k < PE; ++k) y.v[k] = f(x.v[k], o.v[k]);
         }
-        store_pack<T, E>(dst_base + bg * p.out_sb + a_loc[i], y);
+        if constexpr (kBytes) {
+          Pack<T, 8> lo, hi;
+          memcpy(&lo, &y, 8);
+          memcpy(&hi, reinterpret_cast<const char*>(&y) + 8, 8);
+          store_pack<T, 8>(dst_base + bg * p.out_sb + a_loc[i], lo);
+          store_pack<T, 8>(dst_base + (bg + 1) * p.out_sb + a_loc[i], hi);
+        } else {
+          store_pack<T, E>(dst_base + bg * p.out_sb + a_loc[i], y);
+        }
       }
     }
   }
@@ -237,11 +281,12 @@ inline bool tma_disabled() {
 template <typename T>
 inline bool tma_make_map(CUtensorMap* m, const T* base, int64_t A, int64_t B, int64_t sa, int nbatch, const uint32_t* bshape,
                          const int64_t* bstride) {
-  typedef TmaGeom<sizeof(T)> G;
+  typedef TmaGeom<(sizeof(T) == 1 ? 2 : sizeof(T))> G;
   TmaEncodeTiledFn enc = tma_encoder();
   if (!enc) return false;
   if (reinterpret_cast<uintptr_t>(base) % 16 || A <= 0 || B <= 0 || A >= (int64_t(1) << 31) || B >= (int64_t(1) << 31)) return false;
-  cuuint64_t dims[5] = {(cuuint64_t)B, (cuuint64_t)A, 1, 1, 1};
+  if (sizeof(T) == 1 && (B & 1)) return false;  // 1-byte types travel as pairs along b
+  cuuint64_t dims[5] = {(cuuint64_t)(sizeof(T) == 1 ? B / 2 : B), (cuuint64_t)A, 1, 1, 1};
   cuuint64_t strides[4] = {0, 0, 0, 0};  // bytes, dims 1..4
   auto ok_stride = [](int64_t s_bytes) { return s_bytes > 0 && s_bytes % 16 == 0 && s_bytes < (int64_t(1) << 40); };
   if (!ok_stride(sa * (int64_t)sizeof(T))) return false;
@@ -259,7 +304,7 @@ inline bool tma_make_map(CUtensorMap* m, const T* base, int64_t A, int64_t B, in
   }
   const cuuint32_t box[5] = {(cuuint32_t)G::BW, (cuuint32_t)kTmaTA, 1, 1, 1};
   const cuuint32_t estr[5] = {1, (cuuint32_t)G::E, 1, 1, 1};
-  const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+  const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;  // 1-byte: u16 pairs
   const CUresult rc = enc(m, dt, 5, const_cast<T*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return rc == CUDA_SUCCESS;

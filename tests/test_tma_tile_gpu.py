@@ -49,7 +49,7 @@ def test_transposed_unary(hb, d, op):
         assert got.tobytes() == alt.tobytes(), f"{op} {d} {shape}: TMA and shared-memory tile kernels disagree"
 
 
-@pytest.mark.parametrize("d", ["f32", "i32", "u32", "f16", "bf16", "i16", "u16"])
+@pytest.mark.parametrize("d", ["f32", "i32", "u32", "f16", "bf16", "i16", "u16", "i8", "u8", "bool"])
 def test_transposed_copy_is_bit_exact(hb, d):
     rng = np.random.default_rng(41)
     for shape in SHAPES + [(3, 5, 136, 200), (2, 264, 72)]:
@@ -80,7 +80,7 @@ def test_batched_and_sliced_views(hb):
         assert got.tobytes() == alt.tobytes()
 
 
-@pytest.mark.parametrize("d", ["f32", "i32", "bf16", "i16"])
+@pytest.mark.parametrize("d", ["f32", "i32", "bf16", "i16", "i8", "u8"])
 def test_binary_with_one_permuted_operand(hb, d):
     rng = np.random.default_rng(43)
     for shape in [(256, 512), (300, 520), (5, 136, 72)]:
@@ -109,3 +109,19 @@ def test_binary_with_one_permuted_operand(hb, d):
     want, od = O.binary("sub", a.T, d, s, d)
     assert_exact(got, want, od, f"sub scalar {d}")
     assert got.tobytes() == alt.tobytes()
+
+
+@pytest.mark.parametrize("d", ["i8", "u8"])
+def test_one_byte_unary_on_transposed_view(hb, d):
+    """1-byte types ride the 2-byte tiles as pairs along b and are pulled apart with byte permutes (tma_tile.cuh)"""
+    rng = np.random.default_rng(44)
+    for shape in [(256, 512), (264, 1040), (1000, 72), (3, 136, 200)]:
+        x = rand(rng, shape, d)
+        X = hb.Tensor.to_cuda(to_torch(x, d))
+        perm = list(range(len(shape)))
+        perm[-1], perm[-2] = perm[-2], perm[-1]
+        for op in ("neg", "abs", "square"):
+            got, alt = _both_paths(lambda: to_numpy(getattr(X.permute(perm), op)().to_cpu(), d))
+            want, od = O.normal_unary(op, np.transpose(x, perm), d)
+            assert_exact(got, want, od, f"{op} {d} {shape}")
+            assert got.tobytes() == alt.tobytes()
