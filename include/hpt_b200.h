@@ -283,8 +283,8 @@ hptb_status hptb_eye(hptb_ctx* ctx, hptb_tensor* out, int64_t k, void* stream);
 hptb_status hptb_comm_unique_id(void* id128);                          /* rank 0, then broadcast out of band */
 hptb_status hptb_comm_init_rank(hptb_ctx* ctx, int nranks, int rank, const void* id128, hptb_comm** out);
 hptb_status hptb_comm_destroy(hptb_comm* comm);
-/* 1 if small partials are exchanged through peer-mapped mailboxes (CUDA IPC over NVLink, one kernel per rank),
- * 0 if every exchange goes through NCCL (IPC unavailable, or HPTB_NO_P2P=1). */
+/* 1 if accumulators are exchanged through peer-mapped mailboxes (CUDA IPC over NVLink, inside the reduce kernel),
+ * 0 if every exchange goes through NCCL (IPC unavailable, or HPTB_NO_P2P=1 on any rank). */
 int hptb_comm_uses_peer_memory(const hptb_comm* comm);
 /* Outer-axis sharding helpers (pure host code, usable without a GPU).
  * hptb_shard_bounds: rank r of `world` owns rows [offset, offset+len) of an axis of length n — contiguous
@@ -297,7 +297,7 @@ typedef enum hptb_collective {
   HPTB_COLL_ALLREDUCE_PROD = 2,
   HPTB_COLL_ALLREDUCE_MAX = 3,
   HPTB_COLL_ALLREDUCE_MIN = 4,
-  HPTB_COLL_ALLGATHER_ARG = 5   /* argmax/argmin: all-gather (extreme value, global index), rank-ordered strict combine */
+  HPTB_COLL_ALLGATHER_ARG = 5   /* argmax/argmin: (extreme value, global index) pairs, rank-ordered strict combine */
 } hptb_collective;
 typedef struct hptb_shard_plan {
   int32_t crosses;      /* 1 if shard_axis is among the reduced axes */
@@ -310,12 +310,16 @@ typedef struct hptb_shard_plan {
 hptb_status hptb_shard_bounds(int64_t n, int world, int rank, int64_t* offset, int64_t* len);
 hptb_status hptb_shard_plan_reduce(int op, const int32_t* axes, int naxes, int shard_axis, int world,
                                    hptb_shard_plan* plan);
-/* Combine per-rank partials in place.  op = HPTB_SUM / HPTB_MAX / HPTB_MIN / HPTB_PROD. */
+/* Combine per-rank partials in place.  op = HPTB_SUM / HPTB_MAX / HPTB_MIN / HPTB_PROD.  One stream per comm. */
 hptb_status hptb_allreduce(hptb_comm* comm, int op, hptb_tensor* inout, void* stream);
-/* Reduction of a tensor sharded along axis `shard_axis` (each rank passes its own shard).  Reduces
- * locally, then — only if shard_axis is among `axes` — exchanges partials over NCCL and applies the
- * post-op (÷ global count for MEAN, log for LOGSUMEXP, lowest global index for ARGMAX/ARGMIN).
- * `global_axis_len` is the full length of the sharded axis, `shard_offset` this rank's start. */
+/* Reduction of a tensor sharded along axis `shard_axis` (each rank passes its own shard).  Reduces locally, then —
+ * only if shard_axis is among `axes` — combines the per-rank ACCUMULATORS (f32 for f16/bf16/f32 inputs, (value, global
+ * index) pairs for ARGMAX/ARGMIN, Σexp for LOGSUMEXP, the unrooted power sum for REDUCEL2/3) in rank order and applies
+ * the op's post step once (÷ GLOBAL count for MEAN, ln, root): the result is rounded exactly like the single-GPU one
+ * and is bit-identical on every rank.  With peer memory the exchange runs inside the reduce kernel's epilogue (one
+ * launch per rank) or in one small follow-up kernel; otherwise over ncclAllGather.  `global_axis_len` is the full
+ * length of the sharded axis, `shard_offset` this rank's start.  Collective: every rank of the comm must make the same
+ * sequence of calls, all on ONE stream per comm. */
 hptb_status hptb_reduce_sharded(hptb_comm* comm, int op, const hptb_tensor* shard, const int32_t* axes,
                                 int naxes, int shard_axis, int64_t shard_offset, int64_t global_axis_len,
                                 hptb_tensor* out, void* stream);

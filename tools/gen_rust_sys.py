@@ -108,6 +108,14 @@ def rust_type(ctype, known):
     return r
 
 
+RUST_KEYWORDS = {"in", "type", "ref", "box", "move", "fn", "mod", "use", "loop", "match", "impl", "self", "super", "where", "as",
+                 "dyn", "final", "override", "priv", "abstract", "become", "do", "macro", "typeof", "unsized", "virtual", "yield", "try"}
+
+
+def rust_ident(name):
+    return "r#" + name if name in RUST_KEYWORDS else name
+
+
 def generate():
     h = parse_header()
     known = set(h["enums"]) | set(h["structs"]) | set(h["opaque"])
@@ -140,13 +148,13 @@ def generate():
             rt = rust_type(ct, known)
             for d in reversed(dims):
                 rt = f"[{rt}; {d}]"
-            o.append(f"    pub {fn_}: {rt},")
+            o.append(f"    pub {rust_ident(fn_)}: {rt},")
         o.append("}")
         o.append("")
     o.append('#[link(name = "hpt_b200")]')
     o.append('extern "C" {')
     for name, ret, args in h["functions"]:
-        al = ", ".join(f"{an}: {rust_type(ct, known)}" for ct, an in args)
+        al = ", ".join(f"{rust_ident(an)}: {rust_type(ct, known)}" for ct, an in args)
         r = "" if ret == "void" else f" -> {rust_type(ret, known)}"
         o.append(f"    pub fn {name}({al}){r};")
     o.append("}")
