@@ -63,7 +63,7 @@ class HptbReduceRoute(Structure):
                 ("scratch_strides", c_int64 * MAX_DIMS)]
 
 
-ROUTES = ["direct", "peel", "two_step"]
+ROUTES = ["direct", "peel", "two_step", "peel_raw"]
 
 
 class HptbShardPlan(Structure):
@@ -132,6 +132,7 @@ SIGNATURES = {
     "hptb_eye": (c_int, [c_void_p, _T, c_int64, c_void_p]),
     "hptb_comm_unique_id": (c_int, [c_void_p]),
     "hptb_comm_init_rank": (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "hptb_comm_init_local_group": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),
     "hptb_comm_destroy": (c_int, [c_void_p]),
     "hptb_comm_uses_peer_memory": (c_int, [c_void_p]),
     "hptb_shard_bounds": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),

@@ -182,9 +182,15 @@ void plan_reduce_route(int op, const hptb_tensor* in, const int32_t* axes, int n
     const int last = in->ndim - 1;
     const size_t esz = dtype_size(in->dtype);
     const int64_t pack = esz <= 8 ? (int64_t)(16 / esz) : 1;
-    const bool op_ok = op == HPTB_SUM || op == HPTB_MAX || op == HPTB_MIN || op == HPTB_PROD || op == HPTB_SUM_SQUARE ||
-                       op == HPTB_REDUCEL1 || op == HPTB_NANSUM || op == HPTB_NANPROD || op == HPTB_ALL || op == HPTB_ANY;
-    const bool dt_ok = in->dtype != HPTB_F16 && in->dtype != HPTB_BF16;
+    const bool fold_ok = op == HPTB_SUM || op == HPTB_MAX || op == HPTB_MIN || op == HPTB_PROD || op == HPTB_SUM_SQUARE ||
+                         op == HPTB_REDUCEL1 || op == HPTB_NANSUM || op == HPTB_NANPROD || op == HPTB_ALL || op == HPTB_ANY;
+    // ops whose OUTPUT is not their accumulator (mean: Σ then ÷ n; logsumexp: Σexp then ln; l2 / l3: power sum then root)
+    // and half-precision dtypes (f32 accumulator, half output) cannot fold through `out`: their pieces are combined in a
+    // scratch of ACCUMULATORS and finished by the combine kernel (PEEL_RAW)
+    const bool raw_ok = op == HPTB_MEAN || op == HPTB_LOGSUMEXP || op == HPTB_REDUCEL2 || op == HPTB_REDUCEL3;
+    const bool half = in->dtype == HPTB_F16 || in->dtype == HPTB_BF16;
+    const bool op_ok = fold_ok || raw_ok;
+    const bool dt_ok = true;
     bool has_last = false;
     for (int i = 0; i < naxes; ++i) has_last |= axes[i] == last;
     const uintptr_t addr = reinterpret_cast<uintptr_t>(in->data);
@@ -195,7 +201,7 @@ void plan_reduce_route(int op, const hptb_tensor* in, const int32_t* axes, int n
         if (in->shape[d] > 1 && (uint64_t)(std::llabs(in->strides[d]) * (int64_t)esz) % 16) rows_ok = false;
       if (rows_ok) {
         const int64_t L = in->shape[last];
-        route->kind = HPTB_ROUTE_PEEL;
+        route->kind = (raw_ok || half) ? HPTB_ROUTE_PEEL_RAW : HPTB_ROUTE_PEEL;
         route->head = pack - (int64_t)((addr % 16) / esz);
         route->body = ((L - route->head) / pack) * pack;
         route->tail = L - route->head - route->body;
@@ -241,6 +247,10 @@ void plan_reduce_route(int op, const hptb_tensor* in, const int32_t* axes, int n
 namespace hptb {
 hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, hptb_tensor* out,
                         int init_out, double count_override, void* stream);
+hptb_status reduce_pieces(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, const hptb_tensor* lay, double count,
+                          void* raw, bool accumulate, void* stream);
+hptb_status reduce_combine(hptb_ctx* ctx, int op, int in_dtype, double count, const void* partials, int gathered, const XchgParams* x,
+                           const hptb_tensor* out, void* stream);
 }
 using namespace hptb;
 
@@ -309,6 +319,35 @@ hptb_status reduce_impl(hptb_ctx* ctx, int op, const hptb_tensor* in, const int3
     }
     return HPTB_OK;
   }
+  if (route.kind == HPTB_ROUTE_PEEL_RAW) {
+    // head / aligned body / tail reduced into a scratch of accumulators laid out like a row-major `out`, then one small
+    // kernel applies the op's post step and writes `out` (any strides)
+    const int last = in->ndim - 1;
+    const int64_t esz = (int64_t)dtype_size(in->dtype);
+    const int64_t M = numel(*out);
+    if (M == 0) return HPTB_OK;
+    double count = 1.0;
+    for (int i = 0; i < naxes; ++i) count *= (double)in->shape[axes[i]];
+    hptb_tensor lay = *out;
+    int64_t st = 1;
+    for (int i = lay.ndim - 1; i >= 0; --i) { lay.strides[i] = st; st *= lay.shape[i]; }
+    lay.data = nullptr;
+    Scratch raw;
+    HPTB_TRY(raw.get(ctx, (size_t)M * 16, stream));
+    hptb_tensor part = *in;
+    part.data = static_cast<char*>(in->data) + route.head * esz;
+    part.shape[last] = route.body;
+    HPTB_TRY(reduce_pieces(ctx, op, &part, axes, naxes, &lay, count, raw.ptr, false, stream));
+    part.data = in->data;
+    part.shape[last] = route.head;
+    HPTB_TRY(reduce_pieces(ctx, op, &part, axes, naxes, &lay, count, raw.ptr, true, stream));
+    if (route.tail > 0) {
+      part.data = static_cast<char*>(in->data) + (route.head + route.body) * esz;
+      part.shape[last] = route.tail;
+      HPTB_TRY(reduce_pieces(ctx, op, &part, axes, naxes, &lay, count, raw.ptr, true, stream));
+    }
+    return reduce_combine(ctx, op, in->dtype, count, raw.ptr, 1, nullptr, out, stream);
+  }
   if (route.kind == HPTB_ROUTE_TWO_STEP) {
     hptb_tensor tmp = *out;
     for (int j = 0; j < out->ndim; ++j) tmp.strides[j] = route.scratch_strides[j];
@@ -359,6 +398,23 @@ hptb_status reduce_for_exchange(hptb_ctx* ctx, int op, const hptb_tensor* in, co
   plan.fused = fused;
   plan.acc_bytes = acc_bytes;
   plan.reverse = pass_direction(ctx, in->data, (size_t)numel(*in) * dtype_size(in->dtype), true) ? 1 : 0;
+  DeviceGuard g(ctx->device);
+  hptb_status st = fn(plan, (cudaStream_t)stream);
+  if (st == HPTB_OK) count_launches(1);
+  return st;
+}
+
+// One piece of a peeled reduction (PEEL_RAW): bare accumulators into `raw` (row-major `lay`), stored or combined with
+// what the previous pieces left there.
+hptb_status reduce_pieces(hptb_ctx* ctx, int op, const hptb_tensor* in, const int32_t* axes, int naxes, const hptb_tensor* lay, double count,
+                          void* raw, bool accumulate, void* stream) {
+  ReduceLauncher fn = sharded_launcher(op, in->dtype, count);
+  if (!fn) return fail(HPTB_ERR_DTYPE, "reduce: no kernel for op %d on %s", op, dtype_name(in->dtype));
+  ReducePlan plan;
+  HPTB_TRY(build_reduce_plan(ctx, in, axes, naxes, lay, &plan));
+  plan.count = count;
+  plan.fold_out = accumulate ? 3 : 0;  // kFoldRawAcc (reduce.cuh)
+  plan.raw_out = raw;
   DeviceGuard g(ctx->device);
   hptb_status st = fn(plan, (cudaStream_t)stream);
   if (st == HPTB_OK) count_launches(1);

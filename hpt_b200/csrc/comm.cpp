@@ -125,6 +125,7 @@ struct hptb_comm {
   size_t slot_bytes = 0;
   uint32_t seq = 0;     // allreduce call number
   uint32_t ll_seq = 0;  // sharded-reduction call number
+  bool local = false;   // virtual rank of hptb_comm_init_local_group: no NCCL, mailboxes are plain allocations of one device
 };
 
 namespace hptb {
@@ -237,8 +238,50 @@ hptb_status hptb_comm_init_rank(hptb_ctx* ctx, int nranks, int rank, const void*
   return HPTB_OK;
 }
 
+hptb_status hptb_comm_init_local_group(hptb_ctx* ctx, int nranks, hptb_comm** comms) {
+  if (!ctx || !comms) return fail(HPTB_ERR_INVALID, "comm_init_local_group: null argument");
+  if (nranks < 1 || nranks > 16) return fail(HPTB_ERR_INVALID, "comm_init_local_group: %d ranks (1..16)", nranks);
+  DeviceGuard g(ctx->device);
+  const size_t ll_bytes = xchg_mailbox_bytes(nranks, kLLSlotBytes);
+  const size_t bytes = ll_bytes + p2p_mailbox_bytes(nranks, kSlotBytes);
+  void* boxes[16] = {nullptr};
+  for (int r = 0; r < nranks; ++r) {
+    if (cudaMalloc(&boxes[r], bytes) != cudaSuccess || cudaMemset(boxes[r], 0, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      for (int q = 0; q <= r; ++q)
+        if (boxes[q]) cudaFree(boxes[q]);
+      return fail(HPTB_ERR_OOM, "comm_init_local_group: mailbox allocation failed");
+    }
+  }
+  cudaDeviceSynchronize();
+  for (int r = 0; r < nranks; ++r) {
+    hptb_comm* c = new hptb_comm();
+    c->ctx = ctx;
+    c->nranks = nranks;
+    c->rank = r;
+    c->local = true;
+    c->p2p = nranks > 1;
+    c->slot_bytes = kSlotBytes;
+    c->ll_slot_bytes = kLLSlotBytes;
+    c->ll_bytes = ll_bytes;
+    for (int q = 0; q < nranks; ++q) {
+      c->box[q] = boxes[q];
+      c->box_ar[q] = static_cast<char*>(boxes[q]) + ll_bytes;
+    }
+    comms[r] = c;
+  }
+  return HPTB_OK;
+}
+
 hptb_status hptb_comm_destroy(hptb_comm* comm) {
   if (!comm) return HPTB_OK;
+  if (comm->local) {  // every virtual rank frees its own mailbox
+    DeviceGuard g(comm->ctx->device);
+    cudaDeviceSynchronize();
+    if (comm->box[comm->rank]) cudaFree(comm->box[comm->rank]);
+    delete comm;
+    return HPTB_OK;
+  }
   if (comm->p2p) {
     DeviceGuard g(comm->ctx->device);
     cudaDeviceSynchronize();
@@ -314,6 +357,7 @@ hptb_status hptb_allreduce(hptb_comm* comm, int op, hptb_tensor* t, void* stream
     count_launches(1);
     return HPTB_OK;
   }
+  if (comm->local) return fail(HPTB_ERR_UNSUPPORTED, "allreduce: a local group carries at most 16 KB per call (no NCCL path)");
   if (ndt < 0) return fail(HPTB_ERR_DTYPE, "allreduce: NCCL has no type for %s", dtype_name(t->dtype));
   int rc = nccl().AllReduce(t->data, t->data, (size_t)numel(*t), ndt, nop, comm->comm, (cudaStream_t)stream);
   if (rc != ncclSuccess) return nccl_fail("ncclAllReduce", rc);
@@ -371,6 +415,8 @@ hptb_status hptb_reduce_sharded(hptb_comm* comm, int op, const hptb_tensor* shar
   HPTB_TRY(reduce_for_exchange(comm->ctx, op, shard, axes, naxes, &lay, count, use_ll ? &x : nullptr, raw.ptr, &fused, &accb, stream));
   if (fused) return HPTB_OK;
   if (use_ll) return reduce_combine(comm->ctx, op, shard->dtype, count, raw.ptr, 0, &x, out, stream);
+  if (comm->local && k > 1)
+    return fail(HPTB_ERR_UNSUPPORTED, "reduce_sharded: %lld outputs exceed the mailboxes of a local group (no NCCL path)", (long long)M);
   DeviceGuard g(comm->ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
   if (is_arg && shard_offset != 0) {

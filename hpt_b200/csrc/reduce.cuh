@@ -506,14 +506,17 @@ __device__ __forceinline__ bool take_ticket(uint32_t* ticket, uint32_t S) {
 // fold = kFoldRaw: `out` is an array of ACCUMULATORS (sharded reductions whose kernel shape cannot fuse the exchange:
 // the bare local accumulator goes to a scratch, xchg_combine_kernel exchanges, combines and applies post)
 constexpr int kFoldRaw = 2;
+// fold = kFoldRawAcc: combine into the accumulator already there (the head / tail pieces of a peeled reduction)
+constexpr int kFoldRawAcc = 3;
 template <typename Op>
 __device__ __forceinline__ void red_store(typename Op::Out* out, typename Op::Out* out2, int64_t off, typename Op::Acc a,
                                           double count, int fold) {
   if constexpr (Op::kTwoOutputs) {
     Op::store2(out, out2, off, a, count);
   } else {
-    if (fold == kFoldRaw) {
-      reinterpret_cast<typename Op::Acc*>(out)[off] = a;
+    if (fold >= kFoldRaw) {
+      typename Op::Acc* r = reinterpret_cast<typename Op::Acc*>(out);
+      r[off] = fold == kFoldRawAcc ? Op::combine(r[off], a) : a;
       return;
     }
     if (fold) a = Op::combine(Op::from_out(out[off]), a);
@@ -1211,7 +1214,7 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
       if (plan.fused) *plan.fused = true;
     } else {
       out = reinterpret_cast<Out*>(plan.raw_out);
-      fold = kFoldRaw;
+      fold = plan.fold_out == kFoldRawAcc ? kFoldRawAcc : kFoldRaw;
     }
   };
 

@@ -54,6 +54,19 @@ class Comm:
         dist.broadcast_object_list(obj, src=0)
         return Comm(ctx, world, rank, obj[0])
 
+    @staticmethod
+    def local_group(ctx, nranks):
+        """`nranks` virtual ranks on ctx's device (hptb_comm_init_local_group): the exchange protocol without NCCL or
+        IPC, for single-GPU validation.  Give every rank its own stream."""
+        arr = (c_void_p * int(nranks))()
+        check(lib.hptb_comm_init_local_group(ctx.handle, int(nranks), arr))
+        out = []
+        for r in range(int(nranks)):
+            c = Comm.__new__(Comm)
+            c.ctx, c.world, c.rank, c.handle = ctx, int(nranks), r, c_void_p(arr[r])
+            out.append(c)
+        return out
+
     def destroy(self):
         if self.handle:
             lib.hptb_comm_destroy(self.handle)

@@ -213,10 +213,11 @@ hptb_status hptb_collapse(const hptb_tensor* const* operands, int n_operands, co
                           hptb_collapse_plan* plan);
 /* Host-side routing of a reduction (pure; no launch): how hptb_reduce will run it.  New functionality — the
  * reference's planner (reduce.rs:641-838) has neither case.  DIRECT: one kernel.  PEEL: rows start off the 16-byte
- * boundary with a common misalignment → head / aligned body / tail along the last axis, folded into `out`.
+ * boundary with a common misalignment → head / aligned body / tail along the last axis, folded into `out`
+ * (PEEL_RAW: into a scratch of accumulators finished by one more kernel — mean, logsumexp, reducel2/3, f16 / bf16).
  * TWO_STEP: the output's fastest dim is not the input's fastest kept dim → reduce into a scratch with
  * `scratch_strides` (input dim order), then gather into `out`. */
-typedef enum hptb_route_kind { HPTB_ROUTE_DIRECT = 0, HPTB_ROUTE_PEEL = 1, HPTB_ROUTE_TWO_STEP = 2 } hptb_route_kind;
+typedef enum hptb_route_kind { HPTB_ROUTE_DIRECT = 0, HPTB_ROUTE_PEEL = 1, HPTB_ROUTE_TWO_STEP = 2, HPTB_ROUTE_PEEL_RAW = 3 } hptb_route_kind;
 typedef struct hptb_reduce_route_t {
   int32_t kind;      /* hptb_route_kind */
   int32_t reserved;
@@ -282,6 +283,11 @@ hptb_status hptb_eye(hptb_ctx* ctx, hptb_tensor* out, int64_t k, void* stream);
 #define HPTB_NCCL_ID_BYTES 128
 hptb_status hptb_comm_unique_id(void* id128);                          /* rank 0, then broadcast out of band */
 hptb_status hptb_comm_init_rank(hptb_ctx* ctx, int nranks, int rank, const void* id128, hptb_comm** out);
+/* `nranks` VIRTUAL ranks on one device, no NCCL and no IPC: comms[r] behaves like rank r of an nranks-rank communicator
+ * whose mailboxes are plain allocations of ctx's device.  For tests and single-GPU validation of the exchange protocol
+ * (the kernels of one collective call spin on each other: give every virtual rank its own stream and keep the shards
+ * small enough for their kernels to be resident together).  At most 65536 outputs per call. */
+hptb_status hptb_comm_init_local_group(hptb_ctx* ctx, int nranks, hptb_comm** comms);
 hptb_status hptb_comm_destroy(hptb_comm* comm);
 /* 1 if accumulators are exchanged through peer-mapped mailboxes (CUDA IPC over NVLink, inside the reduce kernel),
  * 0 if every exchange goes through NCCL (IPC unavailable, or HPTB_NO_P2P=1 on any rank). */

@@ -299,10 +299,16 @@ def test_reduce_route_is_pure_host_logic():
     assert (kind, hbt) == ("peel", (1, 8096, 0))
     kind, hbt, _ = route("max", "i8", (300, 1030), (1040, 1), [1], (300,), (1,), ptr=0x10000 + 5)
     assert (kind, hbt) == ("peel", (11, 1008, 11))
-    # rows whose stride is not a multiple of a pack have no common misalignment; half types and non-folding ops do not peel
+    # rows whose stride is not a multiple of a pack have no common misalignment: no peeling
     assert route("sum", "f32", (7995, 8097), (8191, 1), [1], (7995,), (1,), ptr=0x10000 + 12)[0] == "direct"
-    assert route("sum", "bf16", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 6)[0] == "direct"
-    assert route("mean", "f32", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 12)[0] == "direct"
+    # half types (f32 accumulator, half output) and ops whose output is not their accumulator peel through a scratch of
+    # accumulators: bf16 base 6 bytes past a boundary → head (16 − 6) / 2 = 5 elements
+    kind, hbt, _ = route("sum", "bf16", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 6)
+    assert (kind, hbt) == ("peel_raw", (5, 8088, 4))
+    kind, hbt, _ = route("mean", "f32", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 12)
+    assert (kind, hbt) == ("peel_raw", (1, 8096, 0))
+    assert route("logsumexp", "f32", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 12)[0] == "peel_raw"
+    # arg reductions carry indices: not peeled
     assert route("argmax", "f32", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 12)[0] == "direct"
     assert route("sum", "f32", (7995, 8097), (8192, 1), [1], (7995,), (1,), ptr=0x10000 + 12, init_out=0)[0] == "direct"
     # x[256,512,512].permute(2,0,1).sum(2): view shape (512,256,512), strides (1,262144,512); out (512,256) contiguous.

@@ -224,3 +224,28 @@ def test_multi_run_outputs_match(hb):
     x = rand(rng, (3, 7, 1000), "f32")  # runs longer than one CTA pass, odd run counts
     _check(hb, "sum", x, "f32", [0, 2])
     _check(hb, "mean", x, "f32", [0, 2])
+
+
+def test_rows_off_the_pack_boundary_are_peeled(hb):
+    """a[5:R, 3:C].op(1): every row starts off the 16-byte boundary by the same amount → head / aligned body / tail.
+    Foldable ops on f32 / f64 / integers fold the pieces through `out` (PEEL); mean, logsumexp, reducel2/3 and the half
+    types combine them in a scratch of accumulators finished by one more kernel (PEEL_RAW).  Same bars as everywhere."""
+    rng = np.random.default_rng(27)
+    for d, shape, sl in (("f32", (700, 2100), (slice(5, 690), slice(3, 2090))), ("bf16", (600, 4200), (slice(2, 590), slice(5, 4190))),
+                         ("f16", (600, 4200), (slice(0, 600), slice(1, 4199))), ("i16", (500, 3000), (slice(1, 499), slice(3, 2999))),
+                         ("f64", (300, 3000), (slice(0, 300), slice(1, 2999)))):
+        x = rand(rng, shape, d)
+        view = lambda t: t[sl]  # noqa: E731
+        for op in ("sum", "mean", "max", "logsumexp", "reducel2", "sum_square", "prod"):
+            if d in O.INTS and op in ("logsumexp",):
+                continue
+            xs = x
+            if op == "prod":
+                xs = (np.sign(x) * (0.99 + 0.02 * np.abs(np.tanh(x)))).astype(x.dtype) if d in O.FLOATS else rand(rng, shape, d, -2, 2)
+                if d == "bf16":
+                    xs = O.round_bf16_from_f32(xs)
+            _check(hb, op, xs, d, [1], view=view)
+    # 3-D: the misaligned dim is the last of two reduced dims
+    x = rand(rng, (40, 50, 1030), "bf16")
+    _check(hb, "mean", x, "bf16", [1, 2], view=lambda t: t[:, 2:48, 3:1027])
+    _check(hb, "sum", x, "bf16", [2], view=lambda t: t[:, :, 1:1025])

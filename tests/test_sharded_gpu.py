@@ -42,3 +42,21 @@ def test_single_rank_comm_offsets_arg_indices():
     np.testing.assert_array_equal(got, x.argmax(axis=0) + 40)
     np.testing.assert_allclose(X.sum([0]).to_cpu().numpy(), x.sum(axis=0), rtol=1e-5, atol=1e-5)
     comm.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_exchange_protocol_with_virtual_ranks_on_one_gpu(world):
+    """The sharded reductions on ONE GPU: `world` virtual ranks (hptb_comm_init_local_group — mailboxes in the same device
+    memory, no NCCL, no IPC), one stream per rank, every rank's kernel of a call in flight at once.  Exercises exactly the
+    code the multi-GPU runs execute — the exchange fused into reduce_rows_kernel / reduce_cols_lean_kernel, the
+    standalone xchg_combine_kernel, index offsets, f32 exchange of half types — at the single-GPU bars, on the box the
+    driver has.  (Real NVLink traffic: tests/sharded_worker.py on ≥ 2 GPUs.)
+    Runs in a subprocess with CUDA_MODULE_LOADING=EAGER and a timeout: kernels of different streams wait for each other
+    here, and with lazy loading the FIRST launch of a kernel may synchronise the context — which a spinning peer kernel
+    would block for ever.  (One process per GPU, the real deployment, has no such coupling.)"""
+    env = dict(os.environ, CUDA_MODULE_LOADING="EAGER")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "virtual_ranks_worker.py"), str(world)], capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-3000:]
+    assert "virtual ranks ok" in r.stdout, r.stdout[-2000:]
