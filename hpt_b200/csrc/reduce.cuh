@@ -665,12 +665,18 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
     for (int w = 1; w < nw; ++w) a = Op::combine(a, s_part[w0 + w]);
   }
   if (p.S == 1) {
-    if (active && g == 0) {
-      if constexpr (!Op::kTwoOutputs) {
-        if (p.xchg.enabled) a = xchg_finish<Op>(p.xchg, out_off, a);  // host: only with G == kRedThreads
+    if constexpr (!Op::kTwoOutputs) {
+      if (p.xchg.enabled) {  // host: only with G == kRedThreads — one output per CTA, `active` is uniform
+        if (active && tid < 32) {
+          Acc t = s_part[0];
+          for (int w = 1; w < kRedThreads / 32; ++w) t = Op::combine(t, s_part[w]);
+          t = xchg_finish_warp<Op>(p.xchg, out_off, t);  // lane r ↔ rank r
+          if (tid == 0) red_store<Op>(out, out2, out_off, t, p.count, p.fold_out);
+        }
+        return;
       }
-      red_store<Op>(out, out2, out_off, a, p.count, p.fold_out);
     }
+    if (active && g == 0) red_store<Op>(out, out2, out_off, a, p.count, p.fold_out);
     return;
   }
   // split outputs (G == kRedThreads, one output per CTA): fixed-slot partials + last-CTA combine → deterministic
@@ -682,14 +688,14 @@ reduce_rows_kernel(const T* __restrict__ in, typename Op::Out* __restrict__ out,
     __syncthreads();
     if ((tid & 31) == 0) s_part[tid >> 5] = r;
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {  // every lane of warp 0 forms the CTA total (the same value): lane r then talks to rank r
       r = s_part[0];
       for (int w = 1; w < kRedThreads / 32; ++w) r = Op::combine(r, s_part[w]);
       // sharded: this rank's accumulator goes to every peer, the k accumulators are combined in rank order (xchg.cuh)
       if constexpr (!Op::kTwoOutputs) {
-        if (p.xchg.enabled) r = xchg_finish<Op>(p.xchg, out_off, r);
+        if (p.xchg.enabled) r = xchg_finish_warp<Op>(p.xchg, out_off, r);
       }
-      red_store<Op>(out, out2, out_off, r, p.count, p.fold_out);
+      if (tid == 0) red_store<Op>(out, out2, out_off, r, p.count, p.fold_out);
     }
   }
 }
@@ -951,22 +957,54 @@ constexpr int lean_cols_min_blocks() {
   return sizeof(typename Op::Local) > 8 ? 3 : (Op::kIndexed || sizeof(typename Op::Local) * VEC > 16) ? 4 : HPTB_LEAN_MINB;
 }
 
-// final write of a thread's VEC adjacent outputs; sharded: all VEC accumulators are pushed to the peers before the
-// first one is awaited, so the k·VEC remote entries are in flight together (xchg.cuh)
+// Final write of a column tile, called by the WHOLE finishing CTA after a barrier; sm row 0 ([j][tx]) holds the tile's
+// accumulators.  Sharded: thread row ty pushes the tile to rank ty and polls rank ty's entries — the k pushes and the k
+// polls are in flight together (xchg.cuh) — the polled accumulators meet in shared memory ([rank][j][tx]) and thread
+// row 0 combines them in rank order.
 template <typename Op, int VEC>
-__device__ __forceinline__ void lean_cols_finish(typename Op::Out* out, typename Op::Out* out2, int64_t off0,
-                                                 const typename Op::Acc* vals, int vstride, const LeanColsParams& p) {
+__device__ __forceinline__ void lean_cols_finish(typename Op::Out* out, typename Op::Out* out2, int64_t off0, typename Op::Acc* sm, bool col_ok,
+                                                 const LeanColsParams& p) {
+  typedef typename Op::Acc Acc;
+  constexpr int TX = 32, TY = kRedThreads / TX;
+  const uint32_t tx = threadIdx.x & (TX - 1), ty = threadIdx.x / TX;
   if constexpr (!Op::kTwoOutputs) {
     if (p.xchg.enabled) {
+      Acc mine[VEC], acc[VEC];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) xchg_push<Op>(p.xchg, off0 + j, vals[j * vstride]);
+      for (int j = 0; j < VEC; ++j) mine[j] = sm[j * TX + tx];
+      __syncthreads();  // row 0 has been read by everybody: the rows are free for the polled accumulators
+      for (int r0 = 0; r0 < p.xchg.nranks; r0 += TY) {
+        const int r = r0 + (int)ty;
+        if (r < p.xchg.nranks && col_ok) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, off0 + j, xchg_collect<Op>(p.xchg, off0 + j), p.count, p.fold_out);
+          for (int j = 0; j < VEC; ++j) xchg_push_to<Op>(p.xchg, r, off0 + j, mine[j]);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) sm[(ty * VEC + j) * TX + tx] = xchg_poll_from<Op>(p.xchg, r, off0 + j);
+        }
+        __syncthreads();
+        if (ty == 0 && col_ok) {
+          const int nr = p.xchg.nranks - r0 < TY ? p.xchg.nranks - r0 : TY;
+          for (int q = 0; q < nr; ++q) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+              const Acc pq = sm[(q * VEC + j) * TX + tx];
+              acc[j] = (r0 == 0 && q == 0) ? pq : Op::combine(acc[j], pq);
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (ty == 0 && col_ok) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, off0 + j, acc[j], p.count, p.fold_out);
+      }
       return;
     }
   }
+  if (ty == 0 && col_ok) {
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, off0 + j, vals[j * vstride], p.count, p.fold_out);
+    for (int j = 0; j < VEC; ++j) red_store<Op>(out, out2, off0 + j, sm[j * TX + tx], p.count, p.fold_out);
+  }
 }
 
 template <typename Op, typename T, int VEC>
@@ -1024,7 +1062,7 @@ reduce_cols_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__
     __syncthreads();
   }
   if (p.S == 1) {
-    if (ty == 0 && col_ok) lean_cols_finish<Op, VEC>(out, out2, out_off + col, sm + tx, TX, p);
+    lean_cols_finish<Op, VEC>(out, out2, out_off + col, sm, col_ok, p);
     return;
   }
   const uint32_t group = k * p.col_tiles + tile;
@@ -1054,7 +1092,7 @@ reduce_cols_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__
       }
       __syncthreads();
     }
-    if (ty == 0 && col_ok) lean_cols_finish<Op, VEC>(out, out2, out_off + col, sm + tx, TX, p);
+    lean_cols_finish<Op, VEC>(out, out2, out_off + col, sm, col_ok, p);
   }
 }
 

@@ -106,6 +106,75 @@ __device__ __forceinline__ typename Op::Acc xchg_finish(const XchgParams& x, int
   xchg_push<Op>(x, m, a);
   return xchg_collect<Op>(x, m);
 }
+
+// ---- the same spread over threads: one (destination / source) rank per thread -------------------------------------------
+// A single thread pushing to k mailboxes and then polling k entries one after the other pays k dependent round trips
+// through L2 (≈ 5 µs at 8 ranks for one output, ≈ 16 µs for the 4 × 8 entries a thread of the column kernel owned);
+// with one rank per lane / thread row the k stores and the k polls are in flight together.
+template <typename Op>
+__device__ __forceinline__ void xchg_push_to(const XchgParams& x, int dst_rank, int64_t m, typename Op::Acc a) {
+  typedef typename Op::Acc Acc;
+  constexpr int W = XchgWords<Acc>::n;
+  if constexpr (Op::kIndexed) a.idx += x.idx_offset;
+  uint32_t w[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) w[i] = 0;
+  memcpy(w, &a, sizeof(Acc));
+  unsigned char* dst = x.box[dst_rank] + xchg_entry_off<Acc>(x, x.rank, m);
+#pragma unroll
+  for (int i = 0; i < W; ++i) xchg_store(dst + 8 * i, w[i], x.seq);
+}
+template <typename Op>
+__device__ __forceinline__ typename Op::Acc xchg_poll_from(const XchgParams& x, int src_rank, int64_t m) {
+  typedef typename Op::Acc Acc;
+  constexpr int W = XchgWords<Acc>::n;
+  const unsigned char* src = x.box[x.rank] + xchg_entry_off<Acc>(x, src_rank, m);
+  uint32_t w[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    uint2 v;
+    do { v = xchg_load(src + 8 * i); } while (v.y != x.seq);
+    w[i] = v.x;
+  }
+  Acc part;
+  memcpy(&part, w, sizeof(Acc));
+  return part;
+}
+template <typename Acc>
+__device__ __forceinline__ Acc xchg_shfl(Acc v, int src_lane) {
+  constexpr int W = XchgWords<Acc>::n;
+  uint32_t w[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) w[i] = 0;
+  memcpy(w, &v, sizeof(Acc));
+#pragma unroll
+  for (int i = 0; i < W; ++i) w[i] = __shfl_sync(0xffffffffu, w[i], src_lane);
+  Acc o;
+  memcpy(&o, w, sizeof(Acc));
+  return o;
+}
+// ONE output, called by all 32 lanes of a warp with the same accumulator: lane r talks to rank r; every lane returns the
+// rank-ordered combination
+template <typename Op>
+__device__ __forceinline__ typename Op::Acc xchg_finish_warp(const XchgParams& x, int64_t m, typename Op::Acc a) {
+  typedef typename Op::Acc Acc;
+  const int lane = threadIdx.x & 31;
+  Acc acc = Op::identity();
+  for (int r0 = 0; r0 < x.nranks; r0 += 32) {  // nranks ≤ 16: one round
+    const int r = r0 + lane;
+    Acc part = Op::identity();
+    if (r < x.nranks) {
+      xchg_push_to<Op>(x, r, m, a);
+      part = xchg_poll_from<Op>(x, r, m);
+    }
+    const int nr = x.nranks - r0 < 32 ? x.nranks - r0 : 32;
+    for (int q = 0; q < nr; ++q) {
+      const Acc pq = xchg_shfl<Acc>(part, q);
+      acc = (r0 == 0 && q == 0) ? pq : Op::combine(acc, pq);
+    }
+  }
+  return acc;
+}
 #endif  // __CUDACC__
 
 }  // namespace hptb
