@@ -1015,7 +1015,9 @@ reduce_cols_lean_kernel(const T* __restrict__ in, typename Op::Out* __restrict__
   pdl_prologue();
   typedef typename Op::Acc Acc;
   typedef typename Op::Local Local;
-  constexpr int UNROLL = HPTB_RED_UNROLL;
+  // 8-byte (value, index) pairs run at 3 CTAs/SM (85 registers): twice the loads in flight per thread make up for the
+  // missing CTAs
+  constexpr int UNROLL = (Op::kIndexed && sizeof(Local) > 8 ? 2 : 1) * HPTB_RED_UNROLL;
   constexpr int TX = 32, TY = kRedThreads / TX, W = TX * VEC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Acc* sm = reinterpret_cast<Acc*>(smem_raw);  // [TY][VEC][TX]: lanes are adjacent, so 8- and 16-byte accumulators are conflict-free
@@ -1467,8 +1469,11 @@ hptb_status launch_reduce(const ReducePlan& plan, cudaStream_t stream) {
   // (bf16 NCHW channel mean, 512 outputs × 25088 chunks: S = 1 → 38 µs, S = 2 → 42 µs, S = 10 → 55 µs; the full
   // sum of 17 GB: 8 waves of CTAs → 7.3 TB/s).  Arg reductions carry a (value, index) pair through the cross-warp
   // combine and prefer G = 64 (transposed f32 [8192,8192] argmax: G = 64 → 41.4 µs, G = 256 → 46.6 µs).
+  // (value, index) pairs pay 16-byte shuffles per combine step: half the lanes per output, twice the batches per thread
+  // (f32 [256,512,512] argmax(2): G = 32 → 59.2 µs, G = 8 → 38.2 µs; [65536,1024]: 59.9 → 35.7 µs; tools/g_sweep.py)
+  const int64_t min_batches = Op::kIndexed ? 8 : 2;
   int64_t G = 1;
-  while (G < kRedThreads && G * 2 * HPTB_RED_UNROLL <= p.chunks) G <<= 1;
+  while (G < kRedThreads && G * min_batches * HPTB_RED_UNROLL <= p.chunks) G <<= 1;
   int64_t S = 1;
   if (G == kRedThreads && M < cta_slots) {
     S = (8 * cta_slots + M - 1) / M;
