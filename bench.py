@@ -321,8 +321,15 @@ def run_ours(args):
     e2e_rows = rows_local
     if avail and shard_bytes * world + (8 << 30) > avail:  # all ranks pin their shard on this host
         e2e_rows = max(1024, int((avail - (8 << 30)) / world / (COLS * 4)) // 1024 * 1024)
+    host_x = None
+    while host_x is None:
+        try:
+            host_x = torch.empty((e2e_rows, COLS), dtype=torch.float32, pin_memory=True)
+        except RuntimeError:  # the box cannot pin that much: halve the sample
+            if e2e_rows <= 1024:
+                raise
+            e2e_rows = max(1024, e2e_rows // 2 // 1024 * 1024)
     e2e_note = None if e2e_rows == rows_local else f"host memory holds only {e2e_rows} of {rows_local} rows per rank; value scaled to the sample"
-    host_x = torch.empty((e2e_rows, COLS), dtype=torch.float32, pin_memory=True)
     host_x.copy_(big[:e2e_rows])  # synthetic input placed in host memory once, outside the timed region
     torch.cuda.synchronize()
     pinned_out = [torch.empty((1,), dtype=torch.float32, pin_memory=True), torch.empty((1,), dtype=torch.float32, pin_memory=True),
