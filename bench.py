@@ -43,7 +43,7 @@ CONFIG = {
              "exchanged over NVLink peer memory inside the reduce kernel's epilogue (NCCL all-gather fallback)",
     "l2": "every pass streams 17.18/N GB (>= 2.1 GB), far above the 126 MB L2: no flush needed",
 }
-CPU_SAMPLE_ROWS_REF = 8192      # --impl reference: [8192,16384] f32 = 512 MB per pass
+CPU_SAMPLE_ROWS_REF = 32768     # --impl reference: [32768,16384] f32 = 2.1 GB per pass (well beyond any last-level cache)
 CPU_SAMPLE_ROWS_BASE = 32768    # cpu_baseline of our arm: [32768,16384] = 2.1 GB per pass (an 8-GPU shard)
 
 
@@ -167,7 +167,7 @@ def run_reference(args):
             "steps": steps, "warmup": warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
             "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": "port",
-                             "sample": f"rows [0,{CPU_SAMPLE_ROWS_REF}) of the tensor ([{CPU_SAMPLE_ROWS_REF},16384] f32, 512 MB per pass), "
+                             "sample": f"rows [0,{CPU_SAMPLE_ROWS_REF}) of the tensor ([{CPU_SAMPLE_ROWS_REF},16384] f32, 2.1 GB per pass), "
                                        f"{steps} timed steps of sum(), mean(), sum(axis 0) by the C++/OpenMP restatement of Hpt's CPU path "
                                        "(oracle/oracle_cpu.cpp); Hpt's Rust CPU path cannot be built here"},
             "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
