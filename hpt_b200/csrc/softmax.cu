@@ -672,6 +672,7 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
         q.cl = cl;
         q.log = log;
         q.use64 = p.use64;
+        // enough bands for ≥ 4 rounds per resident cluster: the persistent, double-buffered kernel (one 1024-thread CTA per SM)
         const size_t smem = (size_t)q.per_cta * 128;
         auto kern = softmax_band_cols<T, VECMAX>;
         static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);

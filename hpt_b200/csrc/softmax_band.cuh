@@ -225,3 +225,10 @@ __global__ void __launch_bounds__(kSmThreads) softmax_band_cols(const T* __restr
     store_pack<T, VEC>(dst + (int64_t)e * p.sa_out, o);
   }
 }
+
+// Tried and dropped (profiles/r02r_band_pipe.txt): a persistent variant — ONE 1024-thread CTA per SM, two shared-memory
+// buffers, the cp.async copies of band i+1 in flight while band i goes through max / exp / store, grid sized by
+// cudaOccupancyMaxActiveClusters (a cluster of 8 lives inside one GPC: 16 clusters are co-resident, not 18).  f32
+// [4096,8192] axis 0: 123.5 µs against 78.7 µs for the kernel above (181 µs with 18 clusters launched = two waves);
+// [2048,16384]: 110.9 vs 70.4 µs.  One CTA per SM cannot hide its own barriers (two cluster syncs + six CTA barriers per
+// band), whatever is in flight behind them.
