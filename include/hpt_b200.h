@@ -299,7 +299,9 @@ int hptb_comm_uses_peer_memory(const hptb_comm* comm);
  * the shard axis, which collective combines the per-rank partials and which post-op follows. */
 typedef enum hptb_collective {
   HPTB_COLL_NONE = 0,           /* the reduced axes do not include the shard axis: purely local */
-  HPTB_COLL_ALLREDUCE_SUM = 1,  /* sum, sum_square; mean (local Σ ÷ GLOBAL count); logsumexp (on exp of the local value) */
+  /* how the k per-rank ACCUMULATORS combine (always in rank order, on every rank; mathematically the named all-reduce): */
+  HPTB_COLL_ALLREDUCE_SUM = 1,  /* sum, sum_square, reducel1, nansum; mean (Σ, then ÷ GLOBAL count); logsumexp (Σexp, then ln);
+                                   reducel2/3 (Σ|x|^p, then the root) */
   HPTB_COLL_ALLREDUCE_PROD = 2,
   HPTB_COLL_ALLREDUCE_MAX = 3,
   HPTB_COLL_ALLREDUCE_MIN = 4,
@@ -308,10 +310,10 @@ typedef enum hptb_collective {
 typedef struct hptb_shard_plan {
   int32_t crosses;      /* 1 if shard_axis is among the reduced axes */
   int32_t collective;   /* hptb_collective */
-  int32_t pre_exp;      /* 1: exp() the local result before the collective (logsumexp) */
-  int32_t post_ln;      /* 1: ln() after the collective (logsumexp) */
-  int32_t global_count; /* 1: the local op divides by the GLOBAL element count (mean) */
-  int32_t post_root;    /* p = 2 or 3: the local op leaves Σ|x|^p unrooted, the p-th root follows the collective (reducel2/3) */
+  int32_t pre_exp;      /* 1: the accumulator is Σ exp(x) (logsumexp) */
+  int32_t post_ln;      /* 1: ln() after the combine (logsumexp) */
+  int32_t global_count; /* 1: the post step divides by the GLOBAL element count (mean) */
+  int32_t post_root;    /* p = 2 or 3: the accumulator is Σ|x|^p, the p-th root follows the combine (reducel2/3) */
 } hptb_shard_plan;
 hptb_status hptb_shard_bounds(int64_t n, int world, int rank, int64_t* offset, int64_t* len);
 hptb_status hptb_shard_plan_reduce(int op, const int32_t* axes, int naxes, int shard_axis, int world,
