@@ -3,8 +3,10 @@
 New functionality: the reference has no multi-GPU support (its device is a const generic, hpt/src/tensor.rs:32, and
 there are no collectives).  One process per GPU; a `ShardedTensor` is this rank's row block of a tensor split along
 one axis (k `Tensor<T, Cuda, i>` in Hpt terms).  Elementwise ops and reductions that keep the shard axis are purely
-local; a reduction that crosses it reduces locally and exchanges one small partial per rank through NCCL inside
-`hptb_reduce_sharded` (comm.cpp).  torch.distributed is only the out-of-band channel for the NCCL unique id.
+local; a reduction that crosses it reduces locally to one ACCUMULATOR per output and the k accumulators are combined in
+rank order inside `hptb_reduce_sharded` — over NVLink peer memory, in the reduce kernel's own epilogue (xchg.cuh), or
+over ncclAllGather when peer memory is unavailable (comm.cpp).  torch.distributed is only the out-of-band channel for the
+NCCL unique id.
 """
 from ctypes import byref, c_char_p, c_int, c_int32, c_int64, c_void_p, create_string_buffer
 
