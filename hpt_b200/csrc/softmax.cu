@@ -17,6 +17,7 @@
 //   softmax_cols         axis is strided and another dim is contiguous: one thread per output column,
 //                        lanes along the contiguous dim (coalesced), online pass + write pass.
 #include <cooperative_groups.h>
+#include <array>
 
 #include <algorithm>
 #include "context.h"
@@ -190,48 +191,96 @@ __device__ __forceinline__ void ms_push(MS<C>& a, C x) {
   else a.s += x;  // NaN element: poison the row as exp(NaN) would
 }
 
-// ---- exact-rescale online statistics (f32 compute type) -----------------------------------------------------------
-// The vectorised streaming kernels keep, instead of (max, Σ exp(x − max)), the pair (K, Σ 2^(x·log2e − K)) with K an
-// INTEGER: the smallest one ≥ every x·log2e seen so far.  Moving the reference from K to K' multiplies Σ by
-// 2^(K − K') — a pure exponent shift, exact — so however often the running maximum moves, and however many partial
-// pairs are merged (threads, warps, CTAs, axis splits), Σ carries only the rounding of its additions.
-// A term never forms x − max either: y = x·log2e is carried as hi + lo (≈ 2^-48 relative), split as n + f with
-// n = rint(hi), and 2^(y − K) = 2^f · 2^(n − K) — ex2 of a fraction, then an exponent shift.  Its error is that of
-// ex2 (≤ 2 ulp) whatever the distance to the maximum; exp(x − max) in f32 loses |x − max|/2 ulp to the subtraction.
-constexpr float kLog2eHi = 1.4426950216293335f, kLog2eLo = 1.9259629911266175e-8f;
+// ---- streaming statistics with a power-of-two frame (f32 compute type) --------------------------------------------------
+// The vectorised streaming kernels keep, instead of (max, Σ exp(x − max)), a pair (K, T): K an INTEGER no smaller than
+// any x·log2e seen so far, T = Σ exp(x) · 2^-K.  Moving from K to K' multiplies T by 2^(K − K') — an exponent shift,
+// exact — so however often the running maximum moves, and however many partial pairs are merged (threads, warps, CTAs,
+// axis splits), T carries only the rounding of its additions.
+// Terms are formed in the x domain, against the float r_K = fl(K·ln2): exp(x − r_K) is the register kernel's term — one
+// rounded subtraction, compensated ex2, 8 instructions — and differs from exp(x)·2^-K by the constant
+// c_K = exp(r_K − K·ln2), 1 to within the rounding of r_K, which is applied ONCE per stretch of equal K (a thread's raw sum S joins T as fma(S, c_K, T)), not per element.  Round 2 first
+// shipped terms formed in the log2 domain (2^f · 2^(n − K) with n = rint(x·log2e)): exact whatever the distance to the
+// maximum, but 15–24 instructions per element including three conversion-pipe slots, which left f32 AND bf16
+// [4096,8192] axis 0 at 97 µs (XU-bound), 86 µs with the conversions replaced by magic-number adds (issue-bound).
+constexpr float kLog2eHi = 1.4426950216293335f;
 constexpr float kLn2Hi = 0.693145751953125f, kLn2Lo = 1.42860682030941723212e-6f;  // ln2 = hi + lo, hi with 9 trailing zero bits
 __device__ __forceinline__ float sm_exp2i(float d) {  // 2^d for an integer-valued d ≤ 0 (−inf → 0)
   return d < -126.0f ? 0.0f : __int_as_float((127 + (int)d) << 23);
 }
-__device__ __forceinline__ float sm_term(float x, float K) {  // 2^(x·log2e − K) for x·log2e ≤ K; −inf → 0, NaN → NaN
-  const float hi = x * kLog2eHi;
-  const float lo = fmaf(x, kLog2eLo, fmaf(x, kLog2eHi, -hi));
-  const float n = rintf(hi);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((hi - n) + lo));  // hi − n is exact
-  const float r = e * sm_exp2i(n - K);
-  return x < -3.3e38f ? 0.0f : r;  // −inf: hi − n and lo are NaN
+// r_K = fl(K·ln2), ln c_K = r_K − K·ln2 (a rounding residue: ≤ ulp(r_K)/2), and c_K itself — a cubic while |ln c_K| < 2^-6
+// (remainder < 2^-28).  __fmul_rn: the product must not be contracted into a neighbouring add, every user of r_K has
+// to see the same float.
+__device__ __forceinline__ float sm_ref(float K) { return fmaf(K, kLn2Lo, __fmul_rn(K, kLn2Hi)); }
+__device__ __forceinline__ float sm_frame_ln(float K) {
+  const float p = __fmul_rn(K, kLn2Hi);
+  const float r = fmaf(K, kLn2Lo, p);
+  const float e1 = fmaf(K, kLn2Hi, -p);  // K·ln2_hi − p, exact
+  return fmaf(-K, kLn2Lo, r - p) - e1;   // r − p is exact
 }
-__device__ __forceinline__ double sm_term(double x, double m) { return exp(x - m); }
-// a.m holds K (f32) / the running maximum (f64: the inexact-rescale form, kept for the 64-bit types)
-__device__ __forceinline__ void ms_push_fast(MS<float>& a, float x) {
-  const float y = x * kLog2eHi;
-  if (y > a.m) {  // false for NaN and for −inf against the initial −inf
-    const float K = ceilf(y);
-    if (K > a.m) {  // +inf input: K = +inf, the terms become NaN as exp(inf − inf) does
-      a.s *= sm_exp2i(a.m - K);  // a.m = −inf initially: a.s is 0 anyway
-      a.m = K;
-    }
+__device__ __forceinline__ float sm_frame(float K) {
+  const float z = sm_frame_ln(K);
+  if (fabsf(z) < 0.015625f) return fmaf(z, fmaf(z, fmaf(z, 1.0f / 6.0f, 0.5f), 1.0f), 1.0f);
+  return fast_expf(z);
+}
+// a thread's running statistics of one softmax lane
+template <typename C> struct SmRun;
+template <> struct SmRun<float> {
+  float K, r, T, S, comp;  // frame, its reference r_K, the sum in frame units, the raw sum of the current stretch (+ its lost bits)
+  __device__ __forceinline__ void init() { K = Limits<float>::lowest(); r = 0.0f; T = 0.0f; S = 0.0f; comp = 0.0f; }
+  __device__ __forceinline__ void close() {
+    if (S != 0.0f) T = fmaf(S, sm_frame(K), T);  // also when S is NaN
+    S = 0.0f;
+    comp = 0.0f;
   }
-  if (x > Limits<float>::lowest() || x != x) a.s += sm_term(x, a.m);  // −inf contributes nothing (and K may still be −inf)
-}
+  // N values at once: ONE frame update for the block (its maximum decides), then N plain terms
+  template <int N>
+  __device__ __forceinline__ void push(const float (&x)[N]) {
+    float bm = x[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) bm = fmaxf(bm, x[i]);  // NaNs drop out here and poison S through their term
+    const float y = bm * kLog2eHi;
+    if (y > K) {  // false for NaN and for −inf against the initial −inf; K is an integer, so ceil(y) > K
+      const float Kn = ceilf(y);  // +inf input: K = r = +inf, every term NaN or 0 as exp(x − inf) is
+      close();
+      T *= sm_exp2i(K - Kn);
+      K = Kn;
+      r = sm_ref(Kn);
+    }
+    // A thread adds a hundred or more terms to S, most of them far below the largest: added one by one, terms under
+    // half an ulp of S vanish — a one-sided loss, measured at 3–6 · 2^-24 of the lane's Σ on N(0, 4²) columns of 4096.
+    // The block is summed on its own first (pairwise), and its sum joins S with the rounding error carried along.
+    float t[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = fast_expf(x[i] - r);  // −inf → 0 (r = 0 until the first finite value)
+#pragma unroll
+    for (int w = 1; w < N; w <<= 1)
+#pragma unroll
+      for (int i = 0; i + w < N; i += 2 * w) t[i] += t[i + w];
+    const float v = t[0] - comp, s2 = S + v;
+    comp = (s2 - S) - v;
+    S = s2;
+  }
+  __device__ __forceinline__ MS<float> done() { close(); return MS<float>{K, T}; }
+};
+// 64-bit compute type: the plain online pair
 __device__ __forceinline__ void ms_push_fast(MS<double>& a, double x) {
   if (a.s == 0.0) { a.m = x; a.s = 1.0; return; }
   if (x <= a.m) a.s += exp(x - a.m);
   else if (x > a.m) { a.s = a.s * exp(a.m - x) + 1.0; a.m = x; }
   else a.s += x;
 }
-// merge two (K, Σ) pairs: exact scalings, one rounded addition
+template <> struct SmRun<double> {
+  MS<double> a;
+  __device__ __forceinline__ void init() { a = MS<double>{Limits<double>::lowest(), 0.0}; }
+  template <int N>
+  __device__ __forceinline__ void push(const double (&x)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (x[i] > Limits<double>::lowest() || x[i] != x[i]) ms_push_fast(a, x[i]);  // −inf (a real one or tail padding) adds nothing
+  }
+  __device__ __forceinline__ MS<double> done() { return a; }
+};
+// merge two (K, T) pairs: exact scalings, one rounded addition
 __device__ __forceinline__ MS<float> ms_merge_fast(MS<float> a, MS<float> b) {
   if (a.s == 0.0f) return b;
   if (b.s == 0.0f) return a;
@@ -239,14 +288,32 @@ __device__ __forceinline__ MS<float> ms_merge_fast(MS<float> a, MS<float> b) {
   return MS<float>{K, a.s * sm_exp2i(a.m - K) + b.s * sm_exp2i(b.m - K)};
 }
 __device__ __forceinline__ MS<double> ms_merge_fast(MS<double> a, MS<double> b) { return ms_combine<double>(a, b); }
-// the row's normalised output from its (K, Σ): softmax = 2^(x·log2e − K) / Σ; log_softmax = (x − K·ln2) − ln Σ with
-// K·ln2_hi exact (|K| < 2^9, ln2_hi has 9 trailing zero bits) so that the subtraction cancels without loss
+// a RUN of merges into one accumulator (a row's warps, a column's axis splits): typically one partial holds the maximum
+// and the others arrive one at a time at half an ulp of it or less, where plain additions round the same way every
+// time (f32 [6144,96] axis 0 in 24 splits: Σ low by 5 · 2^-24).  TwoSum keeps what each addition drops; ms_run_done
+// folds it back.
+__device__ __forceinline__ void ms_run_add(MS<float>& a, float& comp, MS<float> b) {
+  if (b.s == 0.0f) return;
+  if (a.s == 0.0f) { a = b; comp = 0.0f; return; }
+  const float K = fmaxf(a.m, b.m);
+  const float fa = sm_exp2i(a.m - K), sa = a.s * fa, sb = b.s * sm_exp2i(b.m - K);
+  const float t = sa + sb, bb = t - sa;
+  comp = comp * fa + ((sa - (t - bb)) + (sb - bb));
+  a = MS<float>{K, t};
+}
+__device__ __forceinline__ void ms_run_done(MS<float>& a, float comp) { a.s += comp; }
+__device__ __forceinline__ void ms_run_add(MS<double>& a, double&, MS<double> b) { a = ms_combine<double>(a, b); }
+__device__ __forceinline__ void ms_run_done(MS<double>&, double) {}
+// the lane's normalised output from its (K, T): softmax = exp(x − r_K) · c_K / T, log_softmax = (x − r_K) − (ln T − ln c_K)
 struct SmFinal {
-  float K, inv, lgK;
+  float r, q, lgq;
 };
-__device__ __forceinline__ SmFinal sm_final(MS<float> r) { return SmFinal{r.m, 1.0f / r.s, fmaf(r.m, kLn2Lo, logf(r.s))}; }
+__device__ __forceinline__ SmFinal sm_final(MS<float> a) {
+  return SmFinal{sm_ref(a.m), sm_frame(a.m) / a.s, logf(a.s) - sm_frame_ln(a.m)};
+}
 __device__ __forceinline__ float sm_out(float x, const SmFinal& f, int log) {
-  return log ? fmaf(-f.K, kLn2Hi, x) - f.lgK : sm_term(x, f.K) * f.inv;
+  const float sh = x - f.r;
+  return log ? sh - f.lgq : fast_expf(sh) * f.q;
 }
 struct SmFinalD {
   double m, inv, lg;
@@ -349,19 +416,29 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
     walk2(row, p.kept, p.use64, in_off, out_off);
     const T* src = in + in_off;
     O* dst = out + out_off;
-    MS<C> a{Limits<C>::lowest(), (C)0};
-    for (int64_t c = tid; c < packs; c += (int64_t)NT * UN) {
+    SmRun<C> run;
+    run.init();
+    int64_t c = tid;
+    for (; c + (int64_t)(UN - 1) * NT < packs; c += (int64_t)NT * UN) {  // whole batches: no predicates
       Pack<T, VEC> v[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u)
-        if (c + (int64_t)u * NT < packs) load_pack<T, VEC>(v[u], src + (c + (int64_t)u * NT) * VEC);
+      for (int u = 0; u < UN; ++u) load_pack<T, VEC>(v[u], src + (c + (int64_t)u * NT) * VEC);
+      C xs[UN * VEC];
 #pragma unroll
       for (int u = 0; u < UN; ++u)
-        if (c + (int64_t)u * NT < packs) {
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) ms_push_fast(a, to_compute<O>(cast<O>(v[u].v[k])));
-        }
+        for (int k = 0; k < VEC; ++k) xs[u * VEC + k] = to_compute<O>(cast<O>(v[u].v[k]));
+      run.push(xs);
     }
+    for (; c < packs; c += NT) {  // ragged tail, a pack at a time
+      Pack<T, VEC> v;
+      load_pack<T, VEC>(v, src + c * VEC);
+      C xs[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) xs[k] = to_compute<O>(cast<O>(v.v[k]));
+      run.push(xs);
+    }
+    MS<C> a = run.done();
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       MS<C> b{shfl_xor<C>(a.m, off), shfl_xor<C>(a.s, off)};
@@ -371,21 +448,30 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
     if ((tid & 31) == 0) { s_m[tid >> 5] = a.m; s_s[tid >> 5] = a.s; }
     __syncthreads();
     MS<C> r{Limits<C>::lowest(), (C)0};
-    for (int w = 0; w < NT / 32; ++w) r = ms_merge_fast(r, MS<C>{s_m[w], s_s[w]});
+    C rcomp = (C)0;
+    for (int w = 0; w < NT / 32; ++w) ms_run_add(r, rcomp, MS<C>{s_m[w], s_s[w]});
+    ms_run_done(r, rcomp);
     const auto fin = sm_final(r);
-    for (int64_t c = tid; c < packs; c += (int64_t)NT * UN) {
+    c = tid;
+    for (; c + (int64_t)(UN - 1) * NT < packs; c += (int64_t)NT * UN) {
       Pack<T, VEC> v[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u)
-        if (c + (int64_t)u * NT < packs) load_pack_cached<T, VEC>(v[u], src + (c + (int64_t)u * NT) * VEC);
+      for (int u = 0; u < UN; ++u) load_pack_cached<T, VEC>(v[u], src + (c + (int64_t)u * NT) * VEC);
 #pragma unroll
-      for (int u = 0; u < UN; ++u)
-        if (c + (int64_t)u * NT < packs) {
-          Pack<O, VEC> o;
+      for (int u = 0; u < UN; ++u) {
+        Pack<O, VEC> o;
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v[u].v[k])), fin, p.log));
-          store_pack<O, VEC>(dst + (c + (int64_t)u * NT) * VEC, o);
-        }
+        for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v[u].v[k])), fin, p.log));
+        store_pack<O, VEC>(dst + (c + (int64_t)u * NT) * VEC, o);
+      }
+    }
+    for (; c < packs; c += NT) {
+      Pack<T, VEC> v;
+      load_pack_cached<T, VEC>(v, src + c * VEC);
+      Pack<O, VEC> o;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v.v[k])), fin, p.log));
+      store_pack<O, VEC>(dst + c * VEC, o);
     }
   }
 }
@@ -408,10 +494,12 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
   constexpr int TY = kSmThreads / TX, W = TX * VEC, UN = 4;
   __shared__ C s_m[PHASE == 2 ? 1 : TY][W], s_s[PHASE == 2 ? 1 : TY][W];
   const int lane = threadIdx.x % TX, ty = threadIdx.x / TX;
-  const int64_t e_begin = (int64_t)blockIdx.y * p.rps;
+  // PHASE 2 walks the grid backwards: the slabs PHASE 1 read last are still in L2
+  const unsigned bx = PHASE == 2 ? gridDim.x - 1 - blockIdx.x : blockIdx.x, by = PHASE == 2 ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int64_t e_begin = (int64_t)by * p.rps;
   const int64_t e_end = e_begin + p.rps < p.L ? e_begin + p.rps : p.L;
   const int64_t ncols = (int64_t)gridDim.x * W;  // row length of the `part` arrays (padded to whole tiles)
-  const int64_t outer = (int64_t)blockIdx.x / p.ctiles, tile = (int64_t)blockIdx.x - outer * p.ctiles;
+  const int64_t outer = (int64_t)bx / p.ctiles, tile = (int64_t)bx - outer * p.ctiles;
   const int64_t col0 = tile * W + (int64_t)lane * VEC;
   int64_t in_off = 0, out_off = 0;
   if (p.outer.n > 0) walk2(outer, p.outer, p.use64, in_off, out_off);
@@ -422,20 +510,39 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
 #pragma unroll
   for (int k = 0; k < VEC; ++k) a[k] = MS<C>{Limits<C>::lowest(), (C)0};
   if constexpr (PHASE != 2) {
+    SmRun<C> run[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) run[k].init();
     if (active) {
-      for (int64_t e = e_begin + ty; e < e_end; e += (int64_t)TY * UN) {
-        Pack<T, VEC> v[UN];
+      // rows per batch of the statistics sweep = 16-byte loads in flight per thread.  f32: 8 rows need 76 registers (three
+      // CTAs per SM) and measured 85 µs on [4096,8192] against 80 µs for 4 rows at 63 registers; bf16 (8 lanes per pack)
+      // is at two CTAs per SM either way and prefers 8 rows (64 vs 79 µs)
+      constexpr int US = VEC > 4 ? 8 : 4;
+      int64_t e = e_begin + ty;
+      for (; e + (int64_t)(US - 1) * TY < e_end; e += (int64_t)TY * US) {  // whole batches: no predicates
+        Pack<T, VEC> v[US];
 #pragma unroll
-        for (int u = 0; u < UN; ++u)
-          if (e + (int64_t)u * TY < e_end) load_pack<T, VEC>(v[u], src + (e + (int64_t)u * TY) * p.sa_in);
+        for (int u = 0; u < US; ++u) load_pack<T, VEC>(v[u], src + (e + (int64_t)u * TY) * p.sa_in);
 #pragma unroll
-        for (int u = 0; u < UN; ++u)
-          if (e + (int64_t)u * TY < e_end) {
+        for (int k = 0; k < VEC; ++k) {
+          C xs[US];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) ms_push_fast(a[k], to_compute<O>(cast<O>(v[u].v[k])));
-          }
+          for (int u = 0; u < US; ++u) xs[u] = to_compute<O>(cast<O>(v[u].v[k]));
+          run[k].push(xs);
+        }
+      }
+      for (; e < e_end; e += TY) {  // ragged tail, a row at a time
+        Pack<T, VEC> v;
+        load_pack<T, VEC>(v, src + e * p.sa_in);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          C xs[1] = {to_compute<O>(cast<O>(v.v[k]))};
+          run[k].push(xs);
+        }
       }
     }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) a[k] = run[k].done();
 #pragma unroll
     for (int k = 0; k < VEC; ++k) { s_m[ty][lane * VEC + k] = a[k].m; s_s[ty][lane * VEC + k] = a[k].s; }
     __syncthreads();
@@ -453,7 +560,7 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
     }
     if constexpr (PHASE == 1) {  // one pair per (split, column)
       if (ty == 0) {
-        C* pm = part + ((int64_t)blockIdx.y * 2) * ncols + (int64_t)blockIdx.x * W + lane * VEC;
+        C* pm = part + ((int64_t)by * 2) * ncols + (int64_t)bx * W + lane * VEC;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) { pm[k] = a[k].m; pm[ncols + k] = a[k].s; }
       }
@@ -462,13 +569,16 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
   } else {
     // merge the column's per-split pairs in split order; every thread row needs them, thread row 0 fetches
     if (ty == 0) {
+      C acomp[VEC];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) a[k] = MS<C>{Limits<C>::lowest(), (C)0};
+      for (int k = 0; k < VEC; ++k) { a[k] = MS<C>{Limits<C>::lowest(), (C)0}; acomp[k] = (C)0; }
       for (int sp = 0; sp < (int)gridDim.y; ++sp) {
-        const C* pm = part + ((int64_t)sp * 2) * ncols + (int64_t)blockIdx.x * W + lane * VEC;
+        const C* pm = part + ((int64_t)sp * 2) * ncols + (int64_t)bx * W + lane * VEC;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) a[k] = ms_merge_fast(a[k], MS<C>{pm[k], pm[ncols + k]});
+        for (int k = 0; k < VEC; ++k) ms_run_add(a[k], acomp[k], MS<C>{pm[k], pm[ncols + k]});
       }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) ms_run_done(a[k], acomp[k]);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) { s_m[0][lane * VEC + k] = a[k].m; s_s[0][lane * VEC + k] = a[k].s; }
     }
@@ -478,19 +588,26 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
   decltype(sm_final(MS<C>{})) fin[VEC];  // one division per column; the per-element multiply adds ≤ 0.5 ulp
 #pragma unroll
   for (int k = 0; k < VEC; ++k) fin[k] = sm_final(MS<C>{s_m[0][lane * VEC + k], s_s[0][lane * VEC + k]});
-  for (int64_t e = e_begin + ty; e < e_end; e += (int64_t)TY * UN) {
+  int64_t e = e_begin + ty;
+  for (; e + (int64_t)(UN - 1) * TY < e_end; e += (int64_t)TY * UN) {
     Pack<T, VEC> v[UN];
 #pragma unroll
-    for (int u = 0; u < UN; ++u)
-      if (e + (int64_t)u * TY < e_end) load_pack<T, VEC>(v[u], src + (e + (int64_t)u * TY) * p.sa_in);
+    for (int u = 0; u < UN; ++u) load_pack<T, VEC>(v[u], src + (e + (int64_t)u * TY) * p.sa_in);
 #pragma unroll
-    for (int u = 0; u < UN; ++u)
-      if (e + (int64_t)u * TY < e_end) {
-        Pack<O, VEC> o;
+    for (int u = 0; u < UN; ++u) {
+      Pack<O, VEC> o;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v[u].v[k])), fin[k], p.log));
-        store_pack<O, VEC>(dst + (e + (int64_t)u * TY) * p.sa_out, o);
-      }
+      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v[u].v[k])), fin[k], p.log));
+      store_pack<O, VEC>(dst + (e + (int64_t)u * TY) * p.sa_out, o);
+    }
+  }
+  for (; e < e_end; e += TY) {
+    Pack<T, VEC> v;
+    load_pack<T, VEC>(v, src + e * p.sa_in);
+    Pack<O, VEC> o;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v.v[k])), fin[k], p.log));
+    store_pack<O, VEC>(dst + e * p.sa_out, o);
   }
 }
 
@@ -509,9 +626,12 @@ inline int band_cluster(int64_t band_bytes, int64_t nbands, int sms, int64_t min
   while (cl < kBandMaxCl && nbands * cl < (int64_t)sms * 3 && band_bytes / (cl * 2) >= min_bytes) cl <<= 1;
   return cl;
 }
-inline bool band_disabled() {
+inline bool band_tune_on() {
   static const bool on = [] { const char* e = getenv("HPTB_TUNE"); return e && e[0] == '1'; }();
-  if (!on) return false;
+  return on;
+}
+inline bool band_disabled() {
+  if (!band_tune_on()) return false;
   const char* e = getenv("HPTB_TUNE_NO_BAND");
   return e && e[0] == '1';
 }
@@ -685,16 +805,37 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
     // 32 lanes per row segment unless that leaves the GPU short of CTAs and 8 lanes still fill whole sectors
     int tx = 32;
     if (outer_n * ((p.C + 32 * vec - 1) / (32 * vec)) < (int64_t)ctx->sm_count * 2 && vec > 1) tx = 8;
+    if (band_tune_on() && vec > 1) {
+      if (const char* e = getenv("HPTB_TUNE_SMC_TX")) tx = atoi(e) == 8 ? 8 : 32;
+    }
     p.ctiles = (p.C + (int64_t)tx * vec - 1) / ((int64_t)tx * vec);
     const int64_t blocks = outer_n * p.ctiles;
     if (blocks > 0x7fffffffLL) return fail(HPTB_ERR_UNSUPPORTED, "softmax: grid too large");
-    // splits of the axis: up to ≈ 8 CTAs per SM in total, each thread row keeping ≥ 2 batches of loads
+    // splits of the axis: ONE wave of resident CTAs (f32 [4096,8192]: 256 column tiles × 2 splits 75 µs, × 5 splits —
+    // 2.2 waves — 87 µs), each thread row keeping ≥ 2 batches of loads
     const int ty = kSmThreads / tx;
-    int64_t S = ((int64_t)ctx->sm_count * 8 + blocks - 1) / blocks;
+    static const std::array<int, 3> occs = [] {  // resident CTAs per SM of the three statistics kernels
+      const void* ks[3] = {(const void*)softmax_cols_tiled<T, 1, 32, 1>, (const void*)softmax_cols_tiled<T, VECMAX, 8, 1>,
+                           (const void*)softmax_cols_tiled<T, VECMAX, 32, 1>};
+      std::array<int, 3> o{};
+      for (int i = 0; i < 3; ++i)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[i], ks[i], kSmThreads, 0) != cudaSuccess || o[i] < 1) o[i] = 2;
+      return o;
+    }();
+    const int occ = occs[vec > 1 ? (tx == 32 ? 2 : 1) : 0];
+    // the largest split count that still fits one wave; a lone wave filling under 70 % of the slots is split in two anyway
+    // (256 tiles on 444 slots: 101 µs unsplit, 85 µs as 1.15 waves), but 128 tiles × 5 on 592 slots — 1.08 waves — cost
+    // 108 µs against 82 µs for × 4
+    const int64_t slots = (int64_t)ctx->sm_count * occ;
+    int64_t S = slots / blocks;
+    if (S == 1 && blocks * 10 < slots * 7) S = 2;
     const int64_t max_s = p.L / ((int64_t)ty * 4 * 2);
     if (S > max_s) S = max_s;
     if (S > 64) S = 64;
     if (S < 1) S = 1;
+    if (band_tune_on()) {  // development (tools/band_sweep.py)
+      if (const char* e = getenv("HPTB_TUNE_SMC_S")) S = atoll(e) < 1 ? 1 : (atoll(e) > max_s && max_s >= 1 ? max_s : atoll(e));
+    }
     p.rps = (p.L + S - 1) / S;
     S = (p.L + p.rps - 1) / p.rps;
     typedef compute_t<O> CT;

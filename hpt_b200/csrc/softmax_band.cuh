@@ -20,6 +20,11 @@ __device__ __forceinline__ void band_cp16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void band_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// A CTA may write a peer's shared memory only once that peer is known to have STARTED (compute-sanitizer: "block that
+// might not have entered yet").  Split barrier: every CTA arrives as its first instruction and waits right before its
+// first remote store — by then the band has been copied and reduced, so the wait is free.
+__device__ __forceinline__ void band_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void band_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 struct BandParams {
   DimWalk kept;            // rows: every kept dim; cols: the kept dims other than the contiguous one (stride_a in, stride_b out)
@@ -42,6 +47,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_band_rows(const T* __restr
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x;
   const unsigned rank = p.cl > 1 ? cluster.block_rank() : 0;
+  if (p.cl > 1) band_cluster_arrive();
   const int64_t row = (int64_t)blockIdx.x / p.cl;
   int64_t in_off = 0, out_off = 0;
   walk2(row, p.kept, p.use64, in_off, out_off);
@@ -64,6 +70,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_band_rows(const T* __restr
   }
   mx = group_reduce<MaxOp, C, kSmThreads>(mx, s_buf, neg_inf);
   if (p.cl > 1) {
+    band_cluster_wait();  // every peer is running
     if (tid < p.cl) *cluster.map_shared_rank(&s_max[rank], tid) = mx;
     cluster.sync();
     mx = s_max[0];
@@ -126,6 +133,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_band_cols(const T* __restr
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid % TX, ty = tid / TX, warp = tid >> 5;
   const unsigned rank = p.cl > 1 ? cluster.block_rank() : 0;
+  if (p.cl > 1) band_cluster_arrive();
   const int64_t band = (int64_t)blockIdx.x / p.cl;
   const int64_t outer = band / p.ctiles, ct = band - outer * p.ctiles;
   const int64_t col0 = ct * W + (int64_t)lane * VEC;
@@ -188,6 +196,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_band_cols(const T* __restr
       for (int k = 0; k < VEC; ++k) mx[k] = sm_max<C>(mx[k], to_compute<T>(v.v[k]));
     }
   }
+  if (p.cl > 1) band_cluster_wait();  // every peer is running: remote stores are allowed from here on
   across(mx, true, s_xm);
   constexpr bool kInPlace = std::is_same<T, float>::value;
   if (active) {
