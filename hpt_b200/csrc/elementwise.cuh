@@ -183,7 +183,8 @@ map_flat_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restric
 // ------------------------------------------------------------------------------------------------
 struct Rows32Params {
   uint32_t total_chunks;
-  uint32_t cpr;                     // chunks per row
+  uint32_t total_elems;             // ragged kernel only
+  uint32_t cpr;                     // chunks per row (ragged kernel: elements per row)
   FastDiv cpr_div;
   int32_t nouter;
   int32_t inner_stride[3];          // 1 or 0
@@ -259,6 +260,88 @@ map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restric
       apply_pack<F, O, A, VEC>(f, po, pa[u]);
     }
     store_pack<O, VEC>(out + oo[u], po);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ragged kernel: CONTIGUOUS output; inputs whose rows start off a pack boundary, or with a ragged or stepped inner dim
+// ------------------------------------------------------------------------------------------------
+// The output is walked as ONE flat run in aligned 16-byte packs.  A pack's elements come from one input row, or from the
+// end of one and the start of the next, through element-sized L1-allocating loads: the VEC loads of a warp touch the
+// same sectors, so one of them goes to L2 and the rest hit L1.  One index computation and one 128-bit store per VEC
+// elements, where the scalar rows kernel pays both per element (f32 exp of a[5:8000, 3:8100]: 116 → 95 µs).
+template <int NIN, int VEC, int UNROLL, typename F, typename O, typename A, typename B>
+__global__ void __launch_bounds__(kMapThreads)
+map_ragged_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, Rows32Params p, F f) {
+  pdl_prologue();
+  const uint32_t c0 = blockIdx.x * (uint32_t)(kMapThreads * UNROLL) + threadIdx.x;
+  const int last = p.nouter - 1;
+  auto row_base = [&](uint32_t r, int32_t& o1, int32_t& o2) {
+    o1 = 0;
+    o2 = 0;
+#pragma unroll 1
+    for (int i = 0; i < last; ++i) {  // all but the outermost dim (usually none)
+      const uint32_t q = p.outer_div[i].div(r);
+      const int32_t rem = (int32_t)(r - q * p.outer_shape[i]);
+      o1 += rem * p.outer_stride[1][i];
+      if (NIN == 2) o2 += rem * p.outer_stride[2][i];
+      r = q;
+    }
+    o1 += (int32_t)r * p.outer_stride[1][last];
+    if (NIN == 2) o2 += (int32_t)r * p.outer_stride[2][last];
+  };
+  Pack<A, VEC> pa[UNROLL];
+  Pack<B, VEC> pb[UNROLL];
+  int32_t cnt[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const uint32_t c = c0 + (uint32_t)u * kMapThreads;
+    cnt[u] = 0;
+    if (c < p.total_chunks) {
+      const uint32_t f0 = c * VEC;
+      uint32_t r = p.cpr_div.div(f0);
+      int32_t e = (int32_t)(f0 - r * p.cpr);
+      int32_t o1, o2;
+      row_base(r, o1, o2);
+      const uint32_t left = p.total_elems - f0;
+      cnt[u] = left < (uint32_t)VEC ? (int32_t)left : VEC;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        if (k < cnt[u]) {
+          if (e == (int32_t)p.cpr) {  // the pack runs into the next row (rows shorter than a pack: again and again)
+            e = 0;
+            row_base(++r, o1, o2);
+          }
+          Pack<A, 1> s1;
+          load_pack_cached<A, 1>(s1, a + o1 + e * p.inner_stride[1]);
+          pa[u].v[k] = s1.v[0];
+          if constexpr (NIN == 2) {
+            Pack<B, 1> s2;
+            load_pack_cached<B, 1>(s2, b + o2 + e * p.inner_stride[2]);
+            pb[u].v[k] = s2.v[0];
+          }
+          ++e;
+        } else {
+          pa[u].v[k] = pa[u].v[0];
+          if constexpr (NIN == 2) pb[u].v[k] = pb[u].v[0];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    if (cnt[u] == 0) continue;
+    Pack<O, VEC> po;
+    if constexpr (NIN == 2) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) po.v[k] = f(pa[u].v[k], pb[u].v[k]);
+    } else {
+      apply_pack<F, O, A, VEC>(f, po, pa[u]);
+    }
+    O* dst = out + (size_t)(c0 + (uint32_t)u * kMapThreads) * VEC;
+    if (cnt[u] == VEC) store_pack<O, VEC>(dst, po);
+    else
+      for (int k = 0; k < cnt[u]; ++k) dst[k] = po.v[k];
   }
 }
 
@@ -594,6 +677,56 @@ hptb_status launch_rows(const Collapsed& c, O* out, const A* a, const B* b, F f,
   return HPTB_OK;
 }
 
+// The ragged kernel serves a dense row-major output of < 2^31 elements whose operands fit 32-bit offsets; otherwise
+// HPTB_FALLBACK and the caller takes the scalar rows kernel.
+template <int NIN, int VEC, typename F, typename O, typename A, typename B>
+hptb_status launch_ragged(const Collapsed& c, O* out, const A* a, const B* b, F f, cudaStream_t stream) {
+  const int nd = c.ndim;
+  if (nd < 1 || nd - 1 > kMaxOuter) return HPTB_FALLBACK;
+  static const bool off = [] { const char* t = getenv("HPTB_TUNE"); const char* e = getenv("HPTB_TUNE_NO_RAGGED"); return t && t[0] == '1' && e && e[0] == '1'; }();
+  if (off) return HPTB_FALLBACK;
+  if (reinterpret_cast<uintptr_t>(out) % (sizeof(O) * VEC > 16 ? 16 : sizeof(O) * VEC)) return HPTB_FALLBACK;
+  int64_t dense = 1;
+  for (int d = nd - 1; d >= 0; --d) {
+    if (c.strides[0][d] != dense) return HPTB_FALLBACK;
+    dense *= c.shape[d];
+  }
+  if (dense >= (int64_t(1) << 31) - VEC) return HPTB_FALLBACK;
+  Rows32Params p;
+  memset(&p, 0, sizeof(p));
+  p.nouter = nd - 1;
+  for (int o = 1; o <= NIN; ++o) {
+    if (std::llabs(c.strides[o][nd - 1]) > 0x7fffffffLL) return HPTB_FALLBACK;
+    p.inner_stride[o] = (int32_t)c.strides[o][nd - 1];
+    int64_t span = (c.shape[nd - 1] - 1) * std::llabs(c.strides[o][nd - 1]);
+    for (int i = 0; i < p.nouter; ++i) {
+      const int d = nd - 2 - i;
+      span += (c.shape[d] - 1) * std::llabs(c.strides[o][d]);
+      if (std::llabs(c.strides[o][d]) > 0x7fffffffLL) return HPTB_FALLBACK;
+      p.outer_stride[o][i] = (int32_t)c.strides[o][d];
+    }
+    if (span > 0x7fffffffLL - 64) return HPTB_FALLBACK;
+  }
+  for (int i = 0; i < p.nouter; ++i) {
+    const int d = nd - 2 - i;
+    p.outer_shape[i] = (uint32_t)c.shape[d];
+    p.outer_div[i] = FastDiv((uint32_t)c.shape[d]);
+  }
+  if (p.nouter == 0) {
+    p.nouter = 1;
+    p.outer_shape[0] = 1;
+    p.outer_div[0] = FastDiv(1u);
+  }
+  p.cpr = (uint32_t)c.shape[nd - 1];
+  p.cpr_div = FastDiv(p.cpr);
+  p.total_elems = (uint32_t)dense;
+  p.total_chunks = (uint32_t)((dense + VEC - 1) / VEC);
+  constexpr int UNROLL = VEC >= 8 ? 1 : 2;  // 8 element loads in flight per thread; 16 lose their L1 hits (f32 window 107 vs 95 µs)
+  const int64_t blocks = ((int64_t)p.total_chunks + kMapThreads * UNROLL - 1) / (kMapThreads * UNROLL);
+  HPTB_CUDA_CHECK(launch_kernel(map_ragged_kernel<NIN, VEC, UNROLL, F, O, A, B>, dim3((unsigned)blocks), dim3(kMapThreads), 0, stream, out, a, b, p, f));
+  return HPTB_OK;
+}
+
 // TMA-staged transposing launch (tma_tile.cuh) for a tile plan with exactly ONE operand read along b (mode 1), the output
 // and any partner operand along a (mode 2) or scalar.  HPTB_FALLBACK: the layout is outside what the tensor map or the
 // kernel's grid can describe — the caller takes its other kernels.
@@ -660,9 +793,22 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
       for (int d = 0; d + 1 < nd; ++d)
         if ((uint64_t)(std::llabs(c.strides[o][d]) * (int64_t)esz[o]) % align) misaligned = true;
       // rows that do not start on a pack boundary (a[5:8000, 3:8100]): one element per lane, still one run per warp
-      if (misaligned) return nd ? launch_rows<NIN, 1, kScalarUnroll, F, O, A, B>(c, out, a, b, f, stream) : HPTB_FALLBACK;
+      if (misaligned) {
+        if (!nd) return HPTB_FALLBACK;
+        if constexpr (VEC > 1) {
+          const hptb_status st = launch_ragged<NIN, VEC, F, O, A, B>(c, out, a, b, f, stream);
+          if (st != HPTB_FALLBACK) return st;
+        }
+        return launch_rows<NIN, 1, kScalarUnroll, F, O, A, B>(c, out, a, b, f, stream);
+      }
     }
-    if (nd >= 2 && c.shape[nd - 1] % VEC) return launch_rows<NIN, 1, kScalarUnroll, F, O, A, B>(c, out, a, b, f, stream);  // ragged rows
+    if (nd >= 2 && c.shape[nd - 1] % VEC) {  // ragged rows
+      if constexpr (VEC > 1) {
+        const hptb_status st = launch_ragged<NIN, VEC, F, O, A, B>(c, out, a, b, f, stream);
+        if (st != HPTB_FALLBACK) return st;
+      }
+      return launch_rows<NIN, 1, kScalarUnroll, F, O, A, B>(c, out, a, b, f, stream);
+    }
     if (nd <= 1) {  // flat: one contiguous run per operand (or a broadcast scalar)
       FlatParams p;
       p.n = nd ? c.shape[0] : 1;
@@ -699,6 +845,10 @@ hptb_status launch_map(const MapPlan& plan, F f, cudaStream_t stream) {
     // (a[:, ::2]) or reversed.  Lanes along the output's fastest dim with scalar accesses are as coalesced as such a
     // layout allows (the tile kernel would run 64-element tiles here: f32 a[:, ::2].exp() 1146 µs).
     if (da == nd - 1) {
+      if constexpr (VEC > 1) {
+        const hptb_status sr = launch_ragged<NIN, VEC, F, O, A, B>(c, out, a, b, f, stream);
+        if (sr != HPTB_FALLBACK) return sr;
+      }
       hptb_status st = launch_rows<NIN, 1, kScalarUnroll, F, O, A, B>(c, out, a, b, f, stream);
       if (st != HPTB_FALLBACK) return st;
     }

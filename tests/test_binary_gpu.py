@@ -6,7 +6,7 @@ bit-exact for every dtype pair: both sides cast to the promoted dtype and apply 
 import numpy as np
 import pytest
 
-from util import DTYPES, ENUM, O, assert_exact, rand, to_numpy, to_torch
+from util import DTYPES, ENUM, O, assert_exact, assert_ulp, rand, to_numpy, to_torch
 
 pytestmark = pytest.mark.gpu
 
@@ -129,3 +129,32 @@ def test_config1_shape_and_config4_promotion(hb):
     _run(hb, "add", a, "f32", b, "f32")
     x, k = rand(rng, (8, 128, 4096), "f32"), rand(rng, (4096,), "i64", -1000, 1000)
     _run(hb, "add", x, "f32", k, "i64")  # → f64
+
+
+def test_ragged_kernel_contiguous_output(hb):
+    """Dense output, inputs whose rows start off a 16-byte boundary or have ragged / tiny / stepped / reversed inner dims
+    (map_ragged_kernel): packs that straddle one or several row ends, totals that are not a multiple of the pack, a
+    broadcast partner, several outer dims, every element size."""
+    rng = np.random.default_rng(77)
+    cases = [((40, 70), lambda t: t[1:39, 3:68]),          # unaligned window, 65-wide rows
+             ((33, 9), lambda t: t[:, 1:4]),               # rows of 3: a pack spans two or three rows
+             ((50, 7), lambda t: t[:, 2:3]),               # rows of 1
+             ((7, 6, 35), lambda t: t[1:6, ::2, 2:33]),    # two outer dims, one stepped
+             ((64, 41), lambda t: t[:, ::2]),              # stepped inner dim (21 per row)
+             ((64, 41), lambda t: t[:, ::-1]),             # reversed inner dim
+             ((1, 1003), lambda t: t[:, 1:1000])]          # one row, ragged total
+    for xd, yd in (("f32", "f32"), ("bf16", "bf16"), ("i8", "i8"), ("f64", "f64"), ("i16", "f32")):
+        for shape, view in cases:
+            x, y = rand(rng, shape, xd), rand(rng, shape, yd)
+            _run(hb, "add", x, xd, y, yd, view, view)
+        # partner broadcast along the inner dim / along the rows
+        x = rand(rng, (40, 70), xd)
+        v = lambda t: t[1:39, 3:68]
+        _run(hb, "mul", x, xd, rand(rng, (38, 1), yd), yd, v, None)
+        _run(hb, "mul", x, xd, rand(rng, (1, 65), yd), yd, v, None)
+    # unary through the same path, full-size rows of odd length
+    x = rand(rng, (300, 8200), "f32")
+    X = hb.Tensor.to_cuda(to_torch(x, "f32"))
+    got = X[5:290, 3:8100].exp()
+    want, od = O.unary("exp", x[5:290, 3:8100], "f32")
+    assert_ulp(to_numpy(got.to_cpu(), od), want, od, 2, "exp of an unaligned window")
