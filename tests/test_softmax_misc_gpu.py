@@ -107,6 +107,40 @@ def test_cluster_band_and_streaming_kernels(hb, log):
             os.environ.pop("HPTB_TUNE_NO_BAND", None)
 
 
+@pytest.mark.parametrize("log", [False, True])
+def test_large_offsets_and_special_lanes(hb, log):
+    """Every softmax kernel (register rows, cluster bands, streaming rows / columns) on data far from zero — the streaming
+    kernels' frame K is then in the thousands to millions, its reference r_K = fl(K·ln2) inexact — and on lanes holding
+    NaN, +inf, −inf among finite values, or nothing but −inf (exp(−inf − (−inf)) = NaN, as the reference computes)."""
+    import os
+    rng = np.random.default_rng(35)
+    cases = [((64, 4096), 1), ((5, 131072), 1), ((5, 400000), 1), ((4096, 64), 0), ((7000, 64), 0)]
+    for shape, axis in cases:
+        for offset in (5000.0, -20000.0, 3.0e5, 1.0e6):
+            x = (rand(rng, shape, "f32") * 3 + np.float32(offset)).astype(np.float32)
+            for off in ("0", "1"):
+                os.environ["HPTB_TUNE_NO_BAND"] = off
+                try:
+                    _softmax_check(hb, x, "f32", axis, log)
+                finally:
+                    os.environ.pop("HPTB_TUNE_NO_BAND", None)
+        x = (rand(rng, shape, "f32") * 3).astype(np.float32)
+        lane = (lambda i: (slice(None), i)) if axis == 0 else (lambda i: (i, slice(None)))
+        n = shape[axis]
+        x[lane(0)][n // 3] = np.nan
+        x[lane(1)][n // 2] = np.inf
+        x[lane(2)][:] = -np.inf
+        x[lane(3)][: n - 5] = -np.inf      # a handful of finite values at the very end
+        x[lane(4)][5:] = -np.inf           # ... or at the very start
+        for off in ("0", "1"):
+            os.environ["HPTB_TUNE_NO_BAND"] = off
+            try:
+                with np.errstate(all="ignore"):
+                    _softmax_check(hb, x, "f32", axis, log)
+            finally:
+                os.environ.pop("HPTB_TUNE_NO_BAND", None)
+
+
 def test_softmax_errors(hb):
     X = hb.Tensor.empty((4, 5), ENUM["f32"])
     with pytest.raises(hb.HptError) as e:
