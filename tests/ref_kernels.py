@@ -6,6 +6,11 @@ Launch shapes restate the reference's host logic:
   contiguous_{argmax,argmin}_<T>(out, buffer, in, finished, size)      fast_all_reduce, hpt/src/backends/cuda/utils/reduce/reduce.rs:231-283
   contiguous_{op}_small_fast_dim_only_<T>(out, in, fast_dim, outputs)  reduce.rs:403-437 (case 2) + arg_template.cuh:89-111
   strided_copy_<T>(dst, src, FastDivmod* shape, i32* strides, ndim, n) hpt-cudakernels/src/strided_copy.cu:6-21
+  <op>_<L>_<R>_contiguous(out, lhs, rhs, i32 n)                        binary_template.cuh:104-108, launched by binary_fn_precompiled
+  <op>_<L>_<R>_uncontiguous(out, lhs, FastDivmod* lshape, i32* lstrides, rhs, FastDivmod* rshape, i32* rstrides,
+                            i32 lndim, i32 rndim, i32 n)               (hpt/src/backends/cuda/utils/binary/binary_normal.rs:371-544)
+    — one element per thread: the kernels' grid-stride loops index with the thread id, not the loop variable
+      (binary_template.cuh:9-13), so the reference is only right when the grid covers n; the launches here do
 FastDivmod{i32 divisor; u32 multiplier; u32 shift_right} is CUTLASS's find_divisor as restated in
 hpt/src/backends/common/divmod.rs:1-52.
 """
@@ -23,6 +28,10 @@ def available():
     return all(os.path.exists(os.path.join(REF_DIR, n + ".cubin")) for n in ("argmax", "argmin", "strided_copy"))
 
 
+def available_binary():
+    return all(os.path.exists(os.path.join(REF_DIR, f"binary_{n}.cubin")) for n in ("add", "sub", "mul", "rem"))
+
+
 class RefModule:
     _cuda = None
 
@@ -36,6 +45,10 @@ class RefModule:
         rc = self.cu.cuModuleLoad(ctypes.byref(self.mod), os.path.join(REF_DIR, name + ".cubin").encode())
         assert rc == 0, f"cuModuleLoad({name}) failed: {rc}"
         self.fns = {}
+
+    def has(self, name):
+        f = ctypes.c_void_p()
+        return self.cu.cuModuleGetFunction(ctypes.byref(f), self.mod, name.encode()) == 0
 
     def fn(self, name):
         if name not in self.fns:
@@ -102,3 +115,24 @@ def ref_strided_copy(mod, view, tname="f32"):
                [ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(view.data_ptr()), ctypes.c_void_p(table.data_ptr()),
                 ctypes.c_void_p(st.data_ptr()), ctypes.c_int32(len(shape)), ctypes.c_int64(n)])
     return dst.cpu()
+
+
+def ref_binary_contiguous(mod, op, ld, rd, lhs, rhs, out):
+    """out[i] = op(lhs[i], rhs[i]) through the reference's <op>_<L>_<R>_contiguous; torch CUDA tensors, out preallocated"""
+    n = out.numel()
+    mod.launch(f"{op}_{ld}_{rd}_contiguous", ((n + 255) // 256, 1, 1), (256, 1, 1),
+               [ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(lhs.data_ptr()), ctypes.c_void_p(rhs.data_ptr()), ctypes.c_int32(n)])
+
+
+def ref_binary_uncontiguous(mod, op, ld, rd, lhs, rhs, out):
+    """lhs / rhs: torch CUDA VIEWS already expanded to out's shape (stride 0 on broadcast dims), as the reference's host
+    code passes them"""
+    n = out.numel()
+    shape = list(out.shape)
+    table = torch.frombuffer(bytearray(b"".join(fast_divmod(s) for s in shape)), dtype=torch.uint8).cuda()
+    ls = torch.tensor(list(lhs.stride()), dtype=torch.int32, device="cuda")
+    rs = torch.tensor(list(rhs.stride()), dtype=torch.int32, device="cuda")
+    mod.launch(f"{op}_{ld}_{rd}_uncontiguous", ((n + 255) // 256, 1, 1), (256, 1, 1),
+               [ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(lhs.data_ptr()), ctypes.c_void_p(table.data_ptr()),
+                ctypes.c_void_p(ls.data_ptr()), ctypes.c_void_p(rhs.data_ptr()), ctypes.c_void_p(table.data_ptr()),
+                ctypes.c_void_p(rs.data_ptr()), ctypes.c_int32(len(shape)), ctypes.c_int32(len(shape)), ctypes.c_int32(n)])
