@@ -27,8 +27,10 @@ Pinning: the promotion tables are the reference's own (golden JSON); casts, wrap
 f16/bf16 conversions are pinned against the known-answer values of hpt-tests/src/hpt_types/tests.rs
 (tests/test_oracle.py); reductions / softmax / unary follow the reference's own test oracle, libtorch
 (hpt-tests/src/hpt/cpu/reduce.rs:14), which tests/test_oracle.py cross-checks with torch CPU.
-Cross-dtype promotion at tensor level is pinned by NO reference test — "parity unpinned"
-for that row; the tables are the only spec.
+Cross-dtype promotion at tensor level is pinned by NO reference test; for the four NormalBinOps
+it is pinned instead to the OUTPUT of the reference's own CUDA kernels (oracle/_ref/binary_*.cubin, every dtype pair,
+tests/test_reference_kernels_gpu.py), as are argmax / argmin and strided copies.  For the unary and reduce paths,
+whose reference kernels do not build here, it stays "parity unpinned": the tables are the only spec.
 
 Representation: numpy arrays; f16 is np.float16; bf16 values are carried as np.float32 arrays holding
 bf16-representable numbers together with the dtype name "bf16"; bool is np.bool_.
