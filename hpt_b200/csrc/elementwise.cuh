@@ -305,6 +305,25 @@ map_ragged_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restr
       row_base(r, o1, o2);
       const uint32_t left = p.total_elems - f0;
       cnt[u] = left < (uint32_t)VEC ? (int32_t)left : VEC;
+      if (cnt[u] == VEC && e + VEC <= (int32_t)p.cpr) {  // the whole pack lies in one row: no per-element bookkeeping
+        const A* pa1 = a + o1 + e * p.inner_stride[1];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          Pack<A, 1> s1;
+          load_pack_cached<A, 1>(s1, pa1 + k * p.inner_stride[1]);
+          pa[u].v[k] = s1.v[0];
+        }
+        if constexpr (NIN == 2) {
+          const B* pb1 = b + o2 + e * p.inner_stride[2];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            Pack<B, 1> s2;
+            load_pack_cached<B, 1>(s2, pb1 + k * p.inner_stride[2]);
+            pb[u].v[k] = s2.v[0];
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
         if (k < cnt[u]) {

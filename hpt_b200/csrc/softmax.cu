@@ -224,9 +224,16 @@ __device__ __forceinline__ float sm_frame(float K) {
 }
 // a thread's running statistics of one softmax lane
 template <typename C> struct SmRun;
+// While a thread sweeps, its frame may LAG the running maximum by up to kSmLag binary orders: terms up to 2^kSmLag are
+// as accurate as terms below 1 (what matters is |x − r_K|, and a reference below the maximum is closer to everything
+// under it), Σ has the exponent range to spare, and the frame then moves a few times per sweep instead of whenever some
+// lane of the warp sees a new integer part of max·log2e — which, with 32 independent maxima per warp, was in most
+// blocks: 22 instructions per element instead of 13 (ncu, f32 [4096,8192]: 23.3 M warp instructions, 39 µs).  done()
+// moves the pair to the frame of the TRUE maximum (an exponent shift), so merges and the apply sweep never see the lag.
+constexpr float kSmLag = 8.0f;
 template <> struct SmRun<float> {
-  float K, r, T, S, comp;  // frame, its reference r_K, the sum in frame units, the raw sum of the current stretch (+ its lost bits)
-  __device__ __forceinline__ void init() { K = Limits<float>::lowest(); r = 0.0f; T = 0.0f; S = 0.0f; comp = 0.0f; }
+  float K, r, T, S, comp, ymax;  // frame, its reference r_K, the sum in frame units, the raw sum of the current stretch (+ its lost bits), max of x·log2e
+  __device__ __forceinline__ void init() { K = Limits<float>::lowest(); r = 0.0f; T = 0.0f; S = 0.0f; comp = 0.0f; ymax = K; }
   __device__ __forceinline__ void close() {
     if (S != 0.0f) T = fmaf(S, sm_frame(K), T);  // also when S is NaN
     S = 0.0f;
@@ -239,7 +246,8 @@ template <> struct SmRun<float> {
 #pragma unroll
     for (int i = 1; i < N; ++i) bm = fmaxf(bm, x[i]);  // NaNs drop out here and poison S through their term
     const float y = bm * kLog2eHi;
-    if (y > K) {  // false for NaN and for −inf against the initial −inf; K is an integer, so ceil(y) > K
+    ymax = fmaxf(ymax, y);
+    if (y > K + kSmLag) {  // false for NaN and for −inf against the initial −inf
       const float Kn = ceilf(y);  // +inf input: K = r = +inf, every term NaN or 0 as exp(x − inf) is
       close();
       T *= sm_exp2i(K - Kn);
@@ -260,7 +268,15 @@ template <> struct SmRun<float> {
     comp = (s2 - S) - v;
     S = s2;
   }
-  __device__ __forceinline__ MS<float> done() { close(); return MS<float>{K, T}; }
+  __device__ __forceinline__ MS<float> done() {
+    close();
+    const float Kt = ceilf(ymax);  // the frame of the true maximum
+    if (Kt > K) {
+      T *= sm_exp2i(K - Kt);
+      K = Kt;
+    }
+    return MS<float>{K, T};
+  }
 };
 // 64-bit compute type: the plain online pair
 __device__ __forceinline__ void ms_push_fast(MS<double>& a, double x) {
@@ -396,14 +412,18 @@ softmax_cols(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_o
 }
 
 // Long unit-stride rows (more than 8 packs per thread): one CTA per row, 16-byte loads with four in flight per
-// thread, an online (max, Σ) sweep and a write sweep whose reads come back from L2 (a row is ≤ a few MB).  The scalar
-// softmax_rows_stream below stays for strided axes: f32 [256,131072] softmax(1) 551 µs through it.
+// thread, a statistics sweep and an apply sweep whose reads come back from L2 (a row is ≤ a few MB).  The scalar
+// softmax_rows_stream above stays for strided axes: f32 [256,131072] softmax(1) 551 µs through it.
 // NT = 1024 threads for rows of ≥ 8192 packs: a grid of a few hundred rows otherwise leaves each SM with one or two
-// 256-thread CTAs (f32 [256,131072]: 118 µs with 256 threads per row)
-template <typename T, int VEC, int NT>
+// 256-thread CTAs (f32 [256,131072]: 118 µs with 256 threads per row).
+// PHASE 0: the whole job in one launch.  FEWER rows than CTA slots (a 1-D softmax: one row) would leave most of the GPU
+// idle — f32 [64,524288]: 64 CTAs on 148 SMs, 94 µs — so each row is split into gridDim.x slabs and the job becomes two
+// launches, as for the column kernel below: PHASE 1 leaves one (K, T) pair per (row, slab) in `part`, PHASE 2 merges a
+// row's pairs in slab order and applies to its own slab.
+template <typename T, int VEC, int NT, int PHASE>
 __global__ void __launch_bounds__(NT)
 softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type* __restrict__ out,
-                        SoftmaxParams p) {
+                        compute_t<typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type>* __restrict__ part, SoftmaxParams p) {
   pdl_prologue();
   typedef typename type_of_dtype<promote_ct(dtype_of<T>::value, 0, 2)>::type O;
   typedef compute_t<O> C;
@@ -411,49 +431,73 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
   __shared__ C s_m[NT / 32], s_s[NT / 32];
   const int tid = threadIdx.x;
   const int64_t packs = p.L / VEC;  // the host picks this kernel only when L is a multiple of VEC
-  for (int64_t row = blockIdx.x; row < p.M; row += gridDim.x) {
+  const int64_t row0 = PHASE == 0 ? blockIdx.x : blockIdx.y, row_step = PHASE == 0 ? gridDim.x : p.M;
+  const int64_t c_begin = PHASE == 0 ? 0 : (int64_t)blockIdx.x * p.rps;
+  const int64_t c_end = PHASE == 0 ? packs : (c_begin + p.rps < packs ? c_begin + p.rps : packs);
+  for (int64_t row = row0; row < p.M; row += row_step) {
     int64_t in_off = 0, out_off = 0;
     walk2(row, p.kept, p.use64, in_off, out_off);
     const T* src = in + in_off;
     O* dst = out + out_off;
-    SmRun<C> run;
-    run.init();
-    int64_t c = tid;
-    for (; c + (int64_t)(UN - 1) * NT < packs; c += (int64_t)NT * UN) {  // whole batches: no predicates
-      Pack<T, VEC> v[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) load_pack<T, VEC>(v[u], src + (c + (int64_t)u * NT) * VEC);
-      C xs[UN * VEC];
-#pragma unroll
-      for (int u = 0; u < UN; ++u)
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) xs[u * VEC + k] = to_compute<O>(cast<O>(v[u].v[k]));
-      run.push(xs);
-    }
-    for (; c < packs; c += NT) {  // ragged tail, a pack at a time
-      Pack<T, VEC> v;
-      load_pack<T, VEC>(v, src + c * VEC);
-      C xs[VEC];
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) xs[k] = to_compute<O>(cast<O>(v.v[k]));
-      run.push(xs);
-    }
-    MS<C> a = run.done();
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      MS<C> b{shfl_xor<C>(a.m, off), shfl_xor<C>(a.s, off)};
-      a = (tid & off) == 0 ? ms_merge_fast(a, b) : ms_merge_fast(b, a);
-    }
-    __syncthreads();
-    if ((tid & 31) == 0) { s_m[tid >> 5] = a.m; s_s[tid >> 5] = a.s; }
-    __syncthreads();
     MS<C> r{Limits<C>::lowest(), (C)0};
     C rcomp = (C)0;
-    for (int w = 0; w < NT / 32; ++w) ms_run_add(r, rcomp, MS<C>{s_m[w], s_s[w]});
-    ms_run_done(r, rcomp);
+    if constexpr (PHASE != 2) {
+      SmRun<C> run;
+      run.init();
+      int64_t c = c_begin + tid;
+      for (; c + (int64_t)(UN - 1) * NT < c_end; c += (int64_t)NT * UN) {  // whole batches: no predicates
+        Pack<T, VEC> v[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) load_pack<T, VEC>(v[u], src + (c + (int64_t)u * NT) * VEC);
+        C xs[UN * VEC];
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) xs[u * VEC + k] = to_compute<O>(cast<O>(v[u].v[k]));
+        run.push(xs);
+      }
+      for (; c < c_end; c += NT) {  // ragged tail, a pack at a time
+        Pack<T, VEC> v;
+        load_pack<T, VEC>(v, src + c * VEC);
+        C xs[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) xs[k] = to_compute<O>(cast<O>(v.v[k]));
+        run.push(xs);
+      }
+      MS<C> a = run.done();
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        MS<C> b{shfl_xor<C>(a.m, off), shfl_xor<C>(a.s, off)};
+        a = (tid & off) == 0 ? ms_merge_fast(a, b) : ms_merge_fast(b, a);
+      }
+      __syncthreads();
+      if ((tid & 31) == 0) { s_m[tid >> 5] = a.m; s_s[tid >> 5] = a.s; }
+      __syncthreads();
+      for (int w = 0; w < NT / 32; ++w) ms_run_add(r, rcomp, MS<C>{s_m[w], s_s[w]});
+      ms_run_done(r, rcomp);
+      if constexpr (PHASE == 1) {
+        if (tid == 0) {
+          C* pm = part + (row * gridDim.x + blockIdx.x) * 2;
+          pm[0] = r.m;
+          pm[1] = r.s;
+        }
+        continue;
+      }
+    } else {
+      // the lanes of a warp take the slabs round-robin, a shuffle tree merges the 32 pairs: every warp of every slab's
+      // CTA computes the same bits
+      const C* pm = part + row * gridDim.x * 2;
+      for (int sp = tid & 31; sp < (int)gridDim.x; sp += 32) ms_run_add(r, rcomp, MS<C>{pm[2 * sp], pm[2 * sp + 1]});
+      ms_run_done(r, rcomp);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        MS<C> b{shfl_xor<C>(r.m, off), shfl_xor<C>(r.s, off)};
+        r = (tid & off) == 0 ? ms_merge_fast(r, b) : ms_merge_fast(b, r);
+      }
+    }
     const auto fin = sm_final(r);
-    c = tid;
-    for (; c + (int64_t)(UN - 1) * NT < packs; c += (int64_t)NT * UN) {
+    int64_t c = c_begin + tid;
+    for (; c + (int64_t)(UN - 1) * NT < c_end; c += (int64_t)NT * UN) {
       Pack<T, VEC> v[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) load_pack_cached<T, VEC>(v[u], src + (c + (int64_t)u * NT) * VEC);
@@ -465,7 +509,7 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
         store_pack<O, VEC>(dst + (c + (int64_t)u * NT) * VEC, o);
       }
     }
-    for (; c < packs; c += NT) {
+    for (; c < c_end; c += NT) {
       Pack<T, VEC> v;
       load_pack_cached<T, VEC>(v, src + c * VEC);
       Pack<O, VEC> o;
@@ -742,11 +786,32 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
         }
       }
       if (ok) {
+        typedef compute_t<O> CT;
+        CT* none = nullptr;
         int64_t blocks = M < (int64_t)ctx->sm_count * 16 ? M : (int64_t)ctx->sm_count * 16;
-        if (p.L / VECMAX >= 8192 && M < (int64_t)ctx->sm_count * 8)
-          HPTB_CUDA_CHECK(launch_kernel(softmax_rows_stream_vec<T, VECMAX, 1024>, dim3((unsigned)blocks), dim3(1024), 0, stream, in, out, p));
-        else
-          HPTB_CUDA_CHECK(launch_kernel(softmax_rows_stream_vec<T, VECMAX, kSmThreads>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, p));
+        const int64_t packs = p.L / VECMAX;
+        if (packs >= 8192 && M < (int64_t)ctx->sm_count * 8) {
+          // fewer rows than 1024-thread CTA slots: split every row into slabs of ≥ 8 batches per thread
+          const int64_t slots = (int64_t)ctx->sm_count * 2;
+          int64_t S = slots / M;
+          if (S > packs / (1024 * 4 * 8)) S = packs / (1024 * 4 * 8);
+          if (S > 512) S = 512;
+          if (S >= 2 && M <= 65535) {
+            p.rps = (packs + S - 1) / S;
+            S = (packs + p.rps - 1) / p.rps;
+            Scratch part;
+            HPTB_TRY(part.get(ctx, (size_t)M * S * 2 * sizeof(CT), stream));
+            CT* pp = static_cast<CT*>(part.ptr);
+            HPTB_CUDA_CHECK(launch_kernel(softmax_rows_stream_vec<T, VECMAX, 1024, 1>, dim3((unsigned)S, (unsigned)M), dim3(1024), 0, stream, in, out, pp, p));
+            HPTB_CUDA_CHECK(launch_kernel(softmax_rows_stream_vec<T, VECMAX, 1024, 2>, dim3((unsigned)S, (unsigned)M), dim3(1024), 0, stream, in, out, pp, p));
+            HPTB_CUDA_CHECK(cudaGetLastError());
+            count_launches(2);
+            return HPTB_OK;
+          }
+          HPTB_CUDA_CHECK(launch_kernel(softmax_rows_stream_vec<T, VECMAX, 1024, 0>, dim3((unsigned)blocks), dim3(1024), 0, stream, in, out, none, p));
+        } else {
+          HPTB_CUDA_CHECK(launch_kernel(softmax_rows_stream_vec<T, VECMAX, kSmThreads, 0>, dim3((unsigned)blocks), dim3(kSmThreads), 0, stream, in, out, none, p));
+        }
         HPTB_CUDA_CHECK(cudaGetLastError());
         count_launches(1);
         return HPTB_OK;

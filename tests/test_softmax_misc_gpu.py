@@ -13,7 +13,7 @@ def hb():
     return hpt_b200
 
 
-def _softmax_check(hb, x, d, axis, log, view=None):
+def _softmax_check(hb, x, d, axis, log, view=None, streaming=False):
     X = hb.Tensor.to_cuda(to_torch(x, d))
     if view:
         X, x = view(X), view(x)
@@ -28,13 +28,16 @@ def _softmax_check(hb, x, d, axis, log, view=None):
     # that exp turns into a relative error of |x − max|·2^-24, i.e. |x − max|/2 ulp of the result.  Bound:
     # 4 + |x − max| ulp (the reference's own tests use allclose 1e-3).  log_softmax subtracts two O(|x|)
     # numbers: absolute bound 4·eps·max|x| as well.
+    # streaming=True — the two-sweep kernels for lanes that fit neither registers nor a cluster's shared memory: their
+    # reference is r_K = fl(K·ln2), not the maximum itself, so the LARGEST term is exp(max − r_K) through ex2 (≤ 2 ulp)
+    # instead of exactly 1, and that error reaches every output of the lane through Σ: 6 + |x − max| ulp.
     eps = {"f16": 2.0 ** -10, "bf16": 2.0 ** -7, "f32": 2.0 ** -23, "f64": 2.0 ** -52}[od]
     err = np.abs(np.asarray(got, np.float64) - np.asarray(want, np.float64))
     xc = np.asarray(O.to_compute(O.cast(x, d, od), od), np.float64)
     shift = np.abs(xc - np.max(xc, axis=axis, keepdims=True))
     shift = np.where(np.isfinite(shift), shift, 0.0)
     scale = np.max(np.abs(xc), axis=axis, keepdims=True) + 1.0
-    ulp_ok = u <= 4 + np.ceil(shift)
+    ulp_ok = u <= (6 if streaming else 4) + np.ceil(shift)
     ok = ulp_ok | (err <= 4 * eps * scale if log else err <= 4 * eps * np.maximum(np.asarray(want, np.float64), 1e-30) + 1e-45)
     assert ok.all(), f"softmax log={log} {d} shape={x.shape} axis={axis}: max ulp {u.max()}"
 
@@ -76,8 +79,9 @@ def test_dtypes_shapes_layouts(hb, log):
 def test_cluster_band_and_streaming_kernels(hb, log):
     """Rows beyond the register limit and strided axes: the cluster-resident band kernels (softmax_band.cuh: rows of up to
     8 × 96 KB, 128-byte column bands of up to 6144 rows), and past those the streaming kernels with the exact power-of-two
-    rescale.  Same bound as the register kernel (4 + |x − max| ulp): no allowance for online rescaling any more.  Each
-    shape also runs with the band kernels switched off, i.e. through the streaming kernels, under the same bound."""
+    rescale.  The band kernels hold the register kernel's bound (4 + |x − max| ulp); each shape also runs with them switched
+    off, i.e. through the streaming kernels, whose bound is 6 + |x − max| ulp (_softmax_check): no allowance that grows
+    with the lane length any more."""
     import os
     rng = np.random.default_rng(33)
     cases = [((6, 131072), 1, "f32"), ((3, 200000), 1, "f32"), ((40, 50000), 1, "f32"), ((2, 400000), 1, "f32"),   # rows; 400000 > 8 × 96 KB
@@ -90,10 +94,11 @@ def test_cluster_band_and_streaming_kernels(hb, log):
         if d == "f32":
             x.flat[7] = 30.0          # a late, dominant maximum: every running reference moves
             x.flat[x.size // 2] = -np.inf
+        beyond_band = shape in ((2, 400000), (3, 300000), (7000, 64))
         for off in ("0", "1"):
             os.environ["HPTB_TUNE_NO_BAND"] = off
             try:
-                _softmax_check(hb, x, d, axis, log)
+                _softmax_check(hb, x, d, axis, log, streaming=(off == "1" or beyond_band))
             finally:
                 os.environ.pop("HPTB_TUNE_NO_BAND", None)
     # increasing rows: the running maximum moves at every element
@@ -101,8 +106,8 @@ def test_cluster_band_and_streaming_kernels(hb, log):
     for off in ("0", "1"):
         os.environ["HPTB_TUNE_NO_BAND"] = off
         try:
-            _softmax_check(hb, x, "f32", 1, log)
-            _softmax_check(hb, np.ascontiguousarray(x.T[:4096]), "f32", 0, log)
+            _softmax_check(hb, x, "f32", 1, log, streaming=(off == "1"))
+            _softmax_check(hb, np.ascontiguousarray(x.T[:4096]), "f32", 0, log, streaming=(off == "1"))
         finally:
             os.environ.pop("HPTB_TUNE_NO_BAND", None)
 
@@ -121,7 +126,7 @@ def test_large_offsets_and_special_lanes(hb, log):
             for off in ("0", "1"):
                 os.environ["HPTB_TUNE_NO_BAND"] = off
                 try:
-                    _softmax_check(hb, x, "f32", axis, log)
+                    _softmax_check(hb, x, "f32", axis, log, streaming=(off == "1" or shape in ((5, 400000), (7000, 64))))
                 finally:
                     os.environ.pop("HPTB_TUNE_NO_BAND", None)
         x = (rand(rng, shape, "f32") * 3).astype(np.float32)
@@ -136,9 +141,27 @@ def test_large_offsets_and_special_lanes(hb, log):
             os.environ["HPTB_TUNE_NO_BAND"] = off
             try:
                 with np.errstate(all="ignore"):
-                    _softmax_check(hb, x, "f32", axis, log)
+                    _softmax_check(hb, x, "f32", axis, log, streaming=(off == "1" or shape in ((5, 400000), (7000, 64))))
             finally:
                 os.environ.pop("HPTB_TUNE_NO_BAND", None)
+
+
+@pytest.mark.parametrize("log", [False, True])
+def test_few_very_long_rows_split_into_slabs(hb, log):
+    """Fewer rows than CTA slots (a 1-D softmax is ONE row): the streaming rows kernel splits every row into slabs, two
+    launches (statistics per slab, then merge + apply).  Ragged slab ends, a late maximum, −inf and a NaN row."""
+    rng = np.random.default_rng(36)
+    for shape in ((3000000,), (1, 4 * 1000003), (3, 1300000), (20, 500000)):
+        x = (rand(rng, shape, "f32") * 4).astype(np.float32)
+        x.flat[x.size - 3] = 25.0
+        x.flat[x.size // 2] = -np.inf
+        _softmax_check(hb, x, "f32", len(shape) - 1, log, streaming=True)
+    x = (rand(rng, (2, 2000000), "f32")).astype(np.float32)
+    x[1, 1234567] = np.nan
+    with np.errstate(all="ignore"):
+        _softmax_check(hb, x, "f32", 1, log, streaming=True)
+    x = rand(rng, (2, 1 << 21), "bf16")
+    _softmax_check(hb, x, "bf16", 1, log, streaming=True)
 
 
 def test_softmax_errors(hb):
