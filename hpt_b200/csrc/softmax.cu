@@ -559,7 +559,8 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
     for (int k = 0; k < VEC; ++k) run[k].init();
     if (active) {
       // rows per batch of the statistics sweep = 16-byte loads in flight per thread.  f32: 8 rows need 76 registers (three
-      // CTAs per SM) and measured 85 µs on [4096,8192] against 80 µs for 4 rows at 63 registers; bf16 (8 lanes per pack)
+      // CTAs per SM) and measured 85 µs on [4096,8192] against 80 µs for 4 rows at 63 registers (82 vs 76 µs with the lagging
+      // frame); bf16 (8 lanes per pack)
       // is at two CTAs per SM either way and prefers 8 rows (64 vs 79 µs)
       constexpr int US = VEC > 4 ? 8 : 4;
       int64_t e = e_begin + ty;
