@@ -76,6 +76,21 @@ template <typename C> __device__ __forceinline__ C sm_max(C a, C b) {
 // exp for the register-resident kernel: fast_expf (scalar.cuh)
 __device__ __forceinline__ float sm_exp_fast(float x) { return fast_expf(x); }
 __device__ __forceinline__ double sm_exp_fast(double x) { return exp(x); }
+// exp for a result that is rounded to a 16-BIT output type (and summed in f32): one multiply and one ex2.  The rounding
+// of x·log2e costs |x|·2^-24 relative — under 1e-5 for any argument whose exp is not zero — against an output ulp of
+// 2^-11 (f16) or 2^-8 (bf16); the compensated fast_expf is six more instructions per element, and the 16-bit kernels
+// (8 elements per 16-byte pack) are bound by exactly that instruction stream (bf16 [32768,4096] softmax: 113 µs
+// against 82 µs of HBM time).  −inf → 0, NaN propagates.
+__device__ __forceinline__ float sm_exp_half(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return e;
+}
+// by OUTPUT type
+template <typename O> __device__ __forceinline__ float sm_exp_o(float x) {
+  if constexpr (sizeof(O) == 2) return sm_exp_half(x); else return fast_expf(x);
+}
+template <typename O> __device__ __forceinline__ double sm_exp_o(double x) { return exp(x); }
 
 struct MaxOp {
   template <typename C> static __device__ __forceinline__ C combine(C a, C b) { return sm_max<C>(a, b); }
@@ -88,7 +103,7 @@ struct WrapOp {
   static __device__ __forceinline__ C combine(C a, C b) { return OpT::template combine<C>(a, b); }
 };
 
-// reduce over the G threads that own a row (G = 32: warp shuffle; G = 256: + shared memory)
+// reduce over the G threads that own a row (G = 32: warp shuffle; G = 128 / 256: + shared memory)
 template <typename OpT, typename C, int G>
 __device__ __forceinline__ C group_reduce(C v, C* s_buf, C ident) {
   v = warp_reduce<WrapOp<OpT, C>, C>(v, 32);
@@ -97,7 +112,8 @@ __device__ __forceinline__ C group_reduce(C v, C* s_buf, C ident) {
     __syncthreads();  // s_buf reuse
     if ((tid & 31) == 0) s_buf[tid >> 5] = v;
     __syncthreads();
-    C r = (tid & 31) < G / 32 ? s_buf[tid & 31] : ident;
+    const int wbase = (tid / G) * (G / 32);  // first warp slot of this thread's group (G = 128: two groups per CTA)
+    C r = (tid & 31) < G / 32 ? s_buf[wbase + (tid & 31)] : ident;
     v = warp_reduce<WrapOp<OpT, C>, C>(r, 32);  // full butterfly: every lane ends with the row total
   }
   return v;
@@ -149,7 +165,7 @@ softmax_rows_reg(const T* __restrict__ in, typename type_of_dtype<promote_ct(dty
         // rounding of x − max costs up to |x − max|/2 ulp of the result, which the parity bound accounts for.
         // (The two-pass kernels below fold that error back in — they have instruction slack; this one does not.)
         const C sh = x[i][k] - mx;
-        const C ex = sm_exp_fast(sh);
+        const C ex = sm_exp_o<O>(sh);
         sum += ex;  // padding lanes: exp(-inf - mx) = 0 (or NaN only if mx itself is -inf/NaN, handled by row)
         x[i][k] = LOG ? sh : ex;
       }
@@ -232,7 +248,7 @@ softmax_rows_reg_loop(const T* __restrict__ in, typename type_of_dtype<promote_c
           // plain f32 exp(x − max), as the reference's CPU kernel computes it (cpu/kernels/softmax.rs:204-310): the
           // rounding of x − max costs up to |x − max|/2 ulp of the result, which the parity bound accounts for.
           const C sh = x[i][k] - mx;
-          const C ex = sm_exp_fast(sh);
+          const C ex = sm_exp_o<O>(sh);
           sum += ex;  // padding lanes: exp(-inf - mx) = 0 (or NaN only if mx itself is -inf/NaN, handled by row)
           x[i][k] = LOG ? sh : ex;
         }
@@ -325,7 +341,7 @@ template <> struct SmRun<float> {
     comp = 0.0f;
   }
   // N values at once: ONE frame update for the block (its maximum decides), then N plain terms
-  template <int N>
+  template <bool HALF, int N>
   __device__ __forceinline__ void push(const float (&x)[N]) {
     float bm = x[0];
 #pragma unroll
@@ -344,7 +360,7 @@ template <> struct SmRun<float> {
     // The block is summed on its own first (pairwise), and its sum joins S with the rounding error carried along.
     float t[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) t[i] = fast_expf(x[i] - r);  // −inf → 0 (r = 0 until the first finite value)
+    for (int i = 0; i < N; ++i) t[i] = HALF ? sm_exp_half(x[i] - r) : fast_expf(x[i] - r);  // −inf → 0 (r = 0 until the first finite value)
 #pragma unroll
     for (int w = 1; w < N; w <<= 1)
 #pragma unroll
@@ -373,7 +389,7 @@ __device__ __forceinline__ void ms_push_fast(MS<double>& a, double x) {
 template <> struct SmRun<double> {
   MS<double> a;
   __device__ __forceinline__ void init() { a = MS<double>{Limits<double>::lowest(), 0.0}; }
-  template <int N>
+  template <bool HALF, int N>
   __device__ __forceinline__ void push(const double (&x)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i)
@@ -412,14 +428,16 @@ struct SmFinal {
 __device__ __forceinline__ SmFinal sm_final(MS<float> a) {
   return SmFinal{sm_ref(a.m), sm_frame(a.m) / a.s, logf(a.s) - sm_frame_ln(a.m)};
 }
+template <bool HALF>
 __device__ __forceinline__ float sm_out(float x, const SmFinal& f, int log) {
   const float sh = x - f.r;
-  return log ? sh - f.lgq : fast_expf(sh) * f.q;
+  return log ? sh - f.lgq : (HALF ? sm_exp_half(sh) : fast_expf(sh)) * f.q;
 }
 struct SmFinalD {
   double m, inv, lg;
 };
 __device__ __forceinline__ SmFinalD sm_final(MS<double> r) { return SmFinalD{r.m, 1.0 / r.s, log(r.s)}; }
+template <bool HALF>
 __device__ __forceinline__ double sm_out(double x, const SmFinalD& f, int log) {
   const double sh = x - f.m;
   return log ? sh - f.lg : exp(sh) * f.inv;
@@ -539,7 +557,7 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
         for (int u = 0; u < UN; ++u)
 #pragma unroll
           for (int k = 0; k < VEC; ++k) xs[u * VEC + k] = to_compute<O>(cast<O>(v[u].v[k]));
-        run.push(xs);
+        run.template push<sizeof(O) == 2>(xs);
       }
       for (; c < c_end; c += NT) {  // ragged tail, a pack at a time
         Pack<T, VEC> v;
@@ -547,7 +565,7 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
         C xs[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) xs[k] = to_compute<O>(cast<O>(v.v[k]));
-        run.push(xs);
+        run.template push<sizeof(O) == 2>(xs);
       }
       MS<C> a = run.done();
 #pragma unroll
@@ -590,7 +608,7 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
       for (int u = 0; u < UN; ++u) {
         Pack<O, VEC> o;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v[u].v[k])), fin, p.log));
+        for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out<sizeof(O) == 2>(to_compute<O>(cast<O>(v[u].v[k])), fin, p.log));
         store_pack<O, VEC>(dst + (c + (int64_t)u * NT) * VEC, o);
       }
     }
@@ -599,7 +617,7 @@ softmax_rows_stream_vec(const T* __restrict__ in, typename type_of_dtype<promote
       load_pack_cached<T, VEC>(v, src + c * VEC);
       Pack<O, VEC> o;
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v.v[k])), fin, p.log));
+      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out<sizeof(O) == 2>(to_compute<O>(cast<O>(v.v[k])), fin, p.log));
       store_pack<O, VEC>(dst + c * VEC, o);
     }
   }
@@ -658,7 +676,7 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
           C xs[US];
 #pragma unroll
           for (int u = 0; u < US; ++u) xs[u] = to_compute<O>(cast<O>(v[u].v[k]));
-          run[k].push(xs);
+          run[k].template push<sizeof(O) == 2>(xs);
         }
       }
       for (; e < e_end; e += TY) {  // ragged tail, a row at a time
@@ -667,7 +685,7 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
           C xs[1] = {to_compute<O>(cast<O>(v.v[k]))};
-          run[k].push(xs);
+          run[k].template push<sizeof(O) == 2>(xs);
         }
       }
     }
@@ -727,7 +745,7 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
     for (int u = 0; u < UN; ++u) {
       Pack<O, VEC> o;
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v[u].v[k])), fin[k], p.log));
+      for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out<sizeof(O) == 2>(to_compute<O>(cast<O>(v[u].v[k])), fin[k], p.log));
       store_pack<O, VEC>(dst + (e + (int64_t)u * TY) * p.sa_out, o);
     }
   }
@@ -736,7 +754,7 @@ softmax_cols_tiled(const T* __restrict__ in, typename type_of_dtype<promote_ct(d
     load_pack<T, VEC>(v, src + e * p.sa_in);
     Pack<O, VEC> o;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out(to_compute<O>(cast<O>(v.v[k])), fin[k], p.log));
+    for (int k = 0; k < VEC; ++k) o.v[k] = from_compute<O>(sm_out<sizeof(O) == 2>(to_compute<O>(cast<O>(v.v[k])), fin[k], p.log));
     store_pack<O, VEC>(dst + e * p.sa_out, o);
   }
 }
@@ -763,6 +781,12 @@ inline bool band_tune_on() {
 inline bool band_disabled() {
   if (!band_tune_on()) return false;
   const char* e = getenv("HPTB_TUNE_NO_BAND");
+  return e && e[0] == '1';
+}
+
+inline bool sm_g128_off() {
+  if (!band_tune_on()) return false;
+  const char* e = getenv("HPTB_TUNE_SM_NO_G128");
   return e && e[0] == '1';
 }
 
@@ -809,6 +833,10 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
     const int64_t packs = (p.L + vec - 1) / vec;
     int G = 0;
     if (packs <= 32 * 4) G = 32;                       // short rows: a warp each, ≤ 4 packs per lane
+    // two rows per CTA, 4 packs per thread: one row's block reductions hide under the other's loads (f32 [16384,1536]
+    // 40.1 → 31.1 µs, [65536,768] 118 → 88 µs, [16384,2048] 43.8 → 41.1 µs); the 16-bit types, whose packs carry 8
+    // elements of arithmetic, prefer one row per CTA (bf16 [4096,4096] 14.3 vs 15.5 µs)
+    else if (vec > 1 && VECMAX <= 4 && packs <= 128 * 4 && !sm_g128_off()) G = 128;
     else if (packs <= (int64_t)kSmThreads * kSmChunks) G = kSmThreads;
     if (G) {
       p.G = G;
@@ -843,6 +871,7 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
   } while (0)
       if (vec > 1) {
         if (G == 32) HPTB_SM_LAUNCH(VECMAX, 32);
+        else if (G == 128) HPTB_SM_LAUNCH2(VECMAX, 128, 4);
         else HPTB_SM_LAUNCH(VECMAX, kSmThreads);
       } else {
         if (G == 32) HPTB_SM_LAUNCH(1, 32);

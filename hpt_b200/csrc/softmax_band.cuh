@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_band_rows(const T* __restr
     Pack<T, VEC> v = *slot;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      const C e = sm_exp_fast(to_compute<T>(v.v[k]) - mx);
+      const C e = sm_exp_o<T>(to_compute<T>(v.v[k]) - mx);
       sum += e;
       if constexpr (kInPlace) v.v[k] = e;
     }
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_band_rows(const T* __restr
         o.v[k] = from_compute<T>(to_compute<T>(v.v[k]) * inv);
       } else {
         const C sh = to_compute<T>(v.v[k]) - mx;
-        o.v[k] = from_compute<T>(p.log ? sh - lg : sm_exp_fast(sh) * inv);
+        o.v[k] = from_compute<T>(p.log ? sh - lg : sm_exp_o<T>(sh) * inv);
       }
     }
     store_pack<T, VEC>(dst + (int64_t)c * VEC, o);
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_band_cols(const T* __restr
       Pack<T, VEC> v = *slot;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        const C t = sm_exp_fast(to_compute<T>(v.v[k]) - mx[k]);
+        const C t = sm_exp_o<T>(to_compute<T>(v.v[k]) - mx[k]);
         sum[k] += t;
         if constexpr (kInPlace) v.v[k] = t;
       }
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kSmThreads) softmax_band_cols(const T* __restr
         o.v[k] = from_compute<T>(to_compute<T>(v.v[k]) * inv[k]);
       } else {
         const C sh = to_compute<T>(v.v[k]) - mx[k];
-        o.v[k] = from_compute<T>(p.log ? sh - lg[k] : sm_exp_fast(sh) * inv[k]);
+        o.v[k] = from_compute<T>(p.log ? sh - lg[k] : sm_exp_o<T>(sh) * inv[k]);
       }
     }
     store_pack<T, VEC>(dst + (int64_t)e * p.sa_out, o);
