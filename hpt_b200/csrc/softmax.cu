@@ -975,7 +975,13 @@ hptb_status launch_softmax(hptb_ctx* ctx, const Collapsed& c, const void* in_v, 
       constexpr int BW = 8 * VECMAX;
       const int64_t bctiles = (p.C + BW - 1) / BW;
       const int cl = vec == VECMAX && p.L >= 64 && !band_disabled() ? band_cluster(p.L * 128, outer_n * bctiles, ctx->sm_count, 8192) : 0;
-      if (cl > 0 && outer_n * bctiles * cl <= 0x7fffffffLL && std::llabs(p.sa_in) < (int64_t(1) << 40)) {
+      // Clusters of 8 that fill the GPU for only one to six rounds lose to the streaming kernels (their two cluster
+      // barriers and the quantised last round weigh most there): f32 [4096,8192] axis 0 — 4.6 rounds — 79 µs in bands,
+      // 76 µs streamed; bf16 61 vs 56 µs.  With many rounds ([64,4096,512] axis 1: 18 rounds, 268 vs 285 µs) or less
+      // than one wave the bands win.
+      const int64_t band_ctas = outer_n * bctiles * cl, band_wave = (int64_t)ctx->sm_count * 3;
+      const bool few_rounds = cl == kBandMaxCl && band_ctas >= band_wave && band_ctas < 6 * band_wave;
+      if (cl > 0 && !few_rounds && outer_n * bctiles * cl <= 0x7fffffffLL && std::llabs(p.sa_in) < (int64_t(1) << 40)) {
         BandParams q;
         memset(&q, 0, sizeof(q));
         q.kept = p.outer;
