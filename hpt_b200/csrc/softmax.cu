@@ -7,15 +7,19 @@
 // (hpt/src/backends/cpu/kernels/softmax.rs:204-310): y = exp(x − max) / Σ exp(x − max), computed in the
 // Intermediate type of FloatOutUnaryPromote<T> (f32 for f16/bf16/ints ≤ 32 bit, f64 for 64-bit types).
 //
-// Three kernels, picked after the collapse pass:
-//   softmax_rows_reg     axis has unit stride and the row fits in registers (≤ 8 packs per thread):
-//                        one warp (short rows) or one 256-thread CTA per row; ONE read and ONE write
-//                        of the row with 128-bit accesses (the reference's block variant stages the row
-//                        in shared memory and makes three passes over it).
-//   softmax_rows_stream  any axis stride / any length: one CTA per row, online (max, Σ) pass then a
-//                        write pass (two reads, one write).
-//   softmax_cols         axis is strided and another dim is contiguous: one thread per output column,
-//                        lanes along the contiguous dim (coalesced), online pass + write pass.
+// Kernels, picked after the collapse pass (launch_softmax):
+//   softmax_rows_reg[_loop]   axis has unit stride and the row fits in registers (≤ 8 packs per thread): one warp
+//                             (short rows), half a CTA (4-byte types, ≤ 512 packs) or one 256-thread CTA per row; ONE
+//                             read and ONE write of the row with 128-bit accesses (the reference's block variant
+//                             stages the row in shared memory and makes three passes over it); 8-pack rows persistent.
+//   softmax_band_rows / _cols (softmax_band.cuh) rows of up to 8 × 96 KB, 128-byte column bands of up to 6144 positions:
+//                             the band stays in the shared memory of a thread-block cluster — one read, exact maximum.
+//   softmax_rows_stream_vec   longer unit-stride rows: statistics sweep + apply sweep (power-of-two frame, SmRun); few
+//                             long rows (a 1-D softmax) are split into slabs over two launches.
+//   softmax_cols_tiled        strided axis, another dim contiguous: column tiles × axis splits, the same two sweeps.
+//   softmax_rows_stream, softmax_cols   scalar fallbacks (any strides, unaligned shapes, 64-bit compute type).
+// A unit-stride axis whose OUTPUT axis is strided (x.t().softmax(0) into a fresh tensor) goes through a scratch in the
+// input's order and the transposing copy (hptb_softmax below).
 #include <cooperative_groups.h>
 #include <array>
 
