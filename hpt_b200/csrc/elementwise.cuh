@@ -269,7 +269,8 @@ map_rows_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restric
 // The output is walked as ONE flat run in aligned 16-byte packs.  A pack's elements come from one input row, or from the
 // end of one and the start of the next, through element-sized L1-allocating loads: the VEC loads of a warp touch the
 // same sectors, so one of them goes to L2 and the rest hit L1.  One index computation and one 128-bit store per VEC
-// elements, where the scalar rows kernel pays both per element (f32 exp of a[5:8000, 3:8100]: 116 → 95 µs).
+// elements, where the scalar rows kernel pays both per element (f32 exp of a[5:8000, 3:8100]: 116 → 95 µs; 77 µs —
+// the copy roofline — with the one-row fast path below: ncu had the first version at 39 instructions per element).
 template <int NIN, int VEC, int UNROLL, typename F, typename O, typename A, typename B>
 __global__ void __launch_bounds__(kMapThreads)
 map_ragged_kernel(O* __restrict__ out, const A* __restrict__ a, const B* __restrict__ b, Rows32Params p, F f) {

@@ -258,7 +258,10 @@ hptb_status hptb_binary_reduce(hptb_ctx* ctx, int bin_op, int red_op, const hptb
 hptb_status hptb_mean_var(hptb_ctx* ctx, const hptb_tensor* in, const int32_t* axes, int naxes,
                           hptb_tensor* mean_out, hptb_tensor* var_out, void* stream);
 /* softmax / log_softmax along one axis (NormalizationOps, hpt-traits/src/ops/normalization.rs:51-64);
- * replaces `<T>_{softmax,logsoftmax}_{warp,block,block_large}` (hpt-cudakernels/src/normalization/softmax.cu). */
+ * replaces `<T>_{softmax,logsoftmax}_{warp,block,block_large}` (hpt-cudakernels/src/normalization/softmax.cu).
+ * Computed in f32 (f64 for 64-bit types) as exp(x - max) / sum; against an f64 evaluation the result is within
+ * 4 + |x - max| ulp of the output type when the lane fits registers or a cluster's shared memory, 6 + |x - max| ulp
+ * through the two-sweep kernels for longer lanes.  Any layout; axis < 0 counts from the end. */
 hptb_status hptb_softmax(hptb_ctx* ctx, const hptb_tensor* in, int axis, int log, hptb_tensor* out, void* stream);
 /* NormalizationOps::layernorm over the LAST n_normalized_dims dims (hpt-traits/src/ops/normalization.rs:12-38;
  * hpt/src/backends/cuda/tensor_internal/layernorm.rs:47-…, kernels layernorm.cu + layernorm_post.cu):
