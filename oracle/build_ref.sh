@@ -14,7 +14,8 @@
 #                                                            `typename` as a template argument (accepted by MSVC, the
 #                                                            reference's CI compiler; -std=c++20 relaxes the alias
 #                                                            declarations at :55 but not these)
-#   binary/{add,sub,mul,rem}.cu (the NormalBinOps, §8 a1)   and binary/{div,bitand,bitor,bitxor,shl,shr}.cu (§8 f1 riders)
+#   binary/{add,sub,mul,rem}.cu (the NormalBinOps, §8 a1)   and binary/{div,bitand,bitor,bitxor,shl,shr,cmp}.cu (§8 f1 riders; cmp.cu alone
+#                                                            is 6 × 169 × 6 kernels)
 #                                                            compile once the TOOLCHAIN supplies what the sources assume:
 #                                                            utils/type_cast.cuh uses __half / __nv_bfloat16 without
 #                                                            including their headers → `-include cuda_fp16.h -include
@@ -46,7 +47,7 @@ for f in reduce/argmax reduce/argmin strided_copy; do
   fi
 done
 pids=""
-for n in add sub mul rem div bitand bitor bitxor shl shr; do
+for n in add sub mul rem div bitand bitor bitxor shl shr cmp; do
   if [ ! -f "$OUT/binary_$n.cubin" ] || [ "src/binary/$n.cu" -nt "$OUT/binary_$n.cubin" ]; then
     ( TMPDIR=${TMPDIR:-/tmp} $NVCC -std=c++20 -cubin -O3 -arch=sm_100a --extended-lambda --diag-suppress=20054 \
         -include cuda_fp16.h -include cuda_bf16.h -Isrc/cutlass "src/binary/$n.cu" -o "$OUT/binary_$n.cubin.tmp" \

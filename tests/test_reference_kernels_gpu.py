@@ -189,3 +189,39 @@ def test_rider_binary_ops_three_ways(hb, rmods, op):
                 assert_exact(ours, ref, od, f"library vs reference kernel: {name}")
             checked += 1
     assert checked >= (60 if op != "div" else 120)
+
+
+@pytest.fixture(scope="module")
+def cmod():
+    if not R.available_binary(("cmp",)):
+        pytest.skip("oracle/_ref/binary_cmp.cubin not built (run oracle/build_ref.sh where /root/reference exists)")
+    return R.RefModule("binary_cmp")
+
+
+@pytest.mark.parametrize("op", list(O.CMP_OPS))
+def test_compare_three_ways(hb, cmod, op):
+    """TensorCmp (§8 f1) through the reference's <op>_<L>_<R>_contiguous: compare in NormalOutPromote<L, R>, bool out —
+    every dtype pair, with equal pairs and NaNs planted"""
+    rng = np.random.default_rng(63)
+    api = {"eq": "tensor_eq", "ne": "tensor_neq", "lt": "tensor_lt", "le": "tensor_le", "gt": "tensor_gt", "ge": "tensor_ge"}[op]
+    n, checked = 3000, 0
+    for xd in DTYPES:
+        for yd in DTYPES:
+            name = f"{op}_{xd}_{yd}_contiguous"
+            if not cmod.has(name):
+                continue
+            x = rand(rng, (n,), xd, -3, 3) if xd in O.INTS else rand(rng, (n,), xd)
+            y = rand(rng, (n,), yd, -3, 3) if yd in O.INTS else rand(rng, (n,), yd)
+            if xd in O.FLOATS and yd in O.FLOATS:
+                y[::3] = O.cast(x[::3], xd, yd)
+            if xd in O.FLOATS:
+                x[5] = np.nan
+            want, _ = O.compare(op, x, xd, y, yd)
+            out = torch.empty(n, dtype=torch.bool, device="cuda")
+            R.ref_binary_contiguous(cmod, op, xd, yd, to_torch(x, xd).cuda(), to_torch(y, yd).cuda(), out)
+            ref = out.cpu().numpy()
+            ours = to_numpy(getattr(hb.Tensor.to_cuda(to_torch(x, xd)), api)(hb.Tensor.to_cuda(to_torch(y, yd))).to_cpu(), "bool")
+            assert_exact(ref, want, "bool", f"oracle vs reference kernel: {name}")
+            assert_exact(ours, ref, "bool", f"library vs reference kernel: {name}")
+            checked += 1
+    assert checked >= 150
