@@ -1,9 +1,11 @@
 """Three-way parity against the REFERENCE's own device code: Hpt's CUDA kernels (oracle/_ref/*.cubin, compiled by
 oracle/build_ref.sh from the reference sources), the oracle (oracle/hpt_oracle.py) and this library, on the same
-inputs — all bit-exact (indices, copies, and the four NormalBinOps over all 13 × 13 dtype pairs).  Sizes stay below the
-reference kernels' ~9.7 M-element limit.  argmax / argmin / strided_copy and binary add / sub / mul /
-rem compile with this image's toolchain (build_ref.sh says why the rest does not); for them this upgrades "pinned to the
-reference's test oracle" to "pinned to the reference's own output"."""
+inputs — all bit-exact (indices, copies, the four NormalBinOps, div, the bit ops and the six comparisons over every dtype
+pair the reference defines; f16 / bf16 div to 1 ulp against the reference's __hdiv).  Sizes stay below the reference
+kernels' ~9.7 M-element limit.  argmax / argmin / strided_copy and the binary / compare files compile
+with this image's toolchain (build_ref.sh says why the reduce, unary and softmax files do not); for them this upgrades
+"pinned to the reference's test oracle" to "pinned to the reference's own output".  Where the reference's device code and
+its CPU code disagree (shift counts ≥ the bit width, bool >> bool) the tests say so and hold this library to the CPU."""
 import numpy as np
 import pytest
 import torch
